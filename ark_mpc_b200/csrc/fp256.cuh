@@ -1,0 +1,329 @@
+// 256-bit prime-field arithmetic for sm_100a, one field element per thread.
+//
+// Representation contract (what the reference keeps in memory): canonical Montgomery residues
+// a*2^256 mod p in 4 little-endian u64 limbs == 8 little-endian u32 limbs
+// (ark-ff 0.4 Fp256<MontBackend<_,4>> behind Scalar<C>, /root/reference/online-phase/src/algebra/scalar/scalar.rs:46).
+//
+// The multiplier is a carry-chain CIOS Montgomery product on 32-bit limbs. Every
+// (mad.lo.cc, madc.hi.cc) pair below is fused by ptxas into ONE IMAD.WIDE.U32[.X]
+// (verified with cuobjdump), so an 8x8-limb row costs 8 wide multiply-adds. Products whose
+// low word lands on an even limb position accumulate in E, odd positions in O
+// (value = E + O*2^32); a 32-bit right shift then just swaps the roles of the two arrays,
+// which keeps every 64-bit accumulator pair register-aligned with no moves.
+//
+// `mont_mul2` accumulates TWO products a*x + b*y and reduces ONCE. The Beaver recombination
+// needs 6 field multiplications in the reference's unfused form; with lazy accumulation it is
+// 5 products and 3 reductions (see beaver.cuh).
+//
+// This header is dual-target: under nvcc the carry primitives are inline PTX; under a plain
+// host compiler they are emulated with an explicit carry flag so that the exact instruction
+// sequence can be verified bit-for-bit on a CPU-only box (tests/test_host_emu.py).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ARK_D __device__ __forceinline__
+#define ARK_DM __device__ __forceinline__
+#define ARK_HDM __host__ __device__ __forceinline__
+#define ARK_UNROLL _Pragma("unroll")
+#else
+#define ARK_D static inline __attribute__((always_inline))
+#define ARK_DM inline __attribute__((always_inline))
+#define ARK_HDM inline __attribute__((always_inline))
+#define ARK_UNROLL
+#endif
+
+namespace ark {
+
+// ----------------------------------------------------------------------------------------------
+// Carry-flag primitives
+// ----------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+ARK_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ARK_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ARK_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ARK_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ARK_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ARK_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ARK_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ARK_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ARK_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ARK_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+#define ARK_EMU_EXPECT_NO_CARRY() do { } while (0)
+#else
+namespace emu { static thread_local uint32_t CF = 0; static thread_local uint64_t violations = 0; }
+#define ARK_EMU_EXPECT_NO_CARRY() do { if (::ark::emu::CF) ::ark::emu::violations++; } while (0)
+ARK_D uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; emu::CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+ARK_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + emu::CF; emu::CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+ARK_D uint32_t addc(uint32_t a, uint32_t b) { return a + b + emu::CF; }
+ARK_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; emu::CF = (uint32_t)(t >> 63); return (uint32_t)t; }
+ARK_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - emu::CF; emu::CF = (uint32_t)(t >> 63); return (uint32_t)t; }
+ARK_D uint32_t subc(uint32_t a, uint32_t b) { return a - b - emu::CF; }
+ARK_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)((uint64_t)a * b) + c; emu::CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+ARK_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)((uint64_t)a * b) + c + emu::CF; emu::CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+ARK_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + emu::CF; emu::CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+ARK_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+#endif
+
+// ----------------------------------------------------------------------------------------------
+// Field parameter packs (32-bit LE limbs).  kLazy2: 4p < 2^256 (p < 2^254), which the two-product
+// accumulation and the lazy (unreduced) operand sums in beaver.cuh rely on: a sum of two products of a
+// canonical value with a value < 3p reduces to < (4p/R + 1) p < 2p, so ONE conditional subtraction
+// yields the canonical result.
+// ----------------------------------------------------------------------------------------------
+struct Bn254Fr {
+  static constexpr int kId = 0;
+  static constexpr bool kLazy2 = true;
+  static constexpr uint32_t P0 = 0xf0000001u, P1 = 0x43e1f593u, P2 = 0x79b97091u, P3 = 0x2833e848u,
+                            P4 = 0x8181585du, P5 = 0xb85045b6u, P6 = 0xe131a029u, P7 = 0x30644e72u;
+  static constexpr uint32_t INV = 0xefffffffu;  // -p^-1 mod 2^32
+  // R mod p and R^2 mod p (Montgomery one / conversion constant)
+  static constexpr uint32_t R_0 = 0x4ffffffbu, R_1 = 0xac96341cu, R_2 = 0x9f60cd29u, R_3 = 0x36fc7695u, R_4 = 0x7879462eu, R_5 = 0x666ea36fu, R_6 = 0x9a07df2fu, R_7 = 0x0e0a77c1u;
+  static constexpr uint32_t R2_0 = 0xae216da7u, R2_1 = 0x1bb8e645u, R2_2 = 0xe35c59e3u, R2_3 = 0x53fe3ab1u, R2_4 = 0x53bb8085u, R2_5 = 0x8c49833du, R2_6 = 0x7f4e44a5u, R2_7 = 0x0216d0b1u;
+  static constexpr int kBits = 254;
+};
+struct Curve25519Fr {
+  static constexpr int kId = 1;
+  static constexpr bool kLazy2 = true;
+  static constexpr uint32_t P0 = 0x5cf5d3edu, P1 = 0x5812631au, P2 = 0xa2f79cd6u, P3 = 0x14def9deu,
+                            P4 = 0u, P5 = 0u, P6 = 0u, P7 = 0x10000000u;
+  static constexpr uint32_t INV = 0x12547e1bu;
+  static constexpr uint32_t R_0 = 0x8d98951du, R_1 = 0xd6ec3174u, R_2 = 0x737dcf70u, R_3 = 0xc6ef5bf4u, R_4 = 0xfffffffeu, R_5 = 0xffffffffu, R_6 = 0xffffffffu, R_7 = 0x0fffffffu;
+  static constexpr uint32_t R2_0 = 0x449c0f01u, R2_1 = 0xa40611e3u, R2_2 = 0x68859347u, R2_3 = 0xd00e1ba7u, R2_4 = 0x17f5be65u, R2_5 = 0xceec73d2u, R2_6 = 0x7c309a3du, R2_7 = 0x0399411bu;
+  static constexpr int kBits = 253;
+};
+struct Bn254Fq {
+  static constexpr int kId = 2;
+  static constexpr bool kLazy2 = true;
+  static constexpr uint32_t P0 = 0xd87cfd47u, P1 = 0x3c208c16u, P2 = 0x6871ca8du, P3 = 0x97816a91u,
+                            P4 = 0x8181585du, P5 = 0xb85045b6u, P6 = 0xe131a029u, P7 = 0x30644e72u;
+  static constexpr uint32_t INV = 0xe4866389u;
+  static constexpr uint32_t R_0 = 0xc58f0d9du, R_1 = 0xd35d438du, R_2 = 0xf5c70b3du, R_3 = 0x0a78eb28u, R_4 = 0x7879462cu, R_5 = 0x666ea36fu, R_6 = 0x9a07df2fu, R_7 = 0x0e0a77c1u;
+  static constexpr uint32_t R2_0 = 0x538afa89u, R2_1 = 0xf32cfc5bu, R2_2 = 0xd44501fbu, R2_3 = 0xb5e71911u, R2_4 = 0x0a417ff6u, R2_5 = 0x47ab1effu, R2_6 = 0xcab8351fu, R2_7 = 0x06d89f71u;
+  static constexpr int kBits = 254;
+};
+struct Curve25519Fq {
+  static constexpr int kId = 3;
+  static constexpr bool kLazy2 = false;  // 2^255 - 19: 4p does not fit 256 bits
+  static constexpr uint32_t P0 = 0xffffffedu, P1 = 0xffffffffu, P2 = 0xffffffffu, P3 = 0xffffffffu,
+                            P4 = 0xffffffffu, P5 = 0xffffffffu, P6 = 0xffffffffu, P7 = 0x7fffffffu;
+  static constexpr uint32_t INV = 0x286bca1bu;
+  static constexpr uint32_t R_0 = 0x26u, R_1 = 0, R_2 = 0, R_3 = 0, R_4 = 0, R_5 = 0, R_6 = 0, R_7 = 0;
+  static constexpr uint32_t R2_0 = 0x5a4u, R2_1 = 0, R2_2 = 0, R2_3 = 0, R2_4 = 0, R2_5 = 0, R2_6 = 0, R2_7 = 0;
+  static constexpr int kBits = 255;
+};
+
+
+// A field element in registers: 8 x u32, little endian.
+struct fe8 { uint32_t v[8]; };
+
+// ----------------------------------------------------------------------------------------------
+// Multiply-accumulate rows.  acc[0..7] += {a[0],a[2],a[4],a[6]} * w  (lo parts on even slots,
+// hi parts on odd slots => 4 fused IMAD.WIDE.U32.X), returns with the chain's carry-out pending
+// in the flag; the caller decides where it goes.
+// ----------------------------------------------------------------------------------------------
+template <bool CARRY_IN>
+ARK_D void mad_row4(uint32_t* acc, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t w) {
+  acc[0] = CARRY_IN ? madc_lo_cc(a0, w, acc[0]) : mad_lo_cc(a0, w, acc[0]);
+  acc[1] = madc_hi_cc(a0, w, acc[1]);
+  acc[2] = madc_lo_cc(a2, w, acc[2]);
+  acc[3] = madc_hi_cc(a2, w, acc[3]);
+  acc[4] = madc_lo_cc(a4, w, acc[4]);
+  acc[5] = madc_hi_cc(a4, w, acc[5]);
+  acc[6] = madc_lo_cc(a6, w, acc[6]);
+  acc[7] = madc_hi_cc(a6, w, acc[7]);
+}
+
+// Same, for a compile-time modulus limb quadruple: zero limbs cost an add-with-carry, not a multiply
+// (Curve25519 Fr has three zero limbs).
+template <uint32_t PJ>
+ARK_D void mad_plimb(uint32_t& lo, uint32_t& hi, uint32_t m, bool first) {
+  if (PJ == 0u) {
+    lo = first ? add_cc(lo, 0u) : addc_cc(lo, 0u);
+    hi = addc_cc(hi, 0u);
+  } else {
+    lo = first ? mad_lo_cc(PJ, m, lo) : madc_lo_cc(PJ, m, lo);
+    hi = madc_hi_cc(PJ, m, hi);
+  }
+}
+
+// Accumulator: value = sum E[j] 2^(32j) + 2^32 * sum O[j] 2^(32j).  Invariant:
+// the value stays < 2^288 inside an iteration and < 2^256 after each shift, hence E has 9 words,
+// O has 8 and O never carries out.
+struct MontAcc {
+  uint32_t E[9];
+  uint32_t O[8];
+  uint32_t fold;  // word of weight 2^0 left over by the previous shift, not yet added into E[0]
+};
+
+ARK_D void acc_zero(MontAcc& t) {
+  ARK_UNROLL for (int j = 0; j < 9; j++) t.E[j] = 0;
+  ARK_UNROLL for (int j = 0; j < 8; j++) t.O[j] = 0;
+  t.fold = 0;
+}
+
+// t += a * w, first row after a shift (adds the folded word; its carry has weight 2^32 == O[0])
+ARK_D void acc_row_first(MontAcc& t, const uint32_t* a, uint32_t w) {
+  t.E[0] = add_cc(t.E[0], t.fold);
+  mad_row4<true>(t.O, a[1], a[3], a[5], a[7], w);
+  ARK_EMU_EXPECT_NO_CARRY();
+  mad_row4<false>(t.E, a[0], a[2], a[4], a[6], w);
+  t.E[8] = addc(t.E[8], 0u);
+}
+ARK_D void acc_row(MontAcc& t, const uint32_t* a, uint32_t w) {
+  mad_row4<false>(t.O, a[1], a[3], a[5], a[7], w);
+  ARK_EMU_EXPECT_NO_CARRY();
+  mad_row4<false>(t.E, a[0], a[2], a[4], a[6], w);
+  t.E[8] = addc(t.E[8], 0u);
+}
+
+// One Montgomery step: t = (t + m*p) / 2^32 with m chosen so the low word cancels.
+template <class F>
+ARK_D void acc_reduce_shift(MontAcc& t) {
+  const uint32_t m = mul_lo(t.E[0], F::INV);
+  mad_plimb<F::P1>(t.O[0], t.O[1], m, true);
+  mad_plimb<F::P3>(t.O[2], t.O[3], m, false);
+  mad_plimb<F::P5>(t.O[4], t.O[5], m, false);
+  mad_plimb<F::P7>(t.O[6], t.O[7], m, false);
+  ARK_EMU_EXPECT_NO_CARRY();
+  mad_plimb<F::P0>(t.E[0], t.E[1], m, true);
+  mad_plimb<F::P2>(t.E[2], t.E[3], m, false);
+  mad_plimb<F::P4>(t.E[4], t.E[5], m, false);
+  mad_plimb<F::P6>(t.E[6], t.E[7], m, false);
+  t.E[8] = addc(t.E[8], 0u);
+  // E[0] is now 0.  Divide by 2^32: O becomes the even array, E[2..8] the odd one, E[1] is folded later.
+  const uint32_t fold = t.E[1];
+  uint32_t nO[8];
+  ARK_UNROLL for (int j = 0; j < 7; j++) nO[j] = t.E[j + 2];
+  nO[7] = 0;
+  ARK_UNROLL for (int j = 0; j < 8; j++) t.E[j] = t.O[j];
+  t.E[8] = 0;
+  ARK_UNROLL for (int j = 0; j < 8; j++) t.O[j] = nO[j];
+  t.fold = fold;
+}
+
+// r = E + fold + (O << 32); the caller guarantees the value is < 2^256.
+ARK_D void acc_collapse(fe8& r, const MontAcc& t) {
+  r.v[0] = add_cc(t.E[0], t.fold);
+  ARK_UNROLL for (int j = 1; j < 8; j++) r.v[j] = addc_cc(t.E[j], t.O[j - 1]);
+  ARK_EMU_EXPECT_NO_CARRY();
+}
+
+// ----------------------------------------------------------------------------------------------
+// Field operations
+// ----------------------------------------------------------------------------------------------
+template <class F>
+struct Fp {
+  ARK_DM static void load_p(uint32_t* p) {
+    p[0] = F::P0; p[1] = F::P1; p[2] = F::P2; p[3] = F::P3; p[4] = F::P4; p[5] = F::P5; p[6] = F::P6; p[7] = F::P7;
+  }
+
+  // r = a - p if a >= p else a.  (one conditional subtraction; a < 2p on entry gives canonical output)
+  ARK_DM static void csub_p(fe8& a) {
+    uint32_t p[8];
+    load_p(p);
+    uint32_t t[8];
+    t[0] = sub_cc(a.v[0], p[0]);
+    ARK_UNROLL for (int j = 1; j < 8; j++) t[j] = subc_cc(a.v[j], p[j]);
+    const uint32_t borrow = subc(0u, 0u);  // 0xffffffff if a < p
+    ARK_UNROLL for (int j = 0; j < 8; j++) a.v[j] = borrow ? a.v[j] : t[j];
+  }
+
+  // plain 256-bit add, no reduction (caller guarantees no overflow)
+  ARK_DM static void add_raw(fe8& r, const fe8& a, const fe8& b) {
+    r.v[0] = add_cc(a.v[0], b.v[0]);
+    ARK_UNROLL for (int j = 1; j < 7; j++) r.v[j] = addc_cc(a.v[j], b.v[j]);
+    r.v[7] = addc(a.v[7], b.v[7]);
+  }
+
+  // canonical add: inputs canonical, output canonical (ark-ff add_assign semantics)
+  ARK_DM static void add(fe8& r, const fe8& a, const fe8& b) {
+    if (F::kBits <= 255) {
+      add_raw(r, a, b);  // a + b < 2p < 2^256
+      csub_p(r);
+    }
+  }
+
+  // canonical sub: r = a - b mod p
+  ARK_DM static void sub(fe8& r, const fe8& a, const fe8& b) {
+    uint32_t p[8];
+    load_p(p);
+    r.v[0] = sub_cc(a.v[0], b.v[0]);
+    ARK_UNROLL for (int j = 1; j < 8; j++) r.v[j] = subc_cc(a.v[j], b.v[j]);
+    const uint32_t borrow = subc(0u, 0u);  // all ones if a < b
+    r.v[0] = add_cc(r.v[0], p[0] & borrow);
+    ARK_UNROLL for (int j = 1; j < 7; j++) r.v[j] = addc_cc(r.v[j], p[j] & borrow);
+    r.v[7] = addc(r.v[7], p[7] & borrow);
+  }
+
+  // canonical negation, neg(0) = 0 (ark-ff neg semantics)
+  ARK_DM static void neg(fe8& r, const fe8& a) {
+    uint32_t p[8];
+    load_p(p);
+    uint32_t nz = 0;
+    ARK_UNROLL for (int j = 0; j < 8; j++) nz |= a.v[j];
+    const uint32_t mask = nz ? 0xffffffffu : 0u;
+    r.v[0] = sub_cc(p[0] & mask, a.v[0]);
+    ARK_UNROLL for (int j = 1; j < 7; j++) r.v[j] = subc_cc(p[j] & mask, a.v[j]);
+    r.v[7] = subc(p[7] & mask, a.v[7]);
+  }
+
+  // Lazy Montgomery product: r = a*x/R mod p, with r < a*x/R + p (NOT canonical).
+  // Needs a < 2^256 arbitrary limbs, x arbitrary; bound of the running value: 2^32 (a + p) < 2^288.
+  ARK_DM static void mul_lazy(fe8& r, const fe8& a, const fe8& x) {
+    MontAcc t;
+    acc_zero(t);
+    ARK_UNROLL for (int i = 0; i < 8; i++) {
+      if (i == 0) acc_row(t, a.v, x.v[0]); else acc_row_first(t, a.v, x.v[i]);
+      acc_reduce_shift<F>(t);
+    }
+    acc_collapse(r, t);
+  }
+
+  // canonical product of canonical inputs
+  ARK_DM static void mul(fe8& r, const fe8& a, const fe8& x) {
+    mul_lazy(r, a, x);  // < p*p/R + p < 2p
+    csub_p(r);
+  }
+
+  // Lazy two-product accumulation: r = (a*x + b*y)/R mod p, r < (a*x + b*y)/R + p.
+  // Requires a + b + p < 2^256 (running value < 2^32 (a+b+p) < 2^288): a, b canonical and kLazy2.
+  ARK_DM static void mul2_lazy(fe8& r, const fe8& a, const fe8& x, const fe8& b, const fe8& y) {
+    MontAcc t;
+    acc_zero(t);
+    ARK_UNROLL for (int i = 0; i < 8; i++) {
+      if (i == 0) acc_row(t, a.v, x.v[0]); else acc_row_first(t, a.v, x.v[i]);
+      acc_row(t, b.v, y.v[i]);
+      acc_reduce_shift<F>(t);
+    }
+    acc_collapse(r, t);
+  }
+
+  ARK_DM static bool is_zero(const fe8& a) {
+    uint32_t nz = 0;
+    ARK_UNROLL for (int j = 0; j < 8; j++) nz |= a.v[j];
+    return nz == 0;
+  }
+  ARK_DM static bool eq(const fe8& a, const fe8& b) {
+    uint32_t d = 0;
+    ARK_UNROLL for (int j = 0; j < 8; j++) d |= a.v[j] ^ b.v[j];
+    return d == 0;
+  }
+  // a < p ?
+  ARK_DM static bool is_canonical(const fe8& a) {
+    uint32_t p[8];
+    load_p(p);
+    (void)sub_cc(a.v[0], p[0]);
+    ARK_UNROLL for (int j = 1; j < 8; j++) (void)subc_cc(a.v[j], p[j]);
+    return subc(0u, 0u) != 0u;
+  }
+  ARK_HDM static void set_one(fe8& r) {
+    r.v[0] = F::R_0; r.v[1] = F::R_1; r.v[2] = F::R_2; r.v[3] = F::R_3; r.v[4] = F::R_4; r.v[5] = F::R_5; r.v[6] = F::R_6; r.v[7] = F::R_7;
+  }
+  ARK_HDM static void set_r2(fe8& r) {
+    r.v[0] = F::R2_0; r.v[1] = F::R2_1; r.v[2] = F::R2_2; r.v[3] = F::R2_3; r.v[4] = F::R2_4; r.v[5] = F::R2_5; r.v[6] = F::R2_6; r.v[7] = F::R2_7;
+  }
+  ARK_HDM static void set_zero(fe8& r) { ARK_UNROLL for (int j = 0; j < 8; j++) r.v[j] = 0; }
+};
+
+}  // namespace ark

@@ -1,0 +1,329 @@
+// Kernel skeletons for the scalar-field gates: one gate per thread, 256-bit global loads/stores
+// (LDG.E.256 / STG.E.256 on sm_100a: a warp moves 1024 contiguous bytes per instruction on a
+// planar vector), persistent grid-stride loops sized from the SM count.
+//
+// Every operand is (pointer, byte stride): planar vectors use stride 32, the reference's AoS
+// ScalarShare image {share, mac} (share.rs:32-37) uses stride 64 with the mac plane at +32 bytes, so the
+// same kernels serve device-resident planes and AoS chunks staged from host buffers.
+#pragma once
+#include <cuda_runtime.h>
+#include "beaver.cuh"
+
+namespace ark {
+
+// A strided view of a vector of 32-byte field elements in global memory.
+struct Vec {
+  const char* p;
+  uint32_t stride;  // bytes between consecutive elements (32 planar, 64 AoS)
+};
+struct MVec {
+  char* p;
+  uint32_t stride;
+};
+
+__device__ __forceinline__ void ld_fe(fe8& r, const Vec& v, size_t i) {
+  const char* a = v.p + i * (size_t)v.stride;
+  asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(a)
+               : "memory");
+}
+__device__ __forceinline__ void st_fe(const MVec& v, size_t i, const fe8& r) {
+  char* a = v.p + i * (size_t)v.stride;
+  asm volatile("st.global.L1::no_allocate.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+               :
+               : "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]), "l"(a)
+               : "memory");
+}
+
+constexpr int kBlock = 256;
+
+// ---------------------------------------------------------------------------------------------
+// Beaver phase 1: d_mine = x - a, e_mine = y - b on the share components.   192 B / gate.
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(kBlock) beaver_mask_kernel(size_t n, Vec x, Vec y, Vec a, Vec b, MVec d, MVec e) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 xs, ys, as, bs, dm, em;
+    ld_fe(xs, x, i);
+    ld_fe(ys, y, i);
+    ld_fe(as, a, i);
+    ld_fe(bs, b, i);
+    beaver_mask_elem<F>(dm, em, xs, ys, as, bs);
+    st_fe(d, i, dm);
+    st_fe(e, i, em);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Beaver phase 2 (fused open-add + recombine + MAC update).   384 B / gate (+64 B with OPEN).
+// ---------------------------------------------------------------------------------------------
+struct RecombineArgs {
+  Vec d_mine, e_mine, d_peer, e_peer;
+  Vec a_s, a_m, b_s, b_m, c_s, c_m;
+  MVec out_s, out_m, d_open, e_open;
+  fe8 key;
+};
+
+template <class F, int PARTY, bool OPEN>
+__global__ void __launch_bounds__(kBlock, 2) beaver_recombine_kernel(size_t n, const __grid_constant__ RecombineArgs g) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 dm, em, dp, ep, as, am, bs, bm, cs, cm;
+    ld_fe(dm, g.d_mine, i);
+    ld_fe(dp, g.d_peer, i);
+    ld_fe(em, g.e_mine, i);
+    ld_fe(ep, g.e_peer, i);
+    ld_fe(bs, g.b_s, i);
+    ld_fe(as, g.a_s, i);
+    ld_fe(bm, g.b_m, i);
+    ld_fe(am, g.a_m, i);
+    ld_fe(cs, g.c_s, i);
+    ld_fe(cm, g.c_m, i);
+    fe8 os, om, d, e;
+    beaver_recombine_elem<F>(os, om, d, e, PARTY, g.key, dm, em, dp, ep, as, am, bs, bm, cs, cm);
+    st_fe(g.out_s, i, os);
+    st_fe(g.out_m, i, om);
+    if (OPEN) {
+      st_fe(g.d_open, i, d);
+      st_fe(g.e_open, i, e);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic element-wise gates
+// ---------------------------------------------------------------------------------------------
+enum class Bin { Add, Sub, Mul };
+
+template <class F, Bin OP>
+__global__ void __launch_bounds__(kBlock) fr_binary_kernel(size_t n, Vec a, Vec b, MVec out) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 x, y, r;
+    ld_fe(x, a, i);
+    ld_fe(y, b, i);
+    if (OP == Bin::Add) Fp<F>::add(r, x, y);
+    if (OP == Bin::Sub) Fp<F>::sub(r, x, y);
+    if (OP == Bin::Mul) Fp<F>::mul(r, x, y);
+    st_fe(out, i, r);
+  }
+}
+
+// two planes at once: (a_s op b_s, a_m op b_m) -- share add / sub
+template <class F, Bin OP>
+__global__ void __launch_bounds__(kBlock) fr_share_binary_kernel(size_t n, Vec a_s, Vec a_m, Vec b_s, Vec b_m, MVec out_s, MVec out_m) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 x, y, r;
+    ld_fe(x, a_s, i);
+    ld_fe(y, b_s, i);
+    if (OP == Bin::Add) Fp<F>::add(r, x, y); else Fp<F>::sub(r, x, y);
+    st_fe(out_s, i, r);
+    ld_fe(x, a_m, i);
+    ld_fe(y, b_m, i);
+    if (OP == Bin::Add) Fp<F>::add(r, x, y); else Fp<F>::sub(r, x, y);
+    st_fe(out_m, i, r);
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_neg_kernel(size_t n, Vec a, MVec out) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 x, r;
+    ld_fe(x, a, i);
+    Fp<F>::neg(r, x);
+    st_fe(out, i, r);
+  }
+}
+
+// out = a * s for one broadcast scalar s (also to_mont with s = R^2, from_mont with s = 1)
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_scale_kernel(size_t n, Vec a, fe8 s, MVec out) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 x, r;
+    ld_fe(x, a, i);
+    Fp<F>::mul(r, x, s);
+    st_fe(out, i, r);
+  }
+}
+
+// (share*v, mac*v)
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_share_mul_public_kernel(size_t n, Vec a_s, Vec a_m, Vec v, MVec out_s, MVec out_m) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 s, m, w, r;
+    ld_fe(w, v, i);
+    ld_fe(s, a_s, i);
+    Fp<F>::mul(r, s, w);
+    st_fe(out_s, i, r);
+    ld_fe(m, a_m, i);
+    Fp<F>::mul(r, m, w);
+    st_fe(out_m, i, r);
+  }
+}
+
+template <class F, int PARTY, bool SUB>
+__global__ void __launch_bounds__(kBlock) fr_share_add_public_kernel(size_t n, Vec a_s, Vec a_m, Vec v, fe8 key, MVec out_s, MVec out_m) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 s, m, w, os, om;
+    ld_fe(s, a_s, i);
+    ld_fe(m, a_m, i);
+    ld_fe(w, v, i);
+    if (SUB) share_sub_public_elem<F>(os, om, PARTY, key, s, m, w); else share_add_public_elem<F>(os, om, PARTY, key, s, m, w);
+    st_fe(out_s, i, os);
+    st_fe(out_m, i, om);
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_mac_check_kernel(size_t n, Vec opened, Vec mac, fe8 key, MVec out) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 o, m, r;
+    ld_fe(o, opened, i);
+    ld_fe(m, mac, i);
+    mac_check_elem<F>(r, key, o, m);
+    st_fe(out, i, r);
+  }
+}
+
+// flag (initialised to 1 by the host) is cleared if any mine[i] + peer[i] != 0
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_sum_is_zero_kernel(size_t n, Vec mine, Vec peer, int* flag) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  bool ok = true;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 x, y, r;
+    ld_fe(x, mine, i);
+    ld_fe(y, peer, i);
+    Fp<F>::add(r, x, y);
+    ok = ok && Fp<F>::is_zero(r);
+  }
+  if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(flag, 0);
+}
+
+// canonical integer value as 32 big-endian bytes (scalar.rs:118-127)
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_to_bytes_be_kernel(size_t n, Vec a, MVec out) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  fe8 one;
+  Fp<F>::set_zero(one);
+  one.v[0] = 1;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 x, r, o;
+    ld_fe(x, a, i);
+    Fp<F>::mul(r, x, one);  // out of Montgomery form
+    for (int j = 0; j < 8; j++) o.v[j] = __byte_perm(r.v[7 - j], 0, 0x0123);
+    st_fe(out, i, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sum (share.rs:104-111): thread-serial over a grid-stride slice, then warp-shuffle tree, then
+// one partial per block; a second single-block launch folds the partials.
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void warp_sum(fe8& acc) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    fe8 o, r;
+#pragma unroll
+    for (int j = 0; j < 8; j++) o.v[j] = __shfl_down_sync(0xffffffffu, acc.v[j], off);
+    Fp<F>::add(r, acc, o);
+    acc = r;
+  }
+}
+
+template <class F>
+__device__ __forceinline__ void block_sum_store(fe8 acc, fe8* smem /*[8]*/, MVec out, size_t out_index) {
+  warp_sum<F>(acc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) smem[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    fe8 v;
+    if (lane < kBlock / 32) v = smem[lane]; else Fp<F>::set_zero(v);
+    warp_sum<F>(v);
+    if (lane == 0) st_fe(out, out_index, v);
+  }
+  __syncthreads();
+}
+
+// NPLANES planes summed independently in one pass (2 for share+mac)
+template <class F, int NPLANES>
+__global__ void __launch_bounds__(kBlock) fr_sum_kernel(size_t n, Vec a0, Vec a1, MVec out0, MVec out1, bool per_block) {
+  __shared__ fe8 smem[kBlock / 32];
+  const size_t step = (size_t)gridDim.x * kBlock;
+  fe8 acc0, acc1;
+  Fp<F>::set_zero(acc0);
+  Fp<F>::set_zero(acc1);
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 x, r;
+    ld_fe(x, a0, i);
+    Fp<F>::add(r, acc0, x);
+    acc0 = r;
+    if (NPLANES == 2) {
+      ld_fe(x, a1, i);
+      Fp<F>::add(r, acc1, x);
+      acc1 = r;
+    }
+  }
+  const size_t oi = per_block ? blockIdx.x : 0;
+  block_sum_store<F>(acc0, smem, out0, oi);
+  if (NPLANES == 2) block_sum_store<F>(acc1, smem, out1, oi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layout conversion and synthetic data
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) copy_planes_kernel(size_t n, Vec in_s, Vec in_m, MVec out_s, MVec out_m) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 s, m;
+    ld_fe(s, in_s, i);
+    ld_fe(m, in_m, i);
+    st_fe(out_s, i, s);
+    st_fe(out_m, i, m);
+  }
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// Uniform element of [0,p) from (seed, index), rejection-sampled; bit-identical to
+// oracle/pyoracle.synth_element and oracle/ark_oracle.c:synth_one.
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_random_kernel(size_t n, uint64_t seed, uint64_t first, MVec out) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  const uint64_t top_mask = (1ull << (F::kBits - 192)) - 1;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    const uint64_t index = first + i;
+    fe8 v;
+    for (uint64_t t = 0;; t++) {
+      uint64_t l[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) l[j] = splitmix64((seed ^ splitmix64(index * 4 + (uint64_t)j)) + t * 0xD1342543DE82EF95ull);
+      l[3] &= top_mask;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        v.v[2 * j] = (uint32_t)l[j];
+        v.v[2 * j + 1] = (uint32_t)(l[j] >> 32);
+      }
+      if (Fp<F>::is_canonical(v)) break;
+    }
+    st_fe(out, i, v);
+  }
+}
+
+}  // namespace ark

@@ -1,0 +1,177 @@
+/* arkmpc_b200 — C ABI of the Blackwell-native online-phase gate engine for ark-mpc.
+ *
+ * This is the drop-in boundary: the batched gate evaluation that the reference runs inside Rust
+ * closures handed to `MpcFabric::new_batch_gate_op` (/root/reference/online-phase/src/fabric.rs:841-854)
+ * is exposed here as plain C entry points over device memory.  The reference has no FFI on this path;
+ * each function below names the reference closure / operator it replaces.  INTEGRATION.md shows the
+ * Rust `extern "C"` block and the shim a maintainer would add.
+ *
+ * Conventions
+ *  - Every function returns 0 (ARKMPC_OK) or a negative arkmpc_status; nothing throws across the ABI.
+ *  - Field elements are the reference's memory image: canonical Montgomery residues (R = 2^256) in
+ *    4 little-endian u64 limbs = 32 bytes (`Scalar<C>`, algebra/scalar/scalar.rs:46).
+ *  - Device layout is PLANAR: a vector of n scalars is one contiguous plane of n*32 bytes; a vector
+ *    of n `ScalarShare`s (algebra/scalar/share.rs:32-37) is two planes, `share` and `mac`.  The
+ *    reference's AoS image {share,mac} (64 B) converts with arkmpc_share_unzip / arkmpc_share_zip.
+ *    Planes must be 32-byte aligned.  Output planes may alias input planes element-for-element.
+ *  - Pointers named `*_dev`/planes are DEVICE pointers; `key` arguments are HOST pointers to 4 u64
+ *    (Montgomery image of the party's MAC-key share, `MpcFabric::mac_key()`); `*_host` are host buffers.
+ *  - All work is enqueued on the context's stream and is asynchronous unless stated; a context is
+ *    bound to one device and may be used from any one thread at a time (two parties in one process
+ *    use two contexts, mirroring execute_mock_mpc, online-phase/src/lib.rs:157-201).
+ *  - n == 0 is a no-op returning ARKMPC_OK (the reference returns empty vectors,
+ *    authenticated_scalar.rs:854-856).  Length mismatches cannot occur: one n per call.
+ */
+#ifndef ARKMPC_B200_H
+#define ARKMPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARKMPC_ABI_VERSION 1
+
+typedef enum arkmpc_status {
+  ARKMPC_OK = 0,
+  ARKMPC_ERR_INVALID = -1,     /* bad argument (null pointer, unknown field, misaligned plane, bad party id) */
+  ARKMPC_ERR_CUDA = -2,        /* a CUDA runtime call failed; see arkmpc_last_error */
+  ARKMPC_ERR_NO_DEVICE = -3,   /* no usable sm_100 device */
+  ARKMPC_ERR_OOM = -4,
+  ARKMPC_ERR_UNSUPPORTED = -5, /* e.g. NCCL entry point on a build without NCCL */
+  ARKMPC_ERR_NCCL = -6
+} arkmpc_status;
+
+/* Scalar fields (C::ScalarField of the supported curves). */
+typedef enum arkmpc_field { ARKMPC_BN254_FR = 0, ARKMPC_CURVE25519_FR = 1 } arkmpc_field;
+/* Curve groups. */
+typedef enum arkmpc_curve { ARKMPC_BN254_G1 = 0, ARKMPC_CURVE25519_EDWARDS = 1 } arkmpc_curve;
+
+typedef struct arkmpc_ctx arkmpc_ctx;
+
+/* ---- library / context ---- */
+int arkmpc_abi_version(void);
+const char* arkmpc_status_string(int status);
+int arkmpc_device_count(int* count);
+int arkmpc_ctx_create(int device, arkmpc_ctx** out);
+int arkmpc_ctx_destroy(arkmpc_ctx* ctx);
+/* Run on a caller-owned cudaStream_t.  The handle is used verbatim: NULL is the CUDA default stream
+ * (what torch's default stream reports), not "no stream".  A fresh context runs on its own
+ * non-blocking stream; arkmpc_ctx_reset_stream returns to it. */
+int arkmpc_ctx_set_stream(arkmpc_ctx* ctx, void* cuda_stream);
+int arkmpc_ctx_reset_stream(arkmpc_ctx* ctx);
+void* arkmpc_ctx_get_stream(arkmpc_ctx* ctx);
+int arkmpc_ctx_device(arkmpc_ctx* ctx);
+int arkmpc_ctx_sync(arkmpc_ctx* ctx);
+int arkmpc_ctx_sm_count(arkmpc_ctx* ctx);
+/* Human-readable detail of the last failure on this context (valid until the next call). */
+const char* arkmpc_last_error(arkmpc_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t arkmpc_ctx_launch_count(arkmpc_ctx* ctx);
+
+/* ---- memory ---- */
+int arkmpc_malloc(arkmpc_ctx* ctx, size_t bytes, void** dev_ptr);
+int arkmpc_free(arkmpc_ctx* ctx, void* dev_ptr);
+int arkmpc_host_alloc(arkmpc_ctx* ctx, size_t bytes, void** pinned_ptr); /* pinned host memory */
+int arkmpc_host_free(arkmpc_ctx* ctx, void* pinned_ptr);
+int arkmpc_memcpy_h2d(arkmpc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* async on stream */
+int arkmpc_memcpy_d2h(arkmpc_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on stream */
+int arkmpc_memcpy_d2d(arkmpc_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
+
+/* ---- layout: reference AoS ScalarShare image <-> planes (share.rs:32-37) ---- */
+int arkmpc_share_unzip(arkmpc_ctx* ctx, size_t n, const uint64_t* aos_dev, uint64_t* share_plane, uint64_t* mac_plane);
+int arkmpc_share_zip(arkmpc_ctx* ctx, size_t n, const uint64_t* share_plane, const uint64_t* mac_plane, uint64_t* aos_dev);
+
+/* ---- the hot path: authenticated Beaver multiplication (authenticated_scalar.rs:848-879) ---- */
+
+/* Phase 1, replaces the two `batch_sub` gates (:863-864, closure :679-684) as far as `open_batch`
+ * consumes them (:141-145 sends only the share component):
+ *   d_mine[i] = x_share[i] - a_share[i],  e_mine[i] = y_share[i] - b_share[i]. */
+int arkmpc_fr_beaver_mask(arkmpc_ctx* ctx, int field, size_t n,
+                          const uint64_t* x_share, const uint64_t* y_share,
+                          const uint64_t* a_share, const uint64_t* b_share,
+                          uint64_t* d_mine, uint64_t* e_mine);
+
+/* Phase 2, replaces the open-add gate (:161-171), `ScalarResult::batch_mul` (scalar_result.rs:257-278),
+ * 2x `batch_mul_public` (:883-916), `batch_add_public` (:493-528, share.rs:74-77) and 2x `batch_add`
+ * (:457-489) with one fused kernel:
+ *   d = d_mine + d_peer, e = e_mine + e_peer,
+ *   out = d*e (party 0 share only; mac gets key*d*e) + d*[b] + e*[a] + [c].
+ * d_open / e_open are optional (NULL to skip) outputs of the opened masks. */
+int arkmpc_fr_beaver_recombine(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                               const uint64_t* d_mine, const uint64_t* e_mine,
+                               const uint64_t* d_peer, const uint64_t* e_peer,
+                               const uint64_t* a_share, const uint64_t* a_mac,
+                               const uint64_t* b_share, const uint64_t* b_mac,
+                               const uint64_t* c_share, const uint64_t* c_mac,
+                               uint64_t* out_share, uint64_t* out_mac,
+                               uint64_t* d_open, uint64_t* e_open);
+
+/* ---- public-scalar vector gates (algebra/scalar/scalar_result.rs:170-278) ---- */
+int arkmpc_fr_add(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, const uint64_t* b, uint64_t* out); /* also the open-add */
+int arkmpc_fr_sub(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, const uint64_t* b, uint64_t* out);
+int arkmpc_fr_mul(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, const uint64_t* b, uint64_t* out);
+int arkmpc_fr_neg(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, uint64_t* out);
+/* out[i] = a[i] * s (s: one host scalar) */
+int arkmpc_fr_scale(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, const uint64_t* s_host, uint64_t* out);
+
+/* ---- linear gates on share vectors (authenticated_scalar.rs:457-948, share.rs:74-131) ---- */
+int arkmpc_fr_share_add(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a_share, const uint64_t* a_mac,
+                        const uint64_t* b_share, const uint64_t* b_mac, uint64_t* out_share, uint64_t* out_mac);
+int arkmpc_fr_share_sub(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a_share, const uint64_t* a_mac,
+                        const uint64_t* b_share, const uint64_t* b_mac, uint64_t* out_share, uint64_t* out_mac);
+int arkmpc_fr_share_neg(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a_share, const uint64_t* a_mac,
+                        uint64_t* out_share, uint64_t* out_mac);
+/* batch_add_public / batch_sub_public (:493-528, :692-745): share += v on party 0 only; mac += key*v */
+int arkmpc_fr_share_add_public(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                               const uint64_t* a_share, const uint64_t* a_mac, const uint64_t* v,
+                               uint64_t* out_share, uint64_t* out_mac);
+int arkmpc_fr_share_sub_public(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                               const uint64_t* a_share, const uint64_t* a_mac, const uint64_t* v,
+                               uint64_t* out_share, uint64_t* out_mac);
+/* batch_mul_public / batch_mul_constant (:883-948): share*v, mac*v */
+int arkmpc_fr_share_mul_public(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a_share, const uint64_t* a_mac,
+                               const uint64_t* v, uint64_t* out_share, uint64_t* out_mac);
+
+/* ---- open_authenticated_batch pieces (:278-354) ---- */
+/* check[i] = key * opened[i] - mac[i]   (:299-311) */
+int arkmpc_fr_mac_check(arkmpc_ctx* ctx, int field, const uint64_t* key_host, size_t n,
+                        const uint64_t* opened, const uint64_t* mac, uint64_t* check);
+/* *all_zero_host = 1 iff mine[i] + peer[i] == 0 for every i  (:217-219).  Synchronous. */
+int arkmpc_fr_sum_is_zero(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* mine, const uint64_t* peer, int* all_zero_host);
+/* canonical big-endian 32-byte encoding of each element for the hash commitment (scalar.rs:118-127) */
+int arkmpc_fr_to_bytes_be(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, uint8_t* out_dev);
+
+/* ---- Sum (share.rs:104-111): out_share/out_mac are single device scalars; scratch managed by ctx ---- */
+int arkmpc_fr_share_sum(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a_share, const uint64_t* a_mac,
+                        uint64_t* out_share, uint64_t* out_mac);
+int arkmpc_fr_sum(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, uint64_t* out);
+
+/* ---- representation helpers ---- */
+int arkmpc_fr_to_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* plain, uint64_t* mont);   /* x -> x*R */
+int arkmpc_fr_from_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* mont, uint64_t* plain); /* x*R -> x */
+/* Deterministic synthetic elements, uniform in [0,p): element i = synth(seed, first_index + i)
+ * (`Scalar::random` stand-in for benches, scalar.rs:76-78); identical to oracle synth generators. */
+int arkmpc_fr_random(arkmpc_ctx* ctx, int field, uint64_t seed, uint64_t first_index, size_t n, uint64_t* out);
+
+/* ---- end-to-end over HOST buffers (reference AoS images), both protocol phases ----
+ * begin: uploads x, y and the triple (a, b, c) (n ScalarShares each, AoS, host), runs the mask kernel and
+ *        writes this party's d_mine || e_mine (2n scalars) to de_mine_host.  Synchronous on return.
+ * finish: uploads the peer's d_peer || e_peer (2n scalars), runs the fused recombine kernel and writes n
+ *        AoS ScalarShares to out_host (and, if non-NULL, the opened d || e to de_open_host).  Synchronous.
+ * Transfers are chunked and overlapped with the kernels on internal streams. */
+typedef struct arkmpc_batch_mul arkmpc_batch_mul;
+int arkmpc_fr_batch_mul_begin_host(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                                   const uint64_t* x_host, const uint64_t* y_host, const uint64_t* a_host,
+                                   const uint64_t* b_host, const uint64_t* c_host, uint64_t* de_mine_host,
+                                   arkmpc_batch_mul** session);
+int arkmpc_fr_batch_mul_finish_host(arkmpc_batch_mul* session, const uint64_t* de_peer_host, uint64_t* out_host,
+                                    uint64_t* de_open_host);
+int arkmpc_fr_batch_mul_abort(arkmpc_batch_mul* session);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARKMPC_B200_H */

@@ -1,0 +1,42 @@
+// Host-emulation harness: compiles the SAME per-element device functions (fp256.cuh, beaver.cuh)
+// with the carry flag emulated in software, and exports them with a C ABI so tests/test_host_emu.py
+// can check the exact instruction sequences against the oracle on a CPU-only box.
+// Test infrastructure; not part of the product library.
+#include <cstring>
+#include "../../ark_mpc_b200/csrc/beaver.cuh"
+using namespace ark;
+
+template <class F> static void run(int op, const uint32_t* in, uint32_t* out, int party) {
+  const fe8* v = reinterpret_cast<const fe8*>(in);
+  fe8* o = reinterpret_cast<fe8*>(out);
+  switch (op) {
+    case 0: Fp<F>::add(o[0], v[0], v[1]); break;
+    case 1: Fp<F>::sub(o[0], v[0], v[1]); break;
+    case 2: Fp<F>::neg(o[0], v[0]); break;
+    case 3: Fp<F>::mul(o[0], v[0], v[1]); break;
+    case 4: Fp<F>::mul_lazy(o[0], v[0], v[1]); break;
+    case 5: if constexpr (F::kLazy2) { Fp<F>::mul2_lazy(o[0], v[0], v[1], v[2], v[3]); } break;
+    case 6: beaver_mask_elem<F>(o[0], o[1], v[0], v[1], v[2], v[3]); break;
+    case 7: if constexpr (F::kLazy2) {
+      // in: key, d_mine, e_mine, d_peer, e_peer, a_s, a_m, b_s, b_m, c_s, c_m ; out: out_s, out_m, d, e
+      beaver_recombine_elem<F>(o[0], o[1], o[2], o[3], party, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10]);
+    } break;
+    case 8: share_add_public_elem<F>(o[0], o[1], party, v[0], v[1], v[2], v[3]); break;
+    case 9: share_sub_public_elem<F>(o[0], o[1], party, v[0], v[1], v[2], v[3]); break;
+    case 10: mac_check_elem<F>(o[0], v[0], v[1], v[2]); break;
+    case 11: o[0] = v[0]; Fp<F>::csub_p(o[0]); break;
+    case 12: Fp<F>::set_one(o[0]); Fp<F>::set_r2(o[1]); break;
+  }
+}
+
+extern "C" uint64_t emu_violations() { return ark::emu::violations; }
+
+extern "C" int emu_run(int field, int op, int party, const uint32_t* in, uint32_t* out) {
+  switch (field) {
+    case 0: run<Bn254Fr>(op, in, out, party); return 0;
+    case 1: run<Curve25519Fr>(op, in, out, party); return 0;
+    case 2: run<Bn254Fq>(op, in, out, party); return 0;
+    case 3: run<Curve25519Fq>(op, in, out, party); return 0;
+  }
+  return -1;
+}
