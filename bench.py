@@ -45,43 +45,71 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons; rows are time-stamped on arrival so that only the
+    samples that fall inside the timed region are summarised."""
 
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    FIELDS = ["clocks.sm", "clocks.max.sm", "power.draw"]
+    REASONS = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.err = index, [], None, None
+
+    def _spawn(self, prefix):
+        q = ",".join(self.FIELDS + [f"{prefix}.{r}" for r in self.REASONS])
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = self._spawn("clocks_event_reasons")
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # nvidia-smi missing
+            self.proc, self.err = None, repr(e)
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        for prefix in ("clocks_event_reasons", "clocks_throttle_reasons"):
+            got = False
+            for line in self.proc.stdout:
+                cells = [c.strip() for c in line.split(",")]
+                try:
+                    float(cells[0])
+                except Exception:
+                    continue  # an error line (unknown field on an older nvidia-smi)
+                got = True
+                self.rows.append((time.perf_counter(), cells))
+            if got or prefix == "clocks_throttle_reasons":
+                return
+            try:
+                self.proc = self._spawn("clocks_throttle_reasons")
+            except Exception:
+                return
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while not self.rows and self.proc and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvidia-smi unavailable {self.err or ''}".strip()]}
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        rows = [r for r in self.rows if len(r) >= 7]
+        rows = [(t, r) for t, r in self.rows if len(r) >= 7]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[0]) for r in rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows),
-                "power_w_max": max(float(r[2]) for r in rows)}
+        inside = [r for t, r in rows if t_begin is None or (t_begin <= t <= t_end + 0.06)]
+        window = "timed region"
+        if len(inside) < 2:
+            inside, window = [r for _, r in rows], "whole bench (timed region shorter than the sampling period)"
+        sm = sorted(float(r[0]) for r in inside)
+        reasons = [nm for k, nm in enumerate(self.REASONS) if any(r[3 + k].lower().startswith("active") for r in inside)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": float(inside[0][1]), "reasons": reasons,
+                "samples": len(inside), "window": window, "power_w_max": max(float(r[2]) for r in inside)}
 
 
 def run_reference(args, rank, world):
@@ -94,11 +122,23 @@ def run_reference(args, rank, world):
     from tests.util import TwoPartyData, aos
 
     fid = {"bn254_fr": 0, "curve25519_fr": 1}[args.field]
-    n = 1 << args.log2_batch
+    n_full = 1 << args.log2_batch
     cores = os.cpu_count() or 1
-    D = TwoPartyData(fid, n, seed=0xA11CE)
+    D = TwoPartyData(fid, n_full, seed=0xA11CE)
     g = lambda t: (aos(*t[0]), aos(*t[1]))
-    ins = (D.keys, g(D.x), g(D.y), g(D.a), g(D.b), g(D.c))
+    full = (g(D.x), g(D.y), g(D.a), g(D.b), g(D.c))
+    # calibrate on 2^16 gates, then bound the per-step sample so that warmup+steps stay within ~budget seconds
+    cut = lambda m: tuple((t[0][:m], t[1][:m]) for t in full)
+    m0 = min(n_full, 1 << 16)
+    co.two_party_batch_mul(fid, cores, D.keys, *cut(m0), want_open=False)
+    t0 = time.perf_counter()
+    co.two_party_batch_mul(fid, cores, D.keys, *cut(m0), want_open=False)
+    per_gate = (time.perf_counter() - t0) / m0
+    budget = 90.0
+    n = n_full
+    while n > (1 << 14) and per_gate * n * (args.steps + args.warmup) > budget:
+        n >>= 1
+    ins = (D.keys,) + cut(n)
     for _ in range(args.warmup):
         co.two_party_batch_mul(fid, cores, *ins, want_open=False)
     t0 = time.perf_counter()
@@ -112,7 +152,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "u64 limbs (4x64 Montgomery, CIOS)", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"full 2^{args.log2_batch} two-party batch_mul per step, {args.steps} steps, "
+                         "sample": f"{n} of the 2^{args.log2_batch} gates (two-party batch_mul) per step, {args.steps} steps, "
                                    "unfused reference gate sequence (oracle/ark_oracle.c), static index partition"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "Rust reference unbuildable here (no cargo/rustc, arkworks not vendored): C restatement of its gate "
@@ -132,8 +172,8 @@ def workload_config(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-batch", type=int, default=20)
     ap.add_argument("--field", default="bn254_fr", choices=["bn254_fr", "curve25519_fr"])
@@ -165,6 +205,8 @@ def main():
 
     fid = {"bn254_fr": 0, "curve25519_fr": 1}[args.field]
     n = 1 << args.log2_batch
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         E = Engine(local_rank, args.field)  # binds the current (bench) stream
@@ -216,8 +258,8 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        sampler.wait_first()
+        t_begin = time.perf_counter()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         launches0 = E.launches
@@ -230,6 +272,7 @@ def main():
         ev1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
+        t_end = time.perf_counter()
         launches = E.launches - launches0
         ms = ev0.elapsed_time(ev1)
         k2_ms = sum(a.elapsed_time(b) for a, b in kev) / (2 * args.steps)  # per recombine launch
@@ -238,7 +281,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
             dist.barrier()
-        clocks = sampler.stop()
+        clocks = sampler.stop(t_begin, t_end)
 
         # ---- e2e: host AoS buffers through the C ABI, copies inside the timed region ----
         e2e = None
