@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -31,6 +32,7 @@ struct arkmpc_ctx {
   char* partials = nullptr;  // 2 * kMaxPartialBlocks field elements
   int* flag_dev = nullptr;
   int* flag_host = nullptr;  // pinned
+  bool use_tma = false;  // ARKMPC_RECOMBINE=tma
   std::string last_error;
 };
 
@@ -104,8 +106,40 @@ int launch_mask(arkmpc_ctx* ctx, cudaStream_t s, size_t n, Vec x, Vec y, Vec a, 
   return post_launch(ctx, "beaver_mask_kernel");
 }
 
+template <class F, int PARTY, bool OPEN>
+int launch_recombine_tma(arkmpc_ctx* ctx, cudaStream_t s, size_t n, const RecombineArgs& g) {
+  auto kern = beaver_recombine_tma_kernel<F, PARTY, OPEN>;
+  static thread_local int configured_dev = -1;
+  if (configured_dev != ctx->device) {  // per (instantiation, thread): opt in to > 48 KiB of dynamic shared memory
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    if (e != cudaSuccess) return fail(ctx, ARKMPC_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    configured_dev = ctx->device;
+  }
+  const size_t tiles = (n + kTmaTile - 1) / kTmaTile;
+  const size_t need = (tiles + kTmaWarps - 1) / kTmaWarps;
+  const size_t cap = (size_t)ctx->sm_count * 2;
+  kern<<<(unsigned)(need < cap ? need : cap), kBlock, kTmaSmemBytes, s>>>(n, g);
+  return post_launch(ctx, "beaver_recombine_tma_kernel");
+}
+
+inline bool recombine_is_planar(const RecombineArgs& g, bool open) {
+  const uint32_t st[] = {g.d_mine.stride, g.e_mine.stride, g.d_peer.stride, g.e_peer.stride, g.a_s.stride, g.a_m.stride,
+                         g.b_s.stride,    g.b_m.stride,    g.c_s.stride,    g.c_m.stride};
+  for (uint32_t v : st)
+    if (v != 32) return false;
+  (void)open;
+  return true;
+}
+
+// Default: the LDG kernel.  Measured on B200 (profiles/r01b_ab.txt) the recombination is bound by integer issue
+// (536 IMAD.WIDE at ~4 issue cycles + ~320 other instructions per gate), not by memory latency, so TMA staging buys
+// nothing (88.4 us vs 84.5 us per 2^20 gates); ARKMPC_RECOMBINE=tma selects the staged kernel for planar operands.
 template <class F>
 int launch_recombine(arkmpc_ctx* ctx, cudaStream_t s, int party, size_t n, const RecombineArgs& g, bool open) {
+  if (ctx->use_tma && recombine_is_planar(g, open)) {
+    if (party == 0) return open ? launch_recombine_tma<F, 0, true>(ctx, s, n, g) : launch_recombine_tma<F, 0, false>(ctx, s, n, g);
+    return open ? launch_recombine_tma<F, 1, true>(ctx, s, n, g) : launch_recombine_tma<F, 1, false>(ctx, s, n, g);
+  }
   const unsigned grid = grid_for(ctx, n, 2);
   if (party == 0) {
     if (open) beaver_recombine_kernel<F, 0, true><<<grid, kBlock, 0, s>>>(n, g);
@@ -181,6 +215,10 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
     return ARKMPC_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  {
+    const char* v = getenv("ARKMPC_RECOMBINE");
+    ctx->use_tma = v && strcmp(v, "tma") == 0;
+  }
   *out = ctx;
   return ARKMPC_OK;
 }

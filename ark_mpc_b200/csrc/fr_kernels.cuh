@@ -93,6 +93,127 @@ __global__ void __launch_bounds__(kBlock, 2) beaver_recombine_kernel(size_t n, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Beaver phase 2, TMA-staged variant for planar (stride-32) operands.
+//
+// The LDG kernel above keeps only ~16 warps x 320 B in flight per SM and every warp stalls on its ten loads before
+// its ~850 arithmetic instructions, so neither HBM nor the IMAD pipe saturates (ncu r01a: DRAM 56 %, fma pipe 41 %).
+// Here every warp owns one 10 KiB shared-memory slot (ten planes x 32 elements x 32 B) and one mbarrier.  Per tile
+// of 32 gates the warp (1) waits for the slot, (2) copies its operands into registers (2 x LDS.128 per operand),
+// (3) lane 0 immediately re-arms the barrier and issues the ten 1 KiB bulk copies (cp.async.bulk -> SASS UBLKCP)
+// of the warp's NEXT tile into the same slot, (4) all lanes run the fused recombination and store with STG.256.
+// The copy of tile k+1 therefore overlaps the whole arithmetic of tile k with zero register cost, and warps
+// drift apart so HBM demand is smooth.  2 CTAs x 8 warps x 10 KiB = 160 KiB of the SM's 227 KiB.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTmaPlanes = 10;
+constexpr int kTmaTile = 32;                                   // gates per warp tile
+constexpr int kTmaPlaneBytes = kTmaTile * 32;                  // 1 KiB
+constexpr int kTmaSlotBytes = kTmaPlanes * kTmaPlaneBytes;     // 10 KiB per warp
+constexpr int kTmaWarps = kBlock / 32;
+constexpr int kTmaSmemBytes = kTmaWarps * kTmaSlotBytes + kTmaWarps * 8 + kBlock * 4;  // slots | mbarriers | per-lane sink words
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void lds_fe(fe8& r, uint32_t addr) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]) : "r"(addr) : "memory");
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "r"(addr + 16) : "memory");
+}
+
+template <class F, int PARTY, bool OPEN>
+__global__ void __launch_bounds__(kBlock, 2) beaver_recombine_tma_kernel(size_t n, const __grid_constant__ RecombineArgs g) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t slot = smem_u32(smem) + warp * kTmaSlotBytes;
+  const uint32_t bar = smem_u32(smem) + kTmaWarps * kTmaSlotBytes + warp * 8;
+  const uint32_t sink = smem_u32(smem) + kTmaWarps * kTmaSlotBytes + kTmaWarps * 8 + threadIdx.x * 4;
+  const size_t tiles = (n + kTmaTile - 1) / kTmaTile;
+  const size_t stride = (size_t)gridDim.x * kTmaWarps;
+  size_t t = (size_t)blockIdx.x * kTmaWarps + warp;
+
+  // order in the slot: d_mine d_peer e_mine e_peer b_s a_s b_m a_m c_s c_m
+  auto issue = [&](size_t tile) {
+    const size_t first = tile * kTmaTile;
+    const uint32_t bytes = (uint32_t)((n - first < (size_t)kTmaTile ? n - first : (size_t)kTmaTile) * 32);
+    const size_t off = first * 32;
+    mbar_expect_tx(bar, bytes * kTmaPlanes);
+    bulk_g2s(slot + 0 * kTmaPlaneBytes, g.d_mine.p + off, bytes, bar);
+    bulk_g2s(slot + 1 * kTmaPlaneBytes, g.d_peer.p + off, bytes, bar);
+    bulk_g2s(slot + 2 * kTmaPlaneBytes, g.e_mine.p + off, bytes, bar);
+    bulk_g2s(slot + 3 * kTmaPlaneBytes, g.e_peer.p + off, bytes, bar);
+    bulk_g2s(slot + 4 * kTmaPlaneBytes, g.b_s.p + off, bytes, bar);
+    bulk_g2s(slot + 5 * kTmaPlaneBytes, g.a_s.p + off, bytes, bar);
+    bulk_g2s(slot + 6 * kTmaPlaneBytes, g.b_m.p + off, bytes, bar);
+    bulk_g2s(slot + 7 * kTmaPlaneBytes, g.a_m.p + off, bytes, bar);
+    bulk_g2s(slot + 8 * kTmaPlaneBytes, g.c_s.p + off, bytes, bar);
+    bulk_g2s(slot + 9 * kTmaPlaneBytes, g.c_m.p + off, bytes, bar);
+  };
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (t < tiles) issue(t);
+  }
+  __syncwarp();
+
+  uint32_t parity = 0;
+  for (; t < tiles; t += stride) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    const uint32_t mine = slot + lane * 32;
+    fe8 dm, dp, em, ep, bs, as, bm, am, cs, cm;
+    lds_fe(dm, mine + 0 * kTmaPlaneBytes);
+    lds_fe(dp, mine + 1 * kTmaPlaneBytes);
+    lds_fe(em, mine + 2 * kTmaPlaneBytes);
+    lds_fe(ep, mine + 3 * kTmaPlaneBytes);
+    lds_fe(bs, mine + 4 * kTmaPlaneBytes);
+    lds_fe(as, mine + 5 * kTmaPlaneBytes);
+    lds_fe(bm, mine + 6 * kTmaPlaneBytes);
+    lds_fe(am, mine + 7 * kTmaPlaneBytes);
+    lds_fe(cs, mine + 8 * kTmaPlaneBytes);
+    lds_fe(cm, mine + 9 * kTmaPlaneBytes);
+    // Every LDS must have RETURNED before the slot is handed back to the async proxy: consume one register of
+    // each load (the scoreboard wait happens at first use), then converge the warp.
+    uint32_t seen = (dm.v[0] | dm.v[4]) ^ (dp.v[0] | dp.v[4]) ^ (em.v[0] | em.v[4]) ^ (ep.v[0] | ep.v[4]) ^ (bs.v[0] | bs.v[4]) ^
+                    (as.v[0] | as.v[4]) ^ (bm.v[0] | bm.v[4]) ^ (am.v[0] | am.v[4]) ^ (cs.v[0] | cs.v[4]) ^ (cm.v[0] | cm.v[4]);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sink), "r"(seen) : "memory");  // a side effect ptxas cannot drop
+    __syncwarp();
+    const size_t next = t + stride;
+    if (lane == 0 && next < tiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(next);
+    }
+    const size_t i = t * kTmaTile + lane;
+    if (i < n) {
+      fe8 os, om, d, e;
+      beaver_recombine_elem<F>(os, om, d, e, PARTY, g.key, dm, em, dp, ep, as, am, bs, bm, cs, cm);
+      st_fe(g.out_s, i, os);
+      st_fe(g.out_m, i, om);
+      if (OPEN) {
+        st_fe(g.d_open, i, d);
+        st_fe(g.e_open, i, e);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Generic element-wise gates
 // ---------------------------------------------------------------------------------------------
 enum class Bin { Add, Sub, Mul };
