@@ -75,6 +75,22 @@ _PROTOS = {
     "arkmpc_fr_to_mont": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_fr_from_mont": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_fr_random": [_vp, _i, _u64, _u64, _sz, _vp],
+    "arkmpc_point_bytes": [_i],
+    "arkmpc_pt_add": [_vp, _i, _sz, _vp, _vp, _vp],
+    "arkmpc_pt_sub": [_vp, _i, _sz, _vp, _vp, _vp],
+    "arkmpc_pt_neg": [_vp, _i, _sz, _vp, _vp],
+    "arkmpc_pt_share_add_public": [_vp, _i, _i, _vp, _sz, _vp, _vp, _vp],
+    "arkmpc_pt_share_sub_public": [_vp, _i, _i, _vp, _sz, _vp, _vp, _vp],
+    "arkmpc_pt_mul": [_vp, _i, _sz, _vp, _vp, _vp],
+    "arkmpc_pt_share_mul_public": [_vp, _i, _sz, _vp, _vp, _vp],
+    "arkmpc_pt_mul_authenticated": [_vp, _i, _sz, _vp, _vp, _vp, _vp],
+    "arkmpc_pt_mul_generator": [_vp, _i, _sz, _vp, _vp, _vp],
+    "arkmpc_pt_mul_generator_public": [_vp, _i, _sz, _vp, _vp],
+    "arkmpc_pt_beaver_mask": [_vp, _i, _sz] + [_vp] * 6,
+    "arkmpc_pt_beaver_recombine": [_vp, _i, _i, _vp, _sz] + [_vp] * 13,
+    "arkmpc_pt_mac_check": [_vp, _i, _vp, _sz, _vp, _vp, _vp],
+    "arkmpc_pt_sum_is_identity": [_vp, _i, _sz, _vp, _vp, C.POINTER(_i)],
+    "arkmpc_pt_normalize": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_fr_batch_mul_begin_host": [_vp, _i, _i, _vp, _sz] + [_vp] * 6 + [C.POINTER(_vp)],
     "arkmpc_fr_batch_mul_finish_host": [_vp, _vp, _vp, _vp],
     "arkmpc_fr_batch_mul_abort": [_vp],
@@ -84,6 +100,7 @@ _RESTYPES = {
     "arkmpc_last_error": C.c_char_p,
     "arkmpc_ctx_get_stream": _vp,
     "arkmpc_ctx_launch_count": _u64,
+    "arkmpc_point_bytes": _sz,
 }
 
 # every symbol include/arkmpc_b200.h declares (checked by tests/test_abi.py against the header text)

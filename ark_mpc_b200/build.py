@@ -16,8 +16,9 @@ LIB = os.path.join(LIB_DIR, "libarkmpc_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = os.path.join(PKG, "lib", "obj")
 
 
 def _nvcc() -> str:
@@ -48,12 +49,26 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into ark_mpc_b200/lib/libarkmpc_b200.so."""
     if not force and not is_stale():
         return LIB
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB, *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    dep_time = max(os.path.getmtime(d) for d in _deps())
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < dep_time:
+            cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), file=sys.stderr)
+            subprocess.check_call(cmd)
+        return obj
+
+    # one translation unit per thread: the point kernels take much longer to compile than the scalar ones
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        objs = list(pool.map(compile_one, sources()))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs])
     return LIB
 
 

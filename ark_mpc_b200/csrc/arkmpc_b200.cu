@@ -1,103 +1,11 @@
 // C ABI of libarkmpc_b200 (declared in include/arkmpc_b200.h): contexts, memory, launch wrappers.
 // No torch types, no exceptions across the boundary.  Kernels live in fr_kernels.cuh / beaver.cuh / fp256.cuh.
-#include "../../include/arkmpc_b200.h"
-
-#include <cuda_runtime.h>
-
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <string>
-
-#include "fr_kernels.cuh"
+#include "ctx.hpp"
 
 using namespace ark;
+using namespace arkctx;
 
 namespace {
-constexpr int kSlots = 3;                 // chunk pipeline depth of the host-buffer path
-constexpr size_t kChunkElems = 1u << 16;  // elements per staged chunk
-constexpr int kMaxPartialBlocks = 1024;
-}  // namespace
-
-struct arkmpc_ctx {
-  int device = 0;
-  int sm_count = 0;
-  cudaStream_t own_stream = nullptr;
-  cudaStream_t stream = nullptr;  // current (own or caller's)
-  cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
-  cudaEvent_t slot_event[kSlots] = {nullptr, nullptr, nullptr};
-  uint64_t launches = 0;
-  char* partials = nullptr;  // 2 * kMaxPartialBlocks field elements
-  int* flag_dev = nullptr;
-  int* flag_host = nullptr;  // pinned
-  bool use_tma = false;  // ARKMPC_RECOMBINE=tma
-  std::string last_error;
-};
-
-namespace {
-
-int fail(arkmpc_ctx* ctx, int code, const std::string& msg) {
-  if (ctx) ctx->last_error = msg;
-  return code;
-}
-
-#define ARK_CUDA(ctx, expr)                                                                        \
-  do {                                                                                             \
-    cudaError_t _e = (expr);                                                                       \
-    if (_e != cudaSuccess) {                                                                       \
-      return fail(ctx, _e == cudaErrorMemoryAllocation ? ARKMPC_ERR_OOM : ARKMPC_ERR_CUDA,         \
-                  std::string(#expr) + ": " + cudaGetErrorString(_e));                             \
-    }                                                                                              \
-  } while (0)
-
-#define ARK_REQUIRE(ctx, cond, msg) \
-  do {                              \
-    if (!(cond)) return fail(ctx, ARKMPC_ERR_INVALID, msg); \
-  } while (0)
-
-inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
-
-inline Vec vec(const void* p, uint32_t stride = 32) { return Vec{static_cast<const char*>(p), stride}; }
-inline MVec mvec(void* p, uint32_t stride = 32) { return MVec{static_cast<char*>(p), stride}; }
-
-inline fe8 load_host_fe(const uint64_t* h) {
-  fe8 r;
-  for (int j = 0; j < 4; j++) {
-    r.v[2 * j] = (uint32_t)h[j];
-    r.v[2 * j + 1] = (uint32_t)(h[j] >> 32);
-  }
-  return r;
-}
-
-// persistent grid: enough blocks to cover n, capped at blocks_per_sm resident blocks per SM
-inline unsigned grid_for(const arkmpc_ctx* ctx, size_t n, int blocks_per_sm) {
-  size_t need = (n + kBlock - 1) / kBlock;
-  size_t cap = (size_t)ctx->sm_count * blocks_per_sm;
-  return (unsigned)(need < cap ? (need ? need : 1) : cap);
-}
-
-int post_launch(arkmpc_ctx* ctx, const char* what) {
-  ctx->launches++;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(ctx, ARKMPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
-  return ARKMPC_OK;
-}
-
-#define ARK_FIELD_SWITCH(ctx, field, ...)                    \
-  switch (field) {                                           \
-    case ARKMPC_BN254_FR: { using F = Bn254Fr; __VA_ARGS__; } break; \
-    case ARKMPC_CURVE25519_FR: { using F = Curve25519Fr; __VA_ARGS__; } break; \
-    default: return fail(ctx, ARKMPC_ERR_INVALID, "unknown field id"); \
-  }
-
-#define ARK_CHECK_CTX(ctx) \
-  do {                     \
-    if (!(ctx)) return ARKMPC_ERR_INVALID; \
-    cudaError_t _e = cudaSetDevice((ctx)->device); \
-    if (_e != cudaSuccess) return fail(ctx, ARKMPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_e)); \
-  } while (0)
 
 // ---- launch helpers shared by the device-pointer ABI and the host-buffer path ----
 template <class F>
@@ -234,6 +142,8 @@ int arkmpc_ctx_destroy(arkmpc_ctx* ctx) {
   if (ctx->partials) cudaFree(ctx->partials);
   if (ctx->flag_dev) cudaFree(ctx->flag_dev);
   if (ctx->flag_host) cudaFreeHost(ctx->flag_host);
+  for (int c = 0; c < kNumCurves; c++)
+    if (ctx->gtab[c]) cudaFree(ctx->gtab[c]);
   delete ctx;
   return ARKMPC_OK;
 }

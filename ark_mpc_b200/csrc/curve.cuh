@@ -1,0 +1,407 @@
+// Curve-group arithmetic for the point gates: one point (or one point gate) per thread.
+//
+// What it replaces (paths under /root/reference/online-phase/src/algebra/curve): the plaintext group
+// operations behind `CurvePoint<C>` (curve.rs:194-209 add, :403-409 scalar-mul, both forwarding to
+// ark-ec 0.4 `CurveGroup`, which is NOT vendored) for the two supported groups:
+//   * BN254 G1  — short Weierstrass y^2 = x^3 + 3 over Fq, Jacobian (X,Y,Z), identity Z = 0
+//                 (the memory image of ark-bn254 `G1Projective`: x,y,z, 3 x 32 B Montgomery residues)
+//   * Curve25519 Edwards — twisted Edwards -x^2 + y^2 = 1 + d x^2 y^2 over 2^255-19, extended (X,Y,T,Z),
+//                 identity (0,1,0,1) (ark-curve25519 `EdwardsProjective`: x,y,t,z, 4 x 32 B)
+// Projective representatives are not unique (curve.rs:46 compares through arkworks' projective equality), so
+// parity with the reference is defined on the affine form; `normalize` produces it.
+//
+// Scalar multiplication: the reference does a per-element MSB-first double-and-add (`self.0 * rhs.0`).  Here:
+//   variable base  4-bit fixed windows over a per-thread table {1..15}P kept in local memory (252 doublings + <=64 adds)
+//   fixed base G   table {w * 16^j * G : j < 64, 1 <= w <= 15} in global memory, built once per context
+//                  (no doublings, <= 64 mixed additions)
+// and the callers regroup sums of products that share a base into one pass (see curve_kernels.cuh).
+//
+// Dual-target like fp256.cuh: compiles under g++ for the host-emulation tests.
+#pragma once
+#include "fp256.cuh"
+
+namespace ark {
+
+// ----------------------------------------------------------------------------------------------
+// Base-field helpers (canonical Montgomery residues throughout; in-place aliasing is allowed)
+// ----------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+#define ARK_FQ_MUL ARK_DM
+#else
+#define ARK_FQ_MUL __attribute__((noinline))  // keeps the host-emulation build small and fast to compile
+#endif
+template <class Q>
+struct Fq {
+  using F = Fp<Q>;
+  ARK_FQ_MUL static void mul(fe8& r, const fe8& a, const fe8& b) { F::mul(r, a, b); }
+  ARK_FQ_MUL static void sqr(fe8& r, const fe8& a) { F::mul(r, a, a); }
+  ARK_DM static void add(fe8& r, const fe8& a, const fe8& b) { F::add(r, a, b); }
+  ARK_DM static void sub(fe8& r, const fe8& a, const fe8& b) { F::sub(r, a, b); }
+  ARK_DM static void dbl(fe8& r, const fe8& a) { F::add(r, a, a); }
+  ARK_DM static void neg(fe8& r, const fe8& a) { F::neg(r, a); }
+  ARK_DM static bool is_zero(const fe8& a) { return F::is_zero(a); }
+  ARK_DM static bool eq(const fe8& a, const fe8& b) { return F::eq(a, b); }
+  ARK_DM static void one(fe8& r) { F::set_one(r); }
+  ARK_DM static void zero(fe8& r) { F::set_zero(r); }
+  // a^(p-2) (Fermat), MSB-first square-and-multiply; inv(0) = 0
+  ARK_DM static void inv(fe8& r, const fe8& a) {
+    uint32_t e[8] = {Q::P0 - 2u, Q::P1, Q::P2, Q::P3, Q::P4, Q::P5, Q::P6, Q::P7};  // P0 >= 2 for every modulus here
+    fe8 acc;
+    one(acc);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int i = 255; i >= 0; i--) {
+      sqr(acc, acc);
+      if ((e[i >> 5] >> (i & 31)) & 1u) mul(acc, acc, a);
+    }
+    r = acc;
+  }
+};
+
+// Scalar-field element (Montgomery image) -> plain integer limbs, for window extraction.
+template <class R>
+ARK_D void scalar_to_plain(uint32_t* k, const fe8& s_mont) {
+  fe8 one, r;
+  Fp<R>::set_zero(one);
+  one.v[0] = 1;
+  Fp<R>::mul(r, s_mont, one);
+  ARK_UNROLL for (int j = 0; j < 8; j++) k[j] = r.v[j];
+}
+ARK_D uint32_t window4(const uint32_t* k, int i) { return (k[i >> 3] >> ((i & 7) * 4)) & 15u; }
+
+// ----------------------------------------------------------------------------------------------
+// BN254 G1: Jacobian coordinates, a = 0
+// ----------------------------------------------------------------------------------------------
+struct PtSW { fe8 X, Y, Z; };
+struct AffSW { fe8 x, y; };
+
+struct Bn254G1 {
+  static constexpr int kId = 0;
+  using Q = Bn254Fq;
+  using R = Bn254Fr;
+  using Pt = PtSW;
+  using Cached = PtSW;     // variable-base table entry
+  using Aff = AffSW;       // fixed-base table entry (never the identity)
+  using K = Fq<Q>;
+  static constexpr int kCoords = 3;
+  static constexpr int kPointBytes = 96;
+  static constexpr int kAffWords = 16;  // u32 words per fixed-table entry
+
+  ARK_DM static void set_identity(Pt& p) { K::one(p.X); K::one(p.Y); K::zero(p.Z); }  // ark-ec: (1,1,0)
+  ARK_DM static bool is_identity(const Pt& p) { return K::is_zero(p.Z); }
+  ARK_DM static void set_generator(Pt& p) {  // (1, 2)
+    K::one(p.X);
+    K::add(p.Y, p.X, p.X);
+    K::one(p.Z);
+  }
+  ARK_DM static void neg(Pt& p) { K::neg(p.Y, p.Y); }
+  ARK_DM static void cache(Cached& c, const Pt& p) { c = p; }
+
+  // dbl-2009-l (2M + 5S); Z = 0 stays Z = 0
+  ARK_DM static void dbl(Pt& p) {
+    fe8 A, B, C, D, E, F, t;
+    K::sqr(A, p.X);
+    K::sqr(B, p.Y);
+    K::sqr(C, B);
+    K::add(t, p.X, B);
+    K::sqr(t, t);
+    K::sub(t, t, A);
+    K::sub(t, t, C);
+    K::dbl(D, t);
+    K::dbl(E, A);
+    K::add(E, E, A);
+    K::sqr(F, E);
+    K::mul(p.Z, p.Y, p.Z);
+    K::dbl(p.Z, p.Z);
+    K::dbl(t, D);
+    K::sub(p.X, F, t);
+    K::sub(t, D, p.X);
+    K::mul(t, E, t);
+    K::dbl(C, C);
+    K::dbl(C, C);
+    K::dbl(C, C);
+    K::sub(p.Y, t, C);
+  }
+
+  // add-2007-bl (11M + 5S) with the exceptional cases handled
+  ARK_DM static void add(Pt& p, const Pt& q) {
+    if (is_identity(q)) return;
+    if (is_identity(p)) { p = q; return; }
+    fe8 Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, r, V, t;
+    K::sqr(Z1Z1, p.Z);
+    K::sqr(Z2Z2, q.Z);
+    K::mul(U1, p.X, Z2Z2);
+    K::mul(U2, q.X, Z1Z1);
+    K::mul(S1, p.Y, q.Z);
+    K::mul(S1, S1, Z2Z2);
+    K::mul(S2, q.Y, p.Z);
+    K::mul(S2, S2, Z1Z1);
+    K::sub(H, U2, U1);
+    K::sub(r, S2, S1);
+    if (K::is_zero(H)) {
+      if (K::is_zero(r)) { dbl(p); return; }
+      set_identity(p);
+      return;
+    }
+    K::dbl(r, r);
+    K::dbl(I, H);
+    K::sqr(I, I);
+    K::mul(J, H, I);
+    K::mul(V, U1, I);
+    K::add(t, p.Z, q.Z);
+    K::sqr(t, t);
+    K::sub(t, t, Z1Z1);
+    K::sub(t, t, Z2Z2);
+    K::mul(p.Z, t, H);
+    K::sqr(p.X, r);
+    K::sub(p.X, p.X, J);
+    K::dbl(t, V);
+    K::sub(p.X, p.X, t);
+    K::sub(t, V, p.X);
+    K::mul(t, r, t);
+    K::mul(S1, S1, J);
+    K::dbl(S1, S1);
+    K::sub(p.Y, t, S1);
+  }
+  ARK_DM static void add_cached(Pt& p, const Cached& q) { add(p, q); }
+
+  // madd-2007-bl (7M + 4S), q affine and not the identity
+  ARK_DM static void madd(Pt& p, const Aff& q) {
+    if (is_identity(p)) { p.X = q.x; p.Y = q.y; K::one(p.Z); return; }
+    fe8 Z1Z1, U2, S2, H, HH, I, J, r, V, t;
+    K::sqr(Z1Z1, p.Z);
+    K::mul(U2, q.x, Z1Z1);
+    K::mul(S2, q.y, p.Z);
+    K::mul(S2, S2, Z1Z1);
+    K::sub(H, U2, p.X);
+    K::sub(r, S2, p.Y);
+    if (K::is_zero(H)) {
+      if (K::is_zero(r)) { dbl(p); return; }
+      set_identity(p);
+      return;
+    }
+    K::dbl(r, r);
+    K::sqr(HH, H);
+    K::dbl(I, HH);
+    K::dbl(I, I);
+    K::mul(J, H, I);
+    K::mul(V, p.X, I);
+    K::add(t, p.Z, H);
+    K::sqr(t, t);
+    K::sub(t, t, Z1Z1);
+    K::sub(p.Z, t, HH);
+    K::sqr(p.X, r);
+    K::sub(p.X, p.X, J);
+    K::dbl(t, V);
+    K::sub(p.X, p.X, t);
+    K::sub(t, V, p.X);
+    K::mul(t, r, t);
+    K::mul(J, p.Y, J);
+    K::dbl(J, J);
+    K::sub(p.Y, t, J);
+  }
+
+  // affine (x, y); the identity maps to (0, 0), which is not on the curve
+  ARK_DM static void normalize(fe8& x, fe8& y, const Pt& p) {
+    if (is_identity(p)) { K::zero(x); K::zero(y); return; }
+    fe8 zi, zi2;
+    K::inv(zi, p.Z);
+    K::sqr(zi2, zi);
+    K::mul(x, p.X, zi2);
+    K::mul(zi2, zi2, zi);
+    K::mul(y, p.Y, zi2);
+  }
+  ARK_DM static void to_aff(Aff& a, const Pt& p) { normalize(a.x, a.y, p); }
+};
+
+// ----------------------------------------------------------------------------------------------
+// Curve25519 in twisted-Edwards form (a = -1): extended coordinates, complete unified addition
+// ----------------------------------------------------------------------------------------------
+struct PtTE { fe8 X, Y, T, Z; };
+struct CachedTE { fe8 YpX, YmX, Z2, T2d; };  // (Y+X, Y-X, 2Z, 2d*T)
+struct NielsTE { fe8 ypx, ymx, xy2d; };      // affine: (y+x, y-x, 2d*x*y)
+
+struct Ed25519 {
+  static constexpr int kId = 1;
+  using Q = Curve25519Fq;
+  using R = Curve25519Fr;
+  using Pt = PtTE;
+  using Cached = CachedTE;
+  using Aff = NielsTE;
+  using K = Fq<Q>;
+  static constexpr int kCoords = 4;
+  static constexpr int kPointBytes = 128;
+  static constexpr int kAffWords = 24;
+
+  ARK_DM static void set_2d(fe8& r) {
+    r.v[0] = 0xbe8fd3f4u; r.v[1] = 0x01db17fdu; r.v[2] = 0x5f8c52e7u; r.v[3] = 0x21430eefu;
+    r.v[4] = 0x78310d20u; r.v[5] = 0xcb27240fu; r.v[6] = 0xe53f8a4du; r.v[7] = 0x590456b4u;
+  }
+  ARK_DM static void set_identity(Pt& p) { K::zero(p.X); K::one(p.Y); K::zero(p.T); K::one(p.Z); }
+  ARK_DM static bool is_identity(const Pt& p) { return K::is_zero(p.X) && K::eq(p.Y, p.Z); }
+  ARK_DM static void set_generator(Pt& p) {  // RFC 8032 base point, Montgomery images
+    p.X.v[0] = 0x3f9da287u; p.X.v[1] = 0xe2cabc55u; p.X.v[2] = 0x2396e489u; p.X.v[3] = 0x9ca59856u;
+    p.X.v[4] = 0xade4b5b7u; p.X.v[5] = 0x9879936bu; p.X.v[6] = 0x7e6077d0u; p.X.v[7] = 0x759e2370u;
+    p.Y.v[0] = 0x3333334au;
+    ARK_UNROLL for (int j = 1; j < 8; j++) p.Y.v[j] = 0x33333333u;
+    K::one(p.Z);
+    K::mul(p.T, p.X, p.Y);
+  }
+  ARK_DM static void neg(Pt& p) { K::neg(p.X, p.X); K::neg(p.T, p.T); }
+  ARK_DM static void cache(Cached& c, const Pt& p) {
+    fe8 k;
+    set_2d(k);
+    K::add(c.YpX, p.Y, p.X);
+    K::sub(c.YmX, p.Y, p.X);
+    K::dbl(c.Z2, p.Z);
+    K::mul(c.T2d, p.T, k);
+  }
+
+  // dbl-2008-hwcd with a = -1 (4M + 4S)
+  ARK_DM static void dbl(Pt& p) {
+    fe8 A, B, C, E, G, F, H;
+    K::sqr(A, p.X);
+    K::sqr(B, p.Y);
+    K::sqr(C, p.Z);
+    K::dbl(C, C);
+    K::add(E, p.X, p.Y);
+    K::sqr(E, E);
+    K::sub(E, E, A);
+    K::sub(E, E, B);   // E = 2XY
+    K::sub(G, B, A);   // D + B with D = -A
+    K::sub(F, G, C);
+    K::add(H, A, B);
+    K::neg(H, H);      // D - B = -(A + B)
+    K::mul(p.X, E, F);
+    K::mul(p.Y, G, H);
+    K::mul(p.T, E, H);
+    K::mul(p.Z, F, G);
+  }
+
+  // add-2008-hwcd-3 against a cached operand (8M)
+  ARK_DM static void add_cached(Pt& p, const Cached& q) {
+    fe8 A, B, C, D, E, F, G, H;
+    K::sub(A, p.Y, p.X);
+    K::mul(A, A, q.YmX);
+    K::add(B, p.Y, p.X);
+    K::mul(B, B, q.YpX);
+    K::mul(C, p.T, q.T2d);
+    K::mul(D, p.Z, q.Z2);
+    K::sub(E, B, A);
+    K::sub(F, D, C);
+    K::add(G, D, C);
+    K::add(H, B, A);
+    K::mul(p.X, E, F);
+    K::mul(p.Y, G, H);
+    K::mul(p.T, E, H);
+    K::mul(p.Z, F, G);
+  }
+  ARK_DM static void add(Pt& p, const Pt& q) {
+    Cached c;
+    cache(c, q);
+    add_cached(p, c);
+  }
+  // mixed addition with an affine Niels operand (7M)
+  ARK_DM static void madd(Pt& p, const Aff& q) {
+    fe8 A, B, C, D, E, F, G, H;
+    K::sub(A, p.Y, p.X);
+    K::mul(A, A, q.ymx);
+    K::add(B, p.Y, p.X);
+    K::mul(B, B, q.ypx);
+    K::mul(C, p.T, q.xy2d);
+    K::dbl(D, p.Z);
+    K::sub(E, B, A);
+    K::sub(F, D, C);
+    K::add(G, D, C);
+    K::add(H, B, A);
+    K::mul(p.X, E, F);
+    K::mul(p.Y, G, H);
+    K::mul(p.T, E, H);
+    K::mul(p.Z, F, G);
+  }
+
+  ARK_DM static void normalize(fe8& x, fe8& y, const Pt& p) {
+    fe8 zi;
+    K::inv(zi, p.Z);
+    K::mul(x, p.X, zi);
+    K::mul(y, p.Y, zi);
+  }
+  ARK_DM static void to_aff(Aff& a, const Pt& p) {
+    fe8 x, y, k;
+    normalize(x, y, p);
+    set_2d(k);
+    K::add(a.ypx, y, x);
+    K::sub(a.ymx, y, x);
+    K::mul(a.xy2d, x, y);
+    K::mul(a.xy2d, a.xy2d, k);
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// Scalar multiplication building blocks
+// ----------------------------------------------------------------------------------------------
+constexpr int kWindows = 64;      // 4-bit windows of a 256-bit scalar
+constexpr int kTabEntries = 16;   // index 0 unused
+
+// tab[w] = w*P for w = 1..15
+template <class C>
+ARK_D void build_table(typename C::Cached* tab, const typename C::Pt& P) {
+  typename C::Pt t = P;
+  C::cache(tab[1], t);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int w = 2; w < kTabEntries; w++) {
+    C::add_cached(t, tab[1]);
+    C::cache(tab[w], t);
+  }
+}
+
+// acc = k * P from the table (acc must be the identity on entry)
+template <class C>
+ARK_D void var_mul(typename C::Pt& acc, const typename C::Cached* tab, const uint32_t* k) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int i = kWindows - 1; i >= 0; i--) {
+    if (i != kWindows - 1) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+      for (int j = 0; j < 4; j++) C::dbl(acc);
+    }
+    const uint32_t w = window4(k, i);
+    if (w) C::add_cached(acc, tab[w]);
+  }
+}
+
+// acc += k * G with the fixed-base table gtab[j*16 + w] = w * 16^j * G
+template <class C>
+ARK_D void fix_mul_acc(typename C::Pt& acc, const typename C::Aff* gtab, const uint32_t* k) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int j = 0; j < kWindows; j++) {
+    const uint32_t w = window4(k, j);
+    if (w) C::madd(acc, gtab[j * kTabEntries + w]);
+  }
+}
+
+// One row of the fixed-base table: out[w] = w * 16^j * G for w = 1..15 (out[0] unused).  Run once per context.
+template <class C>
+ARK_D void build_gtab_row(typename C::Aff* out, int j) {
+  typename C::Pt base;
+  C::set_generator(base);
+  for (int i = 0; i < 4 * j; i++) C::dbl(base);
+  typename C::Cached cb;
+  C::cache(cb, base);
+  typename C::Pt t = base;
+  C::to_aff(out[1], t);
+  for (int w = 2; w < kTabEntries; w++) {
+    C::add_cached(t, cb);
+    C::to_aff(out[w], t);
+  }
+}
+
+}  // namespace ark

@@ -1,0 +1,230 @@
+// Kernel skeletons for the point gates.  Points are read and written in the reference's AoS memory image
+// (BN254 G1Projective x,y,z = 96 B; Curve25519 EdwardsProjective x,y,t,z = 128 B; a PointShare is two consecutive
+// points {share, mac}, curve/share.rs:25-30): every coordinate is 32 bytes and 32-byte aligned, so each is one
+// LDG.256 / STG.256.  These kernels are compute-bound by three to four orders of magnitude (a scalar multiplication is
+// ~3000 base-field multiplications per ~200 bytes), so the layout is chosen for a zero-copy boundary, not for
+// coalescing.  Scalars stay planar as in fr_kernels.cuh.
+#pragma once
+#include "curve_gates.cuh"
+#include "fr_kernels.cuh"
+
+namespace ark {
+
+constexpr int kPtBlock = 128;
+
+struct PVec {
+  const char* p;
+  uint32_t stride;  // bytes between consecutive points (kPointBytes for point vectors, 2*kPointBytes inside PointShares)
+};
+struct PMVec {
+  char* p;
+  uint32_t stride;
+};
+
+template <class C>
+__device__ __forceinline__ void ld_pt(typename C::Pt& r, const PVec& v, size_t i) {
+  const Vec c{v.p + i * (size_t)v.stride, 32};
+  fe8* f = reinterpret_cast<fe8*>(&r);
+#pragma unroll
+  for (int k = 0; k < C::kCoords; k++) ld_fe(f[k], c, k);
+}
+template <class C>
+__device__ __forceinline__ void st_pt(const PMVec& v, size_t i, const typename C::Pt& r) {
+  const MVec c{v.p + i * (size_t)v.stride, 32};
+  const fe8* f = reinterpret_cast<const fe8*>(&r);
+#pragma unroll
+  for (int k = 0; k < C::kCoords; k++) st_fe(c, k, f[k]);
+}
+
+// fixed-base table: 64 rows x 16 entries, one thread per row
+template <class C>
+__global__ void __launch_bounds__(64) pt_gtab_kernel(typename C::Aff* gtab) {
+  const int j = threadIdx.x;
+  if (j < kWindows) build_gtab_row<C>(gtab + j * kTabEntries, j);
+}
+
+enum class PtBin { Add, Sub };
+
+// out[i] = a[i] (+|-) b[i]   (open-add :98-108, batch_add/batch_sub on the 2n points of n PointShares :396-465)
+template <class C, PtBin OP>
+__global__ void __launch_bounds__(kPtBlock) pt_binary_kernel(size_t n, PVec a, PVec b, PMVec out) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt x, y;
+    ld_pt<C>(x, a, i);
+    ld_pt<C>(y, b, i);
+    if (OP == PtBin::Sub) C::neg(y);
+    C::add(x, y);
+    st_pt<C>(out, i, x);
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_neg_kernel(size_t n, PVec a, PMVec out) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt x;
+    ld_pt<C>(x, a, i);
+    C::neg(x);
+    st_pt<C>(out, i, x);
+  }
+}
+
+// out[i] = s[i >> sshift] * P[i]   (CurvePointResult::batch_mul curve.rs:459-479; batch_mul_public :718-751 with
+// sshift = 1 over the 2n points of n PointShares)
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_mul_kernel(size_t n, Vec s, int sshift, PVec P, PMVec out) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt x, r;
+    fe8 k;
+    ld_pt<C>(x, P, i);
+    ld_fe(k, s, i >> sshift);
+    pt_mul_elem<C>(r, k, x);
+    st_pt<C>(out, i, r);
+  }
+}
+
+// out[i] = (s_share[i] * P[i], s_mac[i] * P[i])   (batch_mul_authenticated curve.rs:483-517)
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_mul_auth_kernel(size_t n, Vec s_share, Vec s_mac, PVec P, PMVec out_s, PMVec out_m) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt x, r0, r1;
+    fe8 k0, k1;
+    ld_pt<C>(x, P, i);
+    ld_fe(k0, s_share, i);
+    ld_fe(k1, s_mac, i);
+    pt_mul2_elem<C>(r0, r1, k0, k1, x);
+    st_pt<C>(out_s, i, r0);
+    st_pt<C>(out_m, i, r1);
+  }
+}
+
+// out[i] = s[i] * G   (batch_mul_generator :754-780, one launch per plane)
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_mul_gen_kernel(size_t n, Vec s, const typename C::Aff* __restrict__ gtab, PMVec out) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt r;
+    fe8 k;
+    ld_fe(k, s, i);
+    pt_mul_gen_elem<C>(r, k, gtab);
+    st_pt<C>(out, i, r);
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_share_add_public_kernel(size_t n, int party, int sub, fe8 key, PVec a_s, PVec a_m, PVec pub,
+                                                                     PMVec out_s, PMVec out_m) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt s, m, P, os, om;
+    ld_pt<C>(s, a_s, i);
+    ld_pt<C>(m, a_m, i);
+    ld_pt<C>(P, pub, i);
+    pt_share_add_public_elem<C>(os, om, party, sub != 0, key, s, m, P);
+    st_pt<C>(out_s, i, os);
+    st_pt<C>(out_m, i, om);
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_mac_check_kernel(size_t n, fe8 key, PVec opened, PVec mac, PMVec out) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt o, m, r;
+    ld_pt<C>(o, opened, i);
+    ld_pt<C>(m, mac, i);
+    pt_mac_check_elem<C>(r, key, o, m);
+    st_pt<C>(out, i, r);
+  }
+}
+
+// flag (initialised to 1) is cleared if any mine[i] + peer[i] is not the identity (:128-131)
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_sum_is_identity_kernel(size_t n, PVec mine, PVec peer, int* flag) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  bool ok = true;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt x, y;
+    ld_pt<C>(x, mine, i);
+    ld_pt<C>(y, peer, i);
+    C::add(x, y);
+    ok = ok && C::is_identity(x);
+  }
+  if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(flag, 0);
+}
+
+// affine (x, y), 64 B per point; parity with the reference is defined on this form
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_normalize_kernel(size_t n, PVec a, MVec out_x, MVec out_y) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt p;
+    fe8 x, y;
+    ld_pt<C>(p, a, i);
+    C::normalize(x, y, p);
+    st_fe(out_x, i, x);
+    st_fe(out_y, i, y);
+  }
+}
+
+// Point Beaver phase 1
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_beaver_mask_kernel(size_t n, Vec x_s, Vec a_s, Vec b_s, PVec P_s,
+                                                                 const typename C::Aff* __restrict__ gtab, MVec d_mine, PMVec E_mine) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    fe8 xs, as, bs, dm;
+    typename C::Pt P, E;
+    ld_fe(xs, x_s, i);
+    ld_fe(as, a_s, i);
+    ld_fe(bs, b_s, i);
+    ld_pt<C>(P, P_s, i);
+    pt_beaver_mask_elem<C>(dm, E, xs, as, bs, P, gtab);
+    st_fe(d_mine, i, dm);
+    st_pt<C>(E_mine, i, E);
+  }
+}
+
+// Point Beaver phase 2 (open-add of d and E fused with the recombination)
+struct PtRecombineArgs {
+  Vec d_mine, d_peer;
+  PVec E_mine, E_peer;
+  Vec a_s, a_m, b_s, b_m, c_s, c_m;
+  PMVec out_s, out_m;
+  MVec d_open;
+  PMVec E_open;
+  fe8 key;
+  int party;
+  int open;
+};
+
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_beaver_recombine_kernel(size_t n, const __grid_constant__ PtRecombineArgs g,
+                                                                      const typename C::Aff* __restrict__ gtab) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    fe8 dm, dp, as, am, bs, bm, cs, cm, d;
+    typename C::Pt Em, Ep, E;
+    ld_fe(dm, g.d_mine, i);
+    ld_fe(dp, g.d_peer, i);
+    ld_pt<C>(Em, g.E_mine, i);
+    ld_pt<C>(Ep, g.E_peer, i);
+    ld_fe(as, g.a_s, i);
+    ld_fe(am, g.a_m, i);
+    ld_fe(bs, g.b_s, i);
+    ld_fe(bm, g.b_m, i);
+    ld_fe(cs, g.c_s, i);
+    ld_fe(cm, g.c_m, i);
+    pt_beaver_recombine_elem<C>(d, E, g.party, g.key, dm, dp, Em, Ep, as, am, bs, bm, cs, cm, gtab,
+                                [&](int which, const typename C::Pt& r) { st_pt<C>(which ? g.out_m : g.out_s, i, r); });
+    if (g.open) {
+      st_fe(g.d_open, i, d);
+      st_pt<C>(g.E_open, i, E);
+    }
+  }
+}
+
+}  // namespace ark

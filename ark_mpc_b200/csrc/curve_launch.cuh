@@ -1,0 +1,153 @@
+// Internal: templated launch wrappers of the point kernels and the per-curve dispatch table.  Each curve is
+// instantiated in its own translation unit (curve_bn254.cu, curve_ed25519.cu) so the two compile in parallel;
+// arkmpc_curve.cu holds the C ABI and dispatches through `CurveOps`.
+#pragma once
+#include "ctx.hpp"
+
+namespace arkctx {
+
+struct CurveOps {
+  uint32_t point_bytes;
+  int (*binary)(arkmpc_ctx*, size_t n, const void* a, const void* b, void* out, int sub);
+  int (*neg)(arkmpc_ctx*, size_t n, const void* a, void* out);
+  int (*share_add_public)(arkmpc_ctx*, int party, int sub, const ark::fe8& key, size_t n, const void* a_ps, const void* pub, void* out_ps);
+  int (*mul)(arkmpc_ctx*, size_t n_points, const void* scalars, int sshift, const void* pts, void* out);
+  int (*mul_auth)(arkmpc_ctx*, size_t n, const void* s_share, const void* s_mac, const void* pts, void* out_ps);
+  int (*mul_gen)(arkmpc_ctx*, size_t n, const void* scalars, void* out, uint32_t out_stride);
+  int (*beaver_mask)(arkmpc_ctx*, size_t n, const void* x_share, const void* P_ps, const void* a_share, const void* b_share, void* d_mine, void* E_mine);
+  int (*beaver_recombine)(arkmpc_ctx*, int party, const ark::fe8& key, size_t n, const void* d_mine, const void* d_peer, const void* E_mine,
+                          const void* E_peer, const void* a_s, const void* a_m, const void* b_s, const void* b_m, const void* c_s,
+                          const void* c_m, void* out_ps, void* d_open, void* E_open);
+  int (*mac_check)(arkmpc_ctx*, const ark::fe8& key, size_t n, const void* opened, const void* a_ps, void* check);
+  int (*sum_is_identity)(arkmpc_ctx*, size_t n, const void* mine, const void* peer, int* flag_dev);
+  int (*normalize)(arkmpc_ctx*, size_t n, const void* pts, void* out_xy);
+};
+
+const CurveOps* curve_ops_bn254();
+const CurveOps* curve_ops_ed25519();
+
+}  // namespace arkctx
+
+#ifdef ARK_CURVE_IMPL
+#include "curve_kernels.cuh"
+
+namespace arkctx {
+using namespace ark;
+
+inline PVec pvec(const void* p, uint32_t stride) { return PVec{static_cast<const char*>(p), stride}; }
+inline PMVec pmvec(void* p, uint32_t stride) { return PMVec{static_cast<char*>(p), stride}; }
+inline unsigned pt_grid(const arkmpc_ctx* ctx, size_t n, int blocks_per_sm) { return grid_for(ctx, n, blocks_per_sm, kPtBlock); }
+
+template <class C>
+struct CurveLaunch {
+  using Aff = typename C::Aff;
+  static constexpr uint32_t PB = C::kPointBytes;
+
+  // Fixed-base table of the generator, built on first use and kept for the life of the context.
+  static int gtab(arkmpc_ctx* ctx, const Aff** out) {
+    std::lock_guard<std::mutex> lock(ctx->gtab_mutex);
+    void*& slot = ctx->gtab[C::kId];
+    if (!slot) {
+      void* mem = nullptr;
+      ARK_CUDA(ctx, cudaMalloc(&mem, sizeof(Aff) * kWindows * kTabEntries));
+      cudaError_t e = cudaMemsetAsync(mem, 0, sizeof(Aff) * kWindows * kTabEntries, ctx->stream);
+      if (e == cudaSuccess) {
+        pt_gtab_kernel<C><<<1, 64, 0, ctx->stream>>>(static_cast<Aff*>(mem));
+        ctx->launches++;
+        e = cudaGetLastError();
+      }
+      // other streams may read the table later: finish it before publishing the pointer
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) {
+        cudaFree(mem);
+        return fail(ctx, ARKMPC_ERR_CUDA, std::string("fixed-base table: ") + cudaGetErrorString(e));
+      }
+      slot = mem;
+    }
+    *out = static_cast<const Aff*>(slot);
+    return ARKMPC_OK;
+  }
+
+  static int binary(arkmpc_ctx* ctx, size_t n, const void* a, const void* b, void* out, int sub) {
+    if (sub) pt_binary_kernel<C, PtBin::Sub><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, pvec(a, PB), pvec(b, PB), pmvec(out, PB));
+    else pt_binary_kernel<C, PtBin::Add><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, pvec(a, PB), pvec(b, PB), pmvec(out, PB));
+    return post_launch(ctx, "pt_binary_kernel");
+  }
+  static int neg(arkmpc_ctx* ctx, size_t n, const void* a, void* out) {
+    pt_neg_kernel<C><<<pt_grid(ctx, n, 8), kPtBlock, 0, ctx->stream>>>(n, pvec(a, PB), pmvec(out, PB));
+    return post_launch(ctx, "pt_neg_kernel");
+  }
+  static int share_add_public(arkmpc_ctx* ctx, int party, int sub, const fe8& key, size_t n, const void* a_ps, const void* pub, void* out_ps) {
+    const char* a = static_cast<const char*>(a_ps);
+    char* o = static_cast<char*>(out_ps);
+    pt_share_add_public_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, party, sub, key, pvec(a, 2 * PB), pvec(a + PB, 2 * PB), pvec(pub, PB),
+                                                                                  pmvec(o, 2 * PB), pmvec(o + PB, 2 * PB));
+    return post_launch(ctx, "pt_share_add_public_kernel");
+  }
+  static int mul(arkmpc_ctx* ctx, size_t n_points, const void* scalars, int sshift, const void* pts, void* out) {
+    pt_mul_kernel<C><<<pt_grid(ctx, n_points, 2), kPtBlock, 0, ctx->stream>>>(n_points, vec(scalars), sshift, pvec(pts, PB), pmvec(out, PB));
+    return post_launch(ctx, "pt_mul_kernel");
+  }
+  static int mul_auth(arkmpc_ctx* ctx, size_t n, const void* s_share, const void* s_mac, const void* pts, void* out_ps) {
+    char* o = static_cast<char*>(out_ps);
+    pt_mul_auth_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, vec(s_share), vec(s_mac), pvec(pts, PB), pmvec(o, 2 * PB), pmvec(o + PB, 2 * PB));
+    return post_launch(ctx, "pt_mul_auth_kernel");
+  }
+  static int mul_gen(arkmpc_ctx* ctx, size_t n, const void* scalars, void* out, uint32_t out_stride) {
+    const Aff* g;
+    int rc = gtab(ctx, &g);
+    if (rc != ARKMPC_OK) return rc;
+    pt_mul_gen_kernel<C><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, vec(scalars), g, pmvec(out, out_stride));
+    return post_launch(ctx, "pt_mul_gen_kernel");
+  }
+  static int beaver_mask(arkmpc_ctx* ctx, size_t n, const void* x_share, const void* P_ps, const void* a_share, const void* b_share, void* d_mine,
+                         void* E_mine) {
+    const Aff* g;
+    int rc = gtab(ctx, &g);
+    if (rc != ARKMPC_OK) return rc;
+    pt_beaver_mask_kernel<C><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, vec(x_share), vec(a_share), vec(b_share), pvec(P_ps, 2 * PB), g,
+                                                                             mvec(d_mine), pmvec(E_mine, PB));
+    return post_launch(ctx, "pt_beaver_mask_kernel");
+  }
+  static int beaver_recombine(arkmpc_ctx* ctx, int party, const fe8& key, size_t n, const void* d_mine, const void* d_peer, const void* E_mine,
+                              const void* E_peer, const void* a_s, const void* a_m, const void* b_s, const void* b_m, const void* c_s,
+                              const void* c_m, void* out_ps, void* d_open, void* E_open) {
+    const Aff* gt;
+    int rc = gtab(ctx, &gt);
+    if (rc != ARKMPC_OK) return rc;
+    char* o = static_cast<char*>(out_ps);
+    PtRecombineArgs g;
+    g.d_mine = vec(d_mine); g.d_peer = vec(d_peer);
+    g.E_mine = pvec(E_mine, PB); g.E_peer = pvec(E_peer, PB);
+    g.a_s = vec(a_s); g.a_m = vec(a_m); g.b_s = vec(b_s); g.b_m = vec(b_m); g.c_s = vec(c_s); g.c_m = vec(c_m);
+    g.out_s = pmvec(o, 2 * PB); g.out_m = pmvec(o + PB, 2 * PB);
+    g.d_open = mvec(d_open); g.E_open = pmvec(E_open, PB);
+    g.key = key;
+    g.party = party;
+    g.open = d_open != nullptr;
+    pt_beaver_recombine_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, g, gt);
+    return post_launch(ctx, "pt_beaver_recombine_kernel");
+  }
+  static int mac_check(arkmpc_ctx* ctx, const fe8& key, size_t n, const void* opened, const void* a_ps, void* check) {
+    const char* a = static_cast<const char*>(a_ps);
+    pt_mac_check_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, key, pvec(opened, PB), pvec(a + PB, 2 * PB), pmvec(check, PB));
+    return post_launch(ctx, "pt_mac_check_kernel");
+  }
+  static int sum_is_identity(arkmpc_ctx* ctx, size_t n, const void* mine, const void* peer, int* flag_dev) {
+    pt_sum_is_identity_kernel<C><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, pvec(mine, PB), pvec(peer, PB), flag_dev);
+    return post_launch(ctx, "pt_sum_is_identity_kernel");
+  }
+  static int normalize(arkmpc_ctx* ctx, size_t n, const void* pts, void* out_xy) {
+    char* o = static_cast<char*>(out_xy);
+    pt_normalize_kernel<C><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, pvec(pts, PB), mvec(o, 64), mvec(o + 32, 64));
+    return post_launch(ctx, "pt_normalize_kernel");
+  }
+
+  static const CurveOps* ops() {
+    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, normalize};
+    return &t;
+  }
+};
+
+}  // namespace arkctx
+#endif  // ARK_CURVE_IMPL

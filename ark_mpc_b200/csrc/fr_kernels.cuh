@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kBlock) fr_sum_kernel(size_t n, Vec a0, Vec a1
 // ---------------------------------------------------------------------------------------------
 // Layout conversion and synthetic data
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) copy_planes_kernel(size_t n, Vec in_s, Vec in_m, MVec out_s, MVec out_m) {
+static __global__ void __launch_bounds__(kBlock) copy_planes_kernel(size_t n, Vec in_s, Vec in_m, MVec out_s, MVec out_m) {
   const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
     fe8 s, m;

@@ -214,6 +214,112 @@ class Engine:
         self._call("arkmpc_fr_sum", self.field, a.shape[0], self._p(a), self._p(o))
         return o
 
+    # -- point gates (points: int64 tensors (n, words) in the reference's AoS projective image;
+    #    PointShares: (n, 2*words) = {share, mac}) ------------------------------------------------
+    def bind_curve(self, curve: str) -> None:
+        """Select the curve group for the pt_* calls; its scalar field must be this engine's field."""
+        cid = nat.CURVE_IDS[curve]
+        if cid != self.field:
+            raise ValueError(f"curve {curve} does not match the engine's scalar field {self.field_name}")
+        self.curve = cid
+        self.point_words = int(self.lib.arkmpc_point_bytes(cid)) // 8
+
+    def _curve(self) -> int:
+        if getattr(self, "curve", None) is None:
+            self.bind_curve({0: "bn254_g1", 1: "curve25519_edwards"}[self.field])
+        return self.curve
+
+    def empty_points(self, n: int, share: bool = False) -> torch.Tensor:
+        self._curve()
+        return torch.empty((n, self.point_words * (2 if share else 1)), dtype=torch.int64, device=self.tdev)
+
+    def upload_points(self, limbs: np.ndarray) -> torch.Tensor:
+        a = np.ascontiguousarray(limbs, dtype=np.uint64)
+        return torch.from_numpy(a.view(np.int64)).to(self.tdev)
+
+    def _pt_binary(self, name, a, b):
+        out = torch.empty_like(a)
+        n = a.numel() * 8 // int(self.lib.arkmpc_point_bytes(self._curve()))
+        self._call(name, self.curve, n, self._p(a), self._p(b), self._p(out))
+        return out
+
+    def pt_add(self, a, b): return self._pt_binary("arkmpc_pt_add", a, b)      # also PointShare + PointShare (2n points)
+    def pt_sub(self, a, b): return self._pt_binary("arkmpc_pt_sub", a, b)
+
+    def pt_neg(self, a):
+        out = torch.empty_like(a)
+        n = a.numel() * 8 // int(self.lib.arkmpc_point_bytes(self._curve()))
+        self._call("arkmpc_pt_neg", self.curve, n, self._p(a), self._p(out))
+        return out
+
+    def pt_share_add_public(self, party: int, key, a_ps, pub, sub: bool = False):
+        out = torch.empty_like(a_ps)
+        k = self.key_limbs(key)
+        name = "arkmpc_pt_share_sub_public" if sub else "arkmpc_pt_share_add_public"
+        self._call(name, self._curve(), int(party), k.ctypes.data_as(C.c_void_p), pub.shape[0], self._p(a_ps), self._p(pub), self._p(out))
+        return out
+
+    def pt_mul(self, scalars, pts):
+        out = torch.empty_like(pts)
+        self._call("arkmpc_pt_mul", self._curve(), pts.shape[0], self._p(scalars), self._p(pts), self._p(out))
+        return out
+
+    def pt_share_mul_public(self, scalars, a_ps):
+        out = torch.empty_like(a_ps)
+        self._call("arkmpc_pt_share_mul_public", self._curve(), a_ps.shape[0], self._p(scalars), self._p(a_ps), self._p(out))
+        return out
+
+    def pt_mul_authenticated(self, s: Planes, pts):
+        out = self.empty_points(pts.shape[0], share=True)
+        self._call("arkmpc_pt_mul_authenticated", self._curve(), pts.shape[0], self._p(s[0]), self._p(s[1]), self._p(pts), self._p(out))
+        return out
+
+    def pt_mul_generator(self, s: Planes):
+        out = self.empty_points(s[0].shape[0], share=True)
+        self._call("arkmpc_pt_mul_generator", self._curve(), s[0].shape[0], self._p(s[0]), self._p(s[1]), self._p(out))
+        return out
+
+    def pt_mul_generator_public(self, scalars):
+        out = self.empty_points(scalars.shape[0])
+        self._call("arkmpc_pt_mul_generator_public", self._curve(), scalars.shape[0], self._p(scalars), self._p(out))
+        return out
+
+    def pt_beaver_mask(self, x_share, P_ps, a_share, b_share, out=None):
+        n = x_share.shape[0]
+        d, E = out if out is not None else (self.empty(n), self.empty_points(n))
+        self._call("arkmpc_pt_beaver_mask", self._curve(), n, self._p(x_share), self._p(P_ps), self._p(a_share), self._p(b_share),
+                   self._p(d), self._p(E))
+        return d, E
+
+    def pt_beaver_recombine(self, party: int, key, d_mine, d_peer, E_mine, E_peer, a: Planes, b: Planes, c: Planes, out=None,
+                            want_open: bool = False):
+        n = d_mine.shape[0]
+        out = out if out is not None else self.empty_points(n, share=True)
+        d_o, E_o = (self.empty(n), self.empty_points(n)) if want_open else (None, None)
+        k = self.key_limbs(key)
+        self._call("arkmpc_pt_beaver_recombine", self._curve(), int(party), k.ctypes.data_as(C.c_void_p), n, self._p(d_mine), self._p(d_peer),
+                   self._p(E_mine), self._p(E_peer), self._p(a[0]), self._p(a[1]), self._p(b[0]), self._p(b[1]), self._p(c[0]), self._p(c[1]),
+                   self._p(out), self._p(d_o), self._p(E_o))
+        return out, (d_o, E_o)
+
+    def pt_mac_check(self, key, opened, a_ps):
+        out = torch.empty_like(opened)
+        k = self.key_limbs(key)
+        self._call("arkmpc_pt_mac_check", self._curve(), k.ctypes.data_as(C.c_void_p), opened.shape[0], self._p(opened), self._p(a_ps), self._p(out))
+        return out
+
+    def pt_sum_is_identity(self, mine, peer) -> bool:
+        flag = C.c_int(0)
+        self._call("arkmpc_pt_sum_is_identity", self._curve(), mine.shape[0], self._p(mine), self._p(peer), C.byref(flag))
+        return bool(flag.value)
+
+    def pt_normalize(self, pts) -> torch.Tensor:
+        """(n, words) projective -> (n, 8) canonical affine (x, y) Montgomery limbs."""
+        n = pts.numel() * 8 // int(self.lib.arkmpc_point_bytes(self._curve()))
+        out = torch.empty((n, 8), dtype=torch.int64, device=self.tdev)
+        self._call("arkmpc_pt_normalize", self.curve, n, self._p(pts), self._p(out))
+        return out
+
     # -- layout ---------------------------------------------------------------------------------
     def share_unzip(self, aos: torch.Tensor) -> Planes:
         """(n, 8) AoS ScalarShare image -> (share, mac) planes."""

@@ -156,6 +156,58 @@ int arkmpc_fr_from_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* mo
  * (`Scalar::random` stand-in for benches, scalar.rs:76-78); identical to oracle synth generators. */
 int arkmpc_fr_random(arkmpc_ctx* ctx, int field, uint64_t seed, uint64_t first_index, size_t n, uint64_t* out);
 
+/* ---- point gates (algebra/curve/authenticated_curve.rs, curve/share.rs, curve/curve.rs) ----
+ * Points are DEVICE arrays in the reference's AoS memory image: BN254 `G1Projective` {x,y,z} = 96 B (Jacobian,
+ * identity z = 0); Curve25519 `EdwardsProjective` {x,y,t,z} = 128 B (extended twisted Edwards); every coordinate a
+ * canonical Montgomery residue of the base field.  A vector of n `PointShare`s (curve/share.rs:25-30) is n consecutive
+ * {share, mac} point pairs (`*_ps` arguments, 2n points).  Scalars / scalar shares are planes as above.
+ * Projective outputs are valid representatives, not necessarily arkworks' (curve.rs:46 compares projectively);
+ * arkmpc_pt_normalize gives the canonical affine form parity is defined on.  Precondition of the fused Beaver
+ * recombination: points lie in the prime-order subgroup (multiples of the generator), as every honestly shared
+ * point does.  All arrays must be 32-byte aligned. */
+size_t arkmpc_point_bytes(int curve); /* 96 / 128; 0 for an unknown curve */
+
+/* CurvePointResult + CurvePointResult, the open-add (:98-108), and on 2n points AuthenticatedPointResult::batch_add /
+ * batch_sub (:396-421, :520-545): out[i] = a[i] +/- b[i] */
+int arkmpc_pt_add(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_pts, const uint64_t* b_pts, uint64_t* out_pts);
+int arkmpc_pt_sub(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_pts, const uint64_t* b_pts, uint64_t* out_pts);
+int arkmpc_pt_neg(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_pts, uint64_t* out_pts); /* batch_neg :604-621 */
+/* batch_add_public / batch_sub_public (:429-465, :553-590; curve/share.rs:57-65) */
+int arkmpc_pt_share_add_public(arkmpc_ctx* ctx, int curve, int party_id, const uint64_t* key_host, size_t n,
+                               const uint64_t* a_ps, const uint64_t* pub_pts, uint64_t* out_ps);
+int arkmpc_pt_share_sub_public(arkmpc_ctx* ctx, int curve, int party_id, const uint64_t* key_host, size_t n,
+                               const uint64_t* a_ps, const uint64_t* pub_pts, uint64_t* out_ps);
+/* CurvePointResult::batch_mul (curve.rs:459-479): out[i] = s[i] * P[i] */
+int arkmpc_pt_mul(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* scalars, const uint64_t* pts, uint64_t* out_pts);
+/* AuthenticatedPointResult::batch_mul_public (:718-751): out[i] = (s[i]*share[i], s[i]*mac[i]) */
+int arkmpc_pt_share_mul_public(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* scalars, const uint64_t* a_ps, uint64_t* out_ps);
+/* CurvePointResult::batch_mul_authenticated (curve.rs:483-517): out[i] = (s_share[i]*P[i], s_mac[i]*P[i]) */
+int arkmpc_pt_mul_authenticated(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* s_share, const uint64_t* s_mac,
+                                const uint64_t* pts, uint64_t* out_ps);
+/* batch_mul_generator (:754-780): out[i] = (s_share[i]*G, s_mac[i]*G); arkmpc_pt_mul_generator_public: out[i] = s[i]*G */
+int arkmpc_pt_mul_generator(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* s_share, const uint64_t* s_mac, uint64_t* out_ps);
+int arkmpc_pt_mul_generator_public(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* scalars, uint64_t* out_pts);
+
+/* AuthenticatedPointResult::batch_mul (:682-714), phase 1: d_mine = x.share - a.share (scalar plane),
+ * E_mine = P.share - b.share*G (n points; what open_batch sends, :66-109). */
+int arkmpc_pt_beaver_mask(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* x_share, const uint64_t* P_ps,
+                          const uint64_t* a_share, const uint64_t* b_share, uint64_t* d_mine, uint64_t* E_mine_pts);
+/* phase 2: d = d_mine + d_peer, E = E_mine + E_peer, out = d*E (public, add_public) + d*[bG] + [a]*E + [c]*G as n
+ * PointShares.  d_open / E_open_pts optional (both or neither). */
+int arkmpc_pt_beaver_recombine(arkmpc_ctx* ctx, int curve, int party_id, const uint64_t* key_host, size_t n,
+                               const uint64_t* d_mine, const uint64_t* d_peer, const uint64_t* E_mine_pts, const uint64_t* E_peer_pts,
+                               const uint64_t* a_share, const uint64_t* a_mac, const uint64_t* b_share, const uint64_t* b_mac,
+                               const uint64_t* c_share, const uint64_t* c_mac, uint64_t* out_ps,
+                               uint64_t* d_open, uint64_t* E_open_pts);
+
+/* open_authenticated_batch on points (:193-283): check[i] = key * opened[i] - mac_i (mac_i from the PointShare vector) */
+int arkmpc_pt_mac_check(arkmpc_ctx* ctx, int curve, const uint64_t* key_host, size_t n, const uint64_t* opened_pts,
+                        const uint64_t* a_ps, uint64_t* check_pts);
+/* *all_identity_host = 1 iff mine[i] + peer[i] is the identity for every i (:128-131).  Synchronous. */
+int arkmpc_pt_sum_is_identity(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* mine_pts, const uint64_t* peer_pts, int* all_identity_host);
+/* Canonical affine form: out_xy[i] = (x, y) Montgomery, 64 B; the BN254 identity maps to (0,0), the Edwards identity is (0,1). */
+int arkmpc_pt_normalize(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, uint64_t* out_xy);
+
 /* ---- end-to-end over HOST buffers (reference AoS images), both protocol phases ----
  * begin: uploads x, y and the triple (a, b, c) (n ScalarShares each, AoS, host), runs the mask kernel and
  *        writes this party's d_mine || e_mine (2n scalars) to de_mine_host.  Synchronous on return.

@@ -333,3 +333,249 @@ int orc_two_party_batch_mul(int f, size_t n, int threads, const uint64_t* key0, 
   for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
   return 0;
 }
+
+/* ====================================================================================================
+ * Curve groups and the point Beaver multiplication (AuthenticatedPointResult::batch_mul,
+ * algebra/curve/authenticated_curve.rs:682-714) in the reference's UNFUSED form: 4 fixed-base and 6
+ * variable-base scalar multiplications per element and party, each a per-element MSB-first double-and-add
+ * as ark-ec 0.4 `Projective * ScalarField` does (curve.rs:403-409 -> `mul_bigint`; crate not vendored).
+ * Memory images: BN254 G1Projective {x,y,z} Jacobian (identity z = 0); Curve25519 EdwardsProjective
+ * {x,y,t,z} extended twisted Edwards, a = -1.  Coordinates are Montgomery residues of the base field.
+ * Projective representatives are not canonical; orc_pt_normalize gives the affine form results are compared on.
+ * ==================================================================================================== */
+typedef struct { fe c[4]; } pt_t; /* x,y,z,(unused) for curve 0 ; x,y,t,z for curve 1 */
+typedef struct { int fq, fr, ncoord; } curve_t;
+static const curve_t CURVES[2] = {{2, 0, 3}, {3, 1, 4}};
+int orc_point_words(int curve) { return CURVES[curve].ncoord * 4; }
+
+static const fe ED_2D = {{0x01db17fdbe8fd3f4ull, 0x21430eef5f8c52e7ull, 0xcb27240f78310d20ull, 0x590456b4e53f8a4dull}}; /* 2d * R mod p */
+static const fe ED_GX = {{0xe2cabc553f9da287ull, 0x9ca598562396e489ull, 0x9879936bade4b5b7ull, 0x759e23707e6077d0ull}};
+static const fe ED_GY = {{0x333333333333334aull, 0x3333333333333333ull, 0x3333333333333333ull, 0x3333333333333333ull}};
+
+static inline int fe_is_zero(const fe* a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0; }
+static inline int fe_eq(const fe* a, const fe* b) { return a->l[0] == b->l[0] && a->l[1] == b->l[1] && a->l[2] == b->l[2] && a->l[3] == b->l[3]; }
+static void fe_inv(const field_t* F, fe* r, const fe* a) { /* Fermat */
+  fe e = F->p, acc = F->r;
+  e.l[0] -= 2;
+  for (int i = 255; i >= 0; i--) {
+    fe_mul(F, &acc, &acc, &acc);
+    if ((e.l[i >> 6] >> (i & 63)) & 1) fe_mul(F, &acc, &acc, a);
+  }
+  *r = acc;
+}
+
+static void pt_identity(int cv, pt_t* p) {
+  const field_t* F = &FIELDS[CURVES[cv].fq];
+  memset(p, 0, sizeof *p);
+  if (cv == 0) { p->c[0] = F->r; p->c[1] = F->r; }           /* (1,1,0) */
+  else { p->c[1] = F->r; p->c[3] = F->r; }                    /* (0,1,0,1) */
+}
+static void pt_generator(int cv, pt_t* p) {
+  const field_t* F = &FIELDS[CURVES[cv].fq];
+  memset(p, 0, sizeof *p);
+  if (cv == 0) { p->c[0] = F->r; fe_add(F, &p->c[1], &F->r, &F->r); p->c[2] = F->r; }
+  else { p->c[0] = ED_GX; p->c[1] = ED_GY; fe_mul(F, &p->c[2], &ED_GX, &ED_GY); p->c[3] = F->r; }
+}
+static int pt_is_identity(int cv, const pt_t* p) {
+  if (cv == 0) return fe_is_zero(&p->c[2]);
+  return fe_is_zero(&p->c[0]) && fe_eq(&p->c[1], &p->c[3]);
+}
+static void pt_neg(int cv, pt_t* r, const pt_t* p) {
+  const field_t* F = &FIELDS[CURVES[cv].fq];
+  *r = *p;
+  if (cv == 0) fe_neg(F, &r->c[1], &p->c[1]);
+  else { fe_neg(F, &r->c[0], &p->c[0]); fe_neg(F, &r->c[2], &p->c[2]); }
+}
+static void pt_dbl(int cv, pt_t* r, const pt_t* p) {
+  const field_t* F = &FIELDS[CURVES[cv].fq];
+  if (cv == 0) { /* dbl-2009-l */
+    fe A, B, C, D, E, G, t, X3, Y3, Z3;
+    fe_mul(F, &A, &p->c[0], &p->c[0]); fe_mul(F, &B, &p->c[1], &p->c[1]); fe_mul(F, &C, &B, &B);
+    fe_add(F, &t, &p->c[0], &B); fe_mul(F, &t, &t, &t); fe_sub(F, &t, &t, &A); fe_sub(F, &t, &t, &C); fe_add(F, &D, &t, &t);
+    fe_add(F, &E, &A, &A); fe_add(F, &E, &E, &A); fe_mul(F, &G, &E, &E);
+    fe_add(F, &t, &D, &D); fe_sub(F, &X3, &G, &t);
+    fe_sub(F, &t, &D, &X3); fe_mul(F, &t, &E, &t);
+    fe_add(F, &C, &C, &C); fe_add(F, &C, &C, &C); fe_add(F, &C, &C, &C); fe_sub(F, &Y3, &t, &C);
+    fe_mul(F, &Z3, &p->c[1], &p->c[2]); fe_add(F, &Z3, &Z3, &Z3);
+    r->c[0] = X3; r->c[1] = Y3; r->c[2] = Z3;
+  } else { /* dbl-2008-hwcd, a = -1 */
+    fe A, B, C, E, G, Fv, H, t;
+    fe_mul(F, &A, &p->c[0], &p->c[0]); fe_mul(F, &B, &p->c[1], &p->c[1]); fe_mul(F, &C, &p->c[3], &p->c[3]); fe_add(F, &C, &C, &C);
+    fe_add(F, &t, &p->c[0], &p->c[1]); fe_mul(F, &E, &t, &t); fe_sub(F, &E, &E, &A); fe_sub(F, &E, &E, &B);
+    fe_sub(F, &G, &B, &A); fe_sub(F, &Fv, &G, &C); fe_add(F, &H, &A, &B); fe_neg(F, &H, &H);
+    fe_mul(F, &r->c[0], &E, &Fv); fe_mul(F, &r->c[1], &G, &H); fe_mul(F, &r->c[2], &E, &H); fe_mul(F, &r->c[3], &Fv, &G);
+  }
+}
+static void pt_add(int cv, pt_t* r, const pt_t* p, const pt_t* q) {
+  const field_t* F = &FIELDS[CURVES[cv].fq];
+  if (cv == 0) { /* add-2007-bl with the exceptional cases */
+    if (pt_is_identity(cv, q)) { *r = *p; return; }
+    if (pt_is_identity(cv, p)) { *r = *q; return; }
+    fe Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, rr, V, t, X3, Y3, Z3;
+    fe_mul(F, &Z1Z1, &p->c[2], &p->c[2]); fe_mul(F, &Z2Z2, &q->c[2], &q->c[2]);
+    fe_mul(F, &U1, &p->c[0], &Z2Z2); fe_mul(F, &U2, &q->c[0], &Z1Z1);
+    fe_mul(F, &S1, &p->c[1], &q->c[2]); fe_mul(F, &S1, &S1, &Z2Z2);
+    fe_mul(F, &S2, &q->c[1], &p->c[2]); fe_mul(F, &S2, &S2, &Z1Z1);
+    fe_sub(F, &H, &U2, &U1); fe_sub(F, &rr, &S2, &S1);
+    if (fe_is_zero(&H)) { if (fe_is_zero(&rr)) pt_dbl(cv, r, p); else pt_identity(cv, r); return; }
+    fe_add(F, &rr, &rr, &rr); fe_add(F, &I, &H, &H); fe_mul(F, &I, &I, &I); fe_mul(F, &J, &H, &I); fe_mul(F, &V, &U1, &I);
+    fe_mul(F, &X3, &rr, &rr); fe_sub(F, &X3, &X3, &J); fe_add(F, &t, &V, &V); fe_sub(F, &X3, &X3, &t);
+    fe_sub(F, &t, &V, &X3); fe_mul(F, &Y3, &rr, &t); fe_mul(F, &t, &S1, &J); fe_add(F, &t, &t, &t); fe_sub(F, &Y3, &Y3, &t);
+    fe_add(F, &t, &p->c[2], &q->c[2]); fe_mul(F, &t, &t, &t); fe_sub(F, &t, &t, &Z1Z1); fe_sub(F, &t, &t, &Z2Z2); fe_mul(F, &Z3, &t, &H);
+    r->c[0] = X3; r->c[1] = Y3; r->c[2] = Z3;
+  } else { /* add-2008-hwcd-3, complete */
+    fe A, B, C, D, E, Fv, G, H, t, u;
+    fe_sub(F, &t, &p->c[1], &p->c[0]); fe_sub(F, &u, &q->c[1], &q->c[0]); fe_mul(F, &A, &t, &u);
+    fe_add(F, &t, &p->c[1], &p->c[0]); fe_add(F, &u, &q->c[1], &q->c[0]); fe_mul(F, &B, &t, &u);
+    fe_mul(F, &C, &p->c[2], &q->c[2]); fe_mul(F, &C, &C, &ED_2D);
+    fe_mul(F, &D, &p->c[3], &q->c[3]); fe_add(F, &D, &D, &D);
+    fe_sub(F, &E, &B, &A); fe_sub(F, &Fv, &D, &C); fe_add(F, &G, &D, &C); fe_add(F, &H, &B, &A);
+    fe_mul(F, &r->c[0], &E, &Fv); fe_mul(F, &r->c[1], &G, &H); fe_mul(F, &r->c[2], &E, &H); fe_mul(F, &r->c[3], &Fv, &G);
+  }
+}
+/* ark-ec `mul_bigint`: MSB-first double-and-add over the canonical integer of the scalar */
+static void pt_mul(int cv, pt_t* r, const pt_t* p, const fe* s_mont) {
+  const field_t* FR = &FIELDS[CURVES[cv].fr];
+  fe one = {{1, 0, 0, 0}}, k;
+  fe_mul(FR, &k, s_mont, &one);
+  pt_t acc; pt_identity(cv, &acc);
+  int started = 0;
+  for (int i = 255; i >= 0; i--) {
+    int bit = (int)((k.l[i >> 6] >> (i & 63)) & 1);
+    if (!started && !bit) continue;
+    started = 1;
+    pt_dbl(cv, &acc, &acc);
+    if (bit) pt_add(cv, &acc, &acc, p);
+  }
+  *r = acc;
+}
+static void pt_sub(int cv, pt_t* r, const pt_t* p, const pt_t* q) { pt_t n; pt_neg(cv, &n, q); pt_add(cv, r, p, &n); }
+
+static void pt_load(int cv, pt_t* p, const uint64_t* src) { memset(p, 0, sizeof *p); memcpy(p, src, CURVES[cv].ncoord * 32); }
+static void pt_store(int cv, uint64_t* dst, const pt_t* p) { memcpy(dst, p, CURVES[cv].ncoord * 32); }
+
+/* affine (x,y), 64 B; BN254 identity -> (0,0) */
+void orc_pt_normalize(int cv, size_t n, const uint64_t* pts, uint64_t* out_xy) {
+  const field_t* F = &FIELDS[CURVES[cv].fq];
+  const int w = CURVES[cv].ncoord * 4;
+  for (size_t i = 0; i < n; i++) {
+    pt_t p; pt_load(cv, &p, pts + i * w);
+    fe x, y, zi, zi2;
+    if (cv == 0) {
+      if (pt_is_identity(cv, &p)) { memset(&x, 0, sizeof x); memset(&y, 0, sizeof y); }
+      else { fe_inv(F, &zi, &p.c[2]); fe_mul(F, &zi2, &zi, &zi); fe_mul(F, &x, &p.c[0], &zi2); fe_mul(F, &zi2, &zi2, &zi); fe_mul(F, &y, &p.c[1], &zi2); }
+    } else { fe_inv(F, &zi, &p.c[3]); fe_mul(F, &x, &p.c[0], &zi); fe_mul(F, &y, &p.c[1], &zi); }
+    memcpy(out_xy + i * 8, &x, 32); memcpy(out_xy + i * 8 + 4, &y, 32);
+  }
+}
+void orc_pt_generator(int cv, uint64_t* out) { pt_t g; pt_generator(cv, &g); pt_store(cv, out, &g); }
+void orc_pt_mul(int cv, size_t n, const uint64_t* scalars, const uint64_t* pts, uint64_t* out) {
+  const int w = CURVES[cv].ncoord * 4;
+  for (size_t i = 0; i < n; i++) { pt_t p, r; pt_load(cv, &p, pts + i * w); pt_mul(cv, &r, &p, (const fe*)scalars + i); pt_store(cv, out + i * w, &r); }
+}
+void orc_pt_mul_generator(int cv, size_t n, const uint64_t* scalars, uint64_t* out) {
+  const int w = CURVES[cv].ncoord * 4;
+  pt_t g; pt_generator(cv, &g);
+  for (size_t i = 0; i < n; i++) { pt_t r; pt_mul(cv, &r, &g, (const fe*)scalars + i); pt_store(cv, out + i * w, &r); }
+}
+void orc_pt_add(int cv, size_t n, const uint64_t* a, const uint64_t* b, uint64_t* out, int sub) {
+  const int w = CURVES[cv].ncoord * 4;
+  for (size_t i = 0; i < n; i++) { pt_t p, q, r; pt_load(cv, &p, a + i * w); pt_load(cv, &q, b + i * w); if (sub) pt_sub(cv, &r, &p, &q); else pt_add(cv, &r, &p, &q); pt_store(cv, out + i * w, &r); }
+}
+/* PointShare::add_public (curve/share.rs:57-60) on AoS PointShares */
+void orc_pt_share_add_public(int cv, int party, const uint64_t* key, size_t n, const uint64_t* a_ps, const uint64_t* pub, uint64_t* out_ps, int sub) {
+  const int w = CURVES[cv].ncoord * 4;
+  for (size_t i = 0; i < n; i++) {
+    pt_t s, m, P, kp; pt_load(cv, &s, a_ps + i * 2 * w); pt_load(cv, &m, a_ps + i * 2 * w + w); pt_load(cv, &P, pub + i * w);
+    if (sub) pt_neg(cv, &P, &P);
+    if (party == 0) pt_add(cv, &s, &s, &P);
+    pt_mul(cv, &kp, &P, (const fe*)key); pt_add(cv, &m, &m, &kp);
+    pt_store(cv, out_ps + i * 2 * w, &s); pt_store(cv, out_ps + i * 2 * w + w, &m);
+  }
+}
+
+/* One party, one element range, phase 1 (:696-700): bG = (b.share*G, b.mac*G) [kept for phase 2], d = x - a, E = P - bG.
+ * The reference computes share AND mac of both masked values; only the share halves are opened. */
+static void point_mask_range(int cv, size_t n, const sshare* x, const uint64_t* P_ps, const sshare* a, const sshare* b,
+                             fe* d_mine, pt_t* E_mine, pt_t* bG_s, pt_t* bG_m) {
+  const field_t* FR = &FIELDS[CURVES[cv].fr];
+  const int w = CURVES[cv].ncoord * 4;
+  pt_t g; pt_generator(cv, &g);
+  for (size_t i = 0; i < n; i++) {
+    pt_mul(cv, &bG_s[i], &g, &b[i].share); pt_mul(cv, &bG_m[i], &g, &b[i].mac);        /* batch_mul_generator :754-780 */
+    sshare dm; batch_sub(FR, 1, &dm, &x[i], &a[i]); d_mine[i] = dm.share;                /* batch_sub :699 */
+    pt_t Ps, Pm, Em; pt_load(cv, &Ps, P_ps + i * 2 * w); pt_load(cv, &Pm, P_ps + i * 2 * w + w);
+    pt_sub(cv, &E_mine[i], &Ps, &bG_s[i]); pt_sub(cv, &Em, &Pm, &bG_m[i]);               /* batch_sub :700 (mac half unused by open) */
+  }
+}
+/* phase 2 (:704-713) */
+static void point_recombine_range(int cv, int party, const fe* key, size_t n, const fe* d, const pt_t* E, const sshare* a, const sshare* c,
+                                  const pt_t* bG_s, const pt_t* bG_m, uint64_t* out_ps) {
+  const int w = CURVES[cv].ncoord * 4;
+  pt_t g; pt_generator(cv, &g);
+  for (size_t i = 0; i < n; i++) {
+    pt_t deG, dbs, dbm, aes, aem, cs, cm, kde, s, m;
+    pt_mul(cv, &deG, &E[i], &d[i]);                                      /* CurvePointResult::batch_mul curve.rs:459-479 */
+    pt_mul(cv, &dbs, &bG_s[i], &d[i]); pt_mul(cv, &dbm, &bG_m[i], &d[i]); /* batch_mul_public :718-751 */
+    pt_mul(cv, &aes, &E[i], &a[i].share); pt_mul(cv, &aem, &E[i], &a[i].mac); /* batch_mul_authenticated curve.rs:483-517 */
+    pt_mul(cv, &cs, &g, &c[i].share); pt_mul(cv, &cm, &g, &c[i].mac);     /* batch_mul_generator */
+    s = dbs; if (party == 0) pt_add(cv, &s, &s, &deG);                    /* batch_add_public: curve/share.rs:57-60 */
+    pt_mul(cv, &kde, &deG, key); pt_add(cv, &m, &dbm, &kde);
+    pt_add(cv, &aes, &aes, &cs); pt_add(cv, &aem, &aem, &cm);             /* batch_add :711 */
+    pt_add(cv, &s, &s, &aes); pt_add(cv, &m, &m, &aem);                   /* batch_add :713 */
+    pt_store(cv, out_ps + i * 2 * w, &s); pt_store(cv, out_ps + i * 2 * w + w, &m);
+  }
+}
+
+typedef struct {
+  int cv; size_t lo, hi;
+  const uint64_t* key[2]; const uint64_t* x[2]; const uint64_t* P[2]; const uint64_t* a[2]; const uint64_t* b[2]; const uint64_t* c[2];
+  uint64_t* out[2]; uint64_t* d_open; uint64_t* E_open;
+} pjob_t;
+
+static void* pjob_run(void* arg) {
+  pjob_t* j = (pjob_t*)arg;
+  const int cv = j->cv;
+  const field_t* FR = &FIELDS[CURVES[cv].fr];
+  const int w = CURVES[cv].ncoord * 4;
+  size_t n = j->hi - j->lo, lo = j->lo;
+  if (!n) return NULL;
+  fe* dm[2]; pt_t* Em[2]; pt_t* bs[2]; pt_t* bm[2];
+  for (int p = 0; p < 2; p++) {
+    dm[p] = (fe*)malloc(n * sizeof(fe)); Em[p] = (pt_t*)malloc(n * sizeof(pt_t)); bs[p] = (pt_t*)malloc(n * sizeof(pt_t)); bm[p] = (pt_t*)malloc(n * sizeof(pt_t));
+    point_mask_range(cv, n, (const sshare*)j->x[p] + lo, j->P[p] + lo * 2 * w, (const sshare*)j->a[p] + lo, (const sshare*)j->b[p] + lo, dm[p], Em[p], bs[p], bm[p]);
+  }
+  fe* d = (fe*)malloc(n * sizeof(fe)); pt_t* E = (pt_t*)malloc(n * sizeof(pt_t));
+  for (int p = 0; p < 2; p++) { /* each party opens for itself (:66-109, scalar :161-171) */
+    scalar_batch_add(FR, n, d, dm[0], dm[1]);
+    for (size_t i = 0; i < n; i++) pt_add(cv, &E[i], &Em[0][i], &Em[1][i]);
+    point_recombine_range(cv, p, (const fe*)j->key[p], n, d, E, (const sshare*)j->a[p] + lo, (const sshare*)j->c[p] + lo, bs[p], bm[p], j->out[p] + lo * 2 * w);
+  }
+  if (j->d_open) memcpy(j->d_open + 4 * lo, d, n * sizeof(fe));
+  if (j->E_open) for (size_t i = 0; i < n; i++) pt_store(cv, j->E_open + (lo + i) * w, &E[i]);
+  for (int p = 0; p < 2; p++) { free(dm[p]); free(Em[p]); free(bs[p]); free(bm[p]); }
+  free(d); free(E);
+  return NULL;
+}
+
+/* x, a, b, c: AoS ScalarShares; P, out: AoS PointShares; d_open (n scalars) / E_open (n points) optional */
+int orc_two_party_point_mul(int cv, size_t n, int threads, const uint64_t* key0, const uint64_t* key1,
+                            const uint64_t* x0, const uint64_t* P0, const uint64_t* a0, const uint64_t* b0, const uint64_t* c0,
+                            const uint64_t* x1, const uint64_t* P1, const uint64_t* a1, const uint64_t* b1, const uint64_t* c1,
+                            uint64_t* out0, uint64_t* out1, uint64_t* d_open, uint64_t* E_open) {
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  pjob_t jobs[256];
+  pthread_t th[256];
+  for (int t = 0; t < threads; t++) {
+    pjob_t* j = &jobs[t];
+    j->cv = cv; j->lo = n * (size_t)t / threads; j->hi = n * (size_t)(t + 1) / threads;
+    j->key[0] = key0; j->key[1] = key1; j->x[0] = x0; j->x[1] = x1; j->P[0] = P0; j->P[1] = P1;
+    j->a[0] = a0; j->a[1] = a1; j->b[0] = b0; j->b[1] = b1; j->c[0] = c0; j->c[1] = c1;
+    j->out[0] = out0; j->out[1] = out1; j->d_open = d_open; j->E_open = E_open;
+  }
+  if (threads == 1) { pjob_run(&jobs[0]); return 0; }
+  for (int t = 0; t < threads; t++) if (pthread_create(&th[t], NULL, pjob_run, &jobs[t])) return -1;
+  for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  return 0;
+}

@@ -164,3 +164,76 @@ def two_party_batch_mul(f, threads, keys, x, y, a, b, c, want_open=True):
         _p(d) if want_open else None, _p(e) if want_open else None)
     assert rc == 0
     return out0, out1, d, e
+
+
+# ---------------------------------------------------------------------------------------------
+# Curve groups (points as uint64 arrays in the reference's AoS projective image: (n, 12) for BN254 G1,
+# (n, 16) for Curve25519 Edwards; PointShares are (n, 2*words) = {share, mac})
+# ---------------------------------------------------------------------------------------------
+CURVE_IDS = {"bn254_g1": 0, "curve25519_edwards": 1}
+CURVE_FQ = {0: 2, 1: 3}  # base-field ids in FIELD_IDS
+CURVE_FR = {0: 0, 1: 1}
+
+
+def point_words(cv: int) -> int:
+    return int(lib().orc_point_words(cv))
+
+
+def pt_generator(cv: int) -> np.ndarray:
+    out = np.zeros(point_words(cv), dtype=np.uint64)
+    lib().orc_pt_generator(cv, _p(out))
+    return out
+
+
+def pt_normalize(cv: int, pts: np.ndarray) -> np.ndarray:
+    """(n, words) projective -> (n, 8) affine (x, y) Montgomery limbs; BN254 identity -> zeros."""
+    pts = _u64(pts).reshape(-1, point_words(cv))
+    out = np.empty((pts.shape[0], 8), dtype=np.uint64)
+    lib().orc_pt_normalize(cv, C.c_size_t(pts.shape[0]), _p(pts), _p(out))
+    return out
+
+
+def pt_mul(cv: int, scalars: np.ndarray, pts: np.ndarray) -> np.ndarray:
+    scalars, pts = _u64(scalars), _u64(pts)
+    out = np.empty_like(pts)
+    lib().orc_pt_mul(cv, C.c_size_t(scalars.shape[0]), _p(scalars), _p(pts), _p(out))
+    return out
+
+
+def pt_mul_generator(cv: int, scalars: np.ndarray) -> np.ndarray:
+    scalars = _u64(scalars)
+    out = np.empty((scalars.shape[0], point_words(cv)), dtype=np.uint64)
+    lib().orc_pt_mul_generator(cv, C.c_size_t(scalars.shape[0]), _p(scalars), _p(out))
+    return out
+
+
+def pt_add(cv: int, a: np.ndarray, b: np.ndarray, sub: bool = False) -> np.ndarray:
+    a, b = _u64(a), _u64(b)
+    out = np.empty_like(a)
+    lib().orc_pt_add(cv, C.c_size_t(a.shape[0]), _p(a), _p(b), _p(out), int(sub))
+    return out
+
+
+def pt_share_add_public(cv: int, party: int, key: np.ndarray, a_ps: np.ndarray, pub: np.ndarray, sub: bool = False) -> np.ndarray:
+    a_ps, pub, key = _u64(a_ps), _u64(pub), _u64(key)
+    out = np.empty_like(a_ps)
+    lib().orc_pt_share_add_public(cv, party, _p(key), C.c_size_t(pub.shape[0]), _p(a_ps), _p(pub), _p(out), int(sub))
+    return out
+
+
+def two_party_point_mul(cv, threads, keys, x, P, a, b, c, want_open=True):
+    """x/a/b/c: pairs of (n,8) AoS ScalarShare arrays; P: pair of (n, 2*words) PointShare arrays.
+    Returns (out0, out1, d_open, E_open) with out* PointShare arrays (projective)."""
+    n = x[0].shape[0]
+    w = point_words(cv)
+    x0, x1, P0, P1, a0, a1, b0, b1, c0, c1 = [_u64(v) for pair in (x, P, a, b, c) for v in pair]
+    k0, k1 = _u64(keys[0]), _u64(keys[1])
+    out0 = np.empty((n, 2 * w), dtype=np.uint64)
+    out1 = np.empty((n, 2 * w), dtype=np.uint64)
+    d = np.empty((n, 4), dtype=np.uint64) if want_open else None
+    E = np.empty((n, w), dtype=np.uint64) if want_open else None
+    rc = lib().orc_two_party_point_mul(cv, C.c_size_t(n), threads, _p(k0), _p(k1), _p(x0), _p(P0), _p(a0), _p(b0), _p(c0),
+                                       _p(x1), _p(P1), _p(a1), _p(b1), _p(c1), _p(out0), _p(out1),
+                                       _p(d) if want_open else None, _p(E) if want_open else None)
+    assert rc == 0
+    return out0, out1, d, E

@@ -40,3 +40,53 @@ extern "C" int emu_run(int field, int op, int party, const uint32_t* in, uint32_
   }
   return -1;
 }
+
+// ---- curve gates (curve.cuh / curve_gates.cuh) ----
+#include <vector>
+#include "../../ark_mpc_b200/csrc/curve_gates.cuh"
+
+template <class C> static const typename C::Aff* host_gtab() {
+  static std::vector<typename C::Aff> tab;
+  if (tab.empty()) {
+    tab.resize(kWindows * kTabEntries);
+    for (int j = 0; j < kWindows; j++) build_gtab_row<C>(tab.data() + j * kTabEntries, j);
+  }
+  return tab.data();
+}
+
+template <class C> static void run_curve(int op, const uint32_t* in, uint32_t* out, int party) {
+  using Pt = typename C::Pt;
+  const fe8* v = reinterpret_cast<const fe8*>(in);
+  fe8* o = reinterpret_cast<fe8*>(out);
+  constexpr int K = C::kCoords;
+  auto pt = [&](int at) { Pt p; memcpy(&p, v + at, sizeof(Pt)); return p; };
+  auto put = [&](int at, const Pt& p) { memcpy(o + at, &p, sizeof(Pt)); };
+  switch (op) {
+    case 0: { Pt p = pt(0); C::add(p, pt(K)); put(0, p); } break;
+    case 1: { Pt p = pt(0); C::dbl(p); put(0, p); } break;
+    case 2: { C::normalize(o[0], o[1], pt(0)); } break;
+    case 3: { Pt r; pt_mul_elem<C>(r, v[0], pt(1)); put(0, r); } break;
+    case 4: { Pt r; pt_mul_gen_elem<C>(r, v[0], host_gtab<C>()); put(0, r); } break;
+    case 5: { Pt E; pt_beaver_mask_elem<C>(o[0], E, v[0], v[1], v[2], pt(3), host_gtab<C>()); put(1, E); } break;
+    case 6: {
+      // in: key d_mine d_peer a_s a_m b_s b_m c_s c_m E_mine E_peer ; out: d, E, out_s, out_m
+      Pt E;
+      pt_beaver_recombine_elem<C>(o[0], E, party, v[0], v[1], v[2], pt(9), pt(9 + K), v[3], v[4], v[5], v[6], v[7], v[8], host_gtab<C>(),
+                                  [&](int which, const Pt& r) { put(1 + K + which * K, r); });
+      put(1, E);
+    } break;
+    case 7: case 8: { Pt s, m; pt_share_add_public_elem<C>(s, m, party, op == 8, v[0], pt(1), pt(1 + K), pt(1 + 2 * K)); put(0, s); put(K, m); } break;
+    case 9: { Pt r; pt_mac_check_elem<C>(r, v[0], pt(1), pt(1 + K)); put(0, r); } break;
+    case 10: { Pt r0, r1; pt_mul2_elem<C>(r0, r1, v[0], v[1], pt(2)); put(0, r0); put(K, r1); } break;
+    case 11: { Pt p; C::set_generator(p); put(0, p); C::set_identity(p); put(K, p); } break;
+    case 12: { Pt p = pt(0); C::neg(p); put(0, p); } break;
+  }
+}
+
+extern "C" int emu_curve(int curve, int op, int party, const uint32_t* in, uint32_t* out) {
+  switch (curve) {
+    case 0: run_curve<Bn254G1>(op, in, out, party); return 0;
+    case 1: run_curve<Ed25519>(op, in, out, party); return 0;
+  }
+  return -1;
+}

@@ -22,9 +22,10 @@ ROOT = os.path.dirname(HERE)
 def emu():
     so = os.path.join(HERE, "host_emu", "libark_emu.so")
     srcs = [os.path.join(HERE, "host_emu", "emu.cpp"), os.path.join(ROOT, "ark_mpc_b200", "csrc", "fp256.cuh"),
-            os.path.join(ROOT, "ark_mpc_b200", "csrc", "beaver.cuh")]
+            os.path.join(ROOT, "ark_mpc_b200", "csrc", "beaver.cuh"),
+            os.path.join(ROOT, "ark_mpc_b200", "csrc", "curve.cuh"), os.path.join(ROOT, "ark_mpc_b200", "csrc", "curve_gates.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])
     lib = C.CDLL(so)
     lib.emu_violations.restype = C.c_uint64
 

@@ -1,0 +1,182 @@
+"""Bit-exact check of the per-element point gates (ark_mpc_b200/csrc/curve.cuh, curve_gates.cuh) on the CPU.
+
+The device headers are compiled by g++ with the carry flag emulated (tests/host_emu/emu.cpp); projective outputs are
+brought to affine form and compared with the exact affine big-int oracle (oracle/pyoracle.py), which is the
+representation parity with the reference is defined on (projective representatives are not unique,
+/root/reference/online-phase/src/algebra/curve/curve.rs:46)."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CURVES = [(po.BN254_G1, 0), (po.CURVE25519_EDWARDS, 1)]
+
+
+def to_proj(Cv, P, rng):
+    """Affine oracle point -> the reference's projective memory image (ints, plain domain) with a random Z."""
+    q = Cv.fq.p
+    z = rng.randrange(1, q)
+    if Cv.kind == "sw":
+        if P is None:
+            return [rng.randrange(1, q), rng.randrange(1, q), 0]
+        return [P[0] * z * z % q, P[1] * z * z * z % q, z]
+    x, y = P
+    return [x * z % q, y * z % q, x * y * z % q, z]
+
+
+def from_proj(Cv, c):
+    q = Cv.fq.p
+    if Cv.kind == "sw":
+        X, Y, Z = c
+        if Z == 0:
+            return None
+        zi = pow(Z, -1, q)
+        return (X * zi * zi % q, Y * zi * zi * zi % q)
+    X, Y, T, Z = c
+    zi = pow(Z, -1, q)
+    assert T * Z % q == X * Y % q, "extended coordinate T inconsistent"
+    return (X * zi % q, Y * zi % q)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(HERE, "host_emu", "libark_emu.so")
+    csrc = os.path.join(ROOT, "ark_mpc_b200", "csrc")
+    srcs = [os.path.join(HERE, "host_emu", "emu.cpp")] + [os.path.join(csrc, f) for f in ("fp256.cuh", "beaver.cuh", "curve.cuh", "curve_gates.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])
+    lib = C.CDLL(so)
+    lib.emu_violations.restype = C.c_uint64
+
+    def run(Cv, cid, op, scalars, points, n_out_fe, party=0):
+        """scalars: Fr ints (plain) ; points: projective coordinate lists (plain Fq ints).  Everything is passed in Montgomery form."""
+        vals = [Cv.fr.to_mont(s) for s in scalars] + [Cv.fq.to_mont(c) for P in points for c in P]
+        buf = np.zeros(8 * max(len(vals), 1), dtype=np.uint32)
+        for k, v in enumerate(vals):
+            for j in range(8):
+                buf[8 * k + j] = (v >> (32 * j)) & 0xFFFFFFFF
+        out = np.zeros(8 * n_out_fe, dtype=np.uint32)
+        assert lib.emu_curve(cid, op, party, buf.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 0
+        assert lib.emu_violations() == 0
+        return [sum(int(out[8 * k + j]) << (32 * j) for j in range(8)) for k in range(n_out_fe)]
+
+    return run
+
+
+def fq_out(Cv, raw):
+    assert all(r < Cv.fq.p for r in raw), "non-canonical coordinate"
+    return [Cv.fq.from_mont(r) for r in raw]
+
+
+def rand_point(Cv, rng):
+    return Cv.mul(Cv.generator, rng.randrange(1, Cv.fr.p))
+
+
+@pytest.mark.parametrize("Cv,cid", CURVES)
+def test_constants_and_group_law(emu, Cv, cid):
+    rng = random.Random(7 + cid)
+    K = 3 if Cv.kind == "sw" else 4
+    out = fq_out(Cv, emu(Cv, cid, 11, [], [], 2 * K))
+    assert from_proj(Cv, out[:K]) == Cv.generator
+    assert from_proj(Cv, out[K:]) == Cv.identity
+    P, Q = rand_point(Cv, rng), rand_point(Cv, rng)
+    ident = Cv.identity
+    cases = [(P, Q), (P, P), (P, Cv.neg(P)), (ident, P), (P, ident), (ident, ident)]
+    for A, B in cases:
+        got = from_proj(Cv, fq_out(Cv, emu(Cv, cid, 0, [], [to_proj(Cv, A, rng), to_proj(Cv, B, rng)], K)))
+        assert got == Cv.add(A, B)
+    for A in (P, Q, ident):
+        assert from_proj(Cv, fq_out(Cv, emu(Cv, cid, 1, [], [to_proj(Cv, A, rng)], K))) == Cv.add(A, A)
+        assert from_proj(Cv, fq_out(Cv, emu(Cv, cid, 12, [], [to_proj(Cv, A, rng)], K))) == Cv.neg(A)
+        x, y = fq_out(Cv, emu(Cv, cid, 2, [], [to_proj(Cv, A, rng)], 2))
+        assert (x, y) == (A if A is not None else (0, 0))
+
+
+@pytest.mark.parametrize("Cv,cid", CURVES)
+def test_scalar_mul(emu, Cv, cid):
+    rng = random.Random(11 + cid)
+    K = 3 if Cv.kind == "sw" else 4
+    r = Cv.fr.p
+    P = rand_point(Cv, rng)
+    for s in [0, 1, 2, 15, 16, 17, r - 1, r - 2, (1 << 252) - 1, rng.randrange(r), rng.randrange(r)]:
+        s %= r
+        got = from_proj(Cv, fq_out(Cv, emu(Cv, cid, 3, [s], [to_proj(Cv, P, rng)], K)))
+        assert got == Cv.mul(P, s), f"var-base s={s:x}"
+        got = from_proj(Cv, fq_out(Cv, emu(Cv, cid, 4, [s], [], K)))
+        assert got == Cv.mul(Cv.generator, s), f"fixed-base s={s:x}"
+    # identity base
+    got = from_proj(Cv, fq_out(Cv, emu(Cv, cid, 3, [12345], [to_proj(Cv, Cv.identity, rng)], K)))
+    assert got == Cv.identity
+    s0, s1 = rng.randrange(r), rng.randrange(r)
+    out = fq_out(Cv, emu(Cv, cid, 10, [s0, s1], [to_proj(Cv, P, rng)], 2 * K))
+    assert from_proj(Cv, out[:K]) == Cv.mul(P, s0) and from_proj(Cv, out[K:]) == Cv.mul(P, s1)
+
+
+@pytest.mark.parametrize("Cv,cid", CURVES)
+def test_point_beaver_gate(emu, Cv, cid):
+    """authenticated_curve.rs:682-714 for both parties on one element at a time, against the unfused oracle."""
+    rng = random.Random(23 + cid)
+    K = 3 if Cv.kind == "sw" else 4
+    F, r, G = Cv.fr, Cv.fr.p, Cv.generator
+    for trial in range(3):
+        keys = (rng.randrange(r), rng.randrange(r))
+        key = sum(keys) % r
+        xv, av, bv = (rng.randrange(r) for _ in range(3))
+        if trial == 2:
+            xv = av  # d = 0
+        cv = av * bv % r
+        sp = rng.randrange(r)
+        Pv = Cv.mul(G, sp)
+        sh = lambda v: po.authenticated_split(F, v, key, rng)
+        x, a, b, c = sh(xv), sh(av), sh(bv), sh(cv)
+        # additive point sharing of P and key*P
+        p0, m0 = rng.randrange(r), rng.randrange(r)
+        Psh = ((Cv.mul(G, p0), Cv.mul(G, m0)), (Cv.mul(G, (sp - p0) % r), Cv.mul(G, (key * sp - m0) % r)))
+        masks = []
+        for p in (0, 1):
+            want_d, want_E = po.point_beaver_mask(Cv, [x[p]], [Psh[p]], [a[p]], [b[p]])
+            out = emu(Cv, cid, 5, [x[p][0], a[p][0], b[p][0]], [to_proj(Cv, Psh[p][0], rng)], 1 + K)
+            assert F.from_mont(out[0]) == want_d[0]
+            Em = fq_out(Cv, out[1:])
+            assert from_proj(Cv, Em) == want_E[0]
+            masks.append((want_d[0], Em))
+        d = (masks[0][0] + masks[1][0]) % r
+        E = Cv.add(from_proj(Cv, masks[0][1]), from_proj(Cv, masks[1][1]))
+        opened = []
+        for p in (0, 1):
+            want = po.point_beaver_recombine(Cv, p, keys[p], [d], [E], [a[p]], [b[p]], [c[p]])[0]
+            sc = [keys[p], masks[p][0], masks[1 - p][0], a[p][0], a[p][1], b[p][0], b[p][1], c[p][0], c[p][1]]
+            out = emu(Cv, cid, 6, sc, [masks[p][1], masks[1 - p][1]], 1 + 3 * K, party=p)
+            assert F.from_mont(out[0]) == d
+            pts = fq_out(Cv, out[1:])
+            assert from_proj(Cv, pts[:K]) == E
+            assert from_proj(Cv, pts[K:2 * K]) == want[0], f"share differs (party {p})"
+            assert from_proj(Cv, pts[2 * K:]) == want[1], f"mac differs (party {p})"
+            opened.append(want)
+        # protocol sanity: opened product and MAC
+        xP = Cv.mul(Pv, xv)
+        assert Cv.add(opened[0][0], opened[1][0]) == xP
+        assert Cv.add(opened[0][1], opened[1][1]) == Cv.mul(xP, key)
+
+
+@pytest.mark.parametrize("Cv,cid", CURVES)
+def test_point_share_public_gates(emu, Cv, cid):
+    rng = random.Random(31 + cid)
+    K = 3 if Cv.kind == "sw" else 4
+    r = Cv.fr.p
+    key = rng.randrange(r)
+    S, M, P = rand_point(Cv, rng), rand_point(Cv, rng), rand_point(Cv, rng)
+    for party in (0, 1):
+        for op, fn in ((7, po.pshare_add_public), (8, lambda C_, a, Pt, k, pid: po.pshare_add_public(C_, a, C_.neg(Pt), k, pid))):
+            out = fq_out(Cv, emu(Cv, cid, op, [key], [to_proj(Cv, S, rng), to_proj(Cv, M, rng), to_proj(Cv, P, rng)], 2 * K, party=party))
+            want = fn(Cv, (S, M), P, key, party)
+            assert (from_proj(Cv, out[:K]), from_proj(Cv, out[K:])) == want
+    out = fq_out(Cv, emu(Cv, cid, 9, [key], [to_proj(Cv, P, rng), to_proj(Cv, M, rng)], K))
+    assert from_proj(Cv, out) == Cv.sub(Cv.mul(P, key), M)
