@@ -51,11 +51,12 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
-    dep_time = max(os.path.getmtime(d) for d in _deps())
+    # a translation unit is rebuilt when it or any header changed (not when a sibling .cu did)
+    hdr_time = max(os.path.getmtime(d) for d in _deps() if not d.endswith(".cu"))
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        if force or not os.path.exists(obj) or os.path.getmtime(obj) < dep_time:
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(hdr_time, os.path.getmtime(src)):
             cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")

@@ -58,13 +58,15 @@ int arkmpc_pt_neg(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a, uint6
 int arkmpc_pt_share_add_public(arkmpc_ctx* ctx, int curve, int party_id, const uint64_t* key_host, size_t n, const uint64_t* a_ps,
                                const uint64_t* pub_pts, uint64_t* out_ps) {
   ARK_REQUIRE(ctx, party_id == 0 || party_id == 1, "party_id must be 0 or 1");
-  ARK_PT_PROLOGUE(key_host, a_ps, pub_pts, out_ps);
+  ARK_REQUIRE(ctx, key_host, "null key");
+  ARK_PT_PROLOGUE(a_ps, pub_pts, out_ps);
   return ops->share_add_public(ctx, party_id, 0, load_host_fe(key_host), n, a_ps, pub_pts, out_ps);
 }
 int arkmpc_pt_share_sub_public(arkmpc_ctx* ctx, int curve, int party_id, const uint64_t* key_host, size_t n, const uint64_t* a_ps,
                                const uint64_t* pub_pts, uint64_t* out_ps) {
   ARK_REQUIRE(ctx, party_id == 0 || party_id == 1, "party_id must be 0 or 1");
-  ARK_PT_PROLOGUE(key_host, a_ps, pub_pts, out_ps);
+  ARK_REQUIRE(ctx, key_host, "null key");
+  ARK_PT_PROLOGUE(a_ps, pub_pts, out_ps);
   return ops->share_add_public(ctx, party_id, 1, load_host_fe(key_host), n, a_ps, pub_pts, out_ps);
 }
 
@@ -104,7 +106,8 @@ int arkmpc_pt_beaver_recombine(arkmpc_ctx* ctx, int curve, int party_id, const u
                                const uint64_t* c_mac, uint64_t* out_ps, uint64_t* d_open, uint64_t* E_open_pts) {
   ARK_REQUIRE(ctx, party_id == 0 || party_id == 1, "party_id must be 0 or 1");
   ARK_REQUIRE(ctx, (d_open == nullptr) == (E_open_pts == nullptr), "d_open and E_open_pts must both be given or both be NULL");
-  ARK_PT_PROLOGUE(key_host, d_mine, d_peer, E_mine_pts, E_peer_pts, a_share, a_mac, b_share, b_mac, c_share, c_mac, out_ps);
+  ARK_REQUIRE(ctx, key_host, "null key");
+  ARK_PT_PROLOGUE(d_mine, d_peer, E_mine_pts, E_peer_pts, a_share, a_mac, b_share, b_mac, c_share, c_mac, out_ps);
   ARK_REQUIRE(ctx, aligned32(d_open) && aligned32(E_open_pts), "arrays must be 32-byte aligned");
   return ops->beaver_recombine(ctx, party_id, load_host_fe(key_host), n, d_mine, d_peer, E_mine_pts, E_peer_pts, a_share, a_mac, b_share, b_mac,
                                c_share, c_mac, out_ps, d_open, E_open_pts);
@@ -112,7 +115,8 @@ int arkmpc_pt_beaver_recombine(arkmpc_ctx* ctx, int curve, int party_id, const u
 
 int arkmpc_pt_mac_check(arkmpc_ctx* ctx, int curve, const uint64_t* key_host, size_t n, const uint64_t* opened_pts, const uint64_t* a_ps,
                         uint64_t* check_pts) {
-  ARK_PT_PROLOGUE(key_host, opened_pts, a_ps, check_pts);
+  ARK_REQUIRE(ctx, key_host, "null key");
+  ARK_PT_PROLOGUE(opened_pts, a_ps, check_pts);
   return ops->mac_check(ctx, load_host_fe(key_host), n, opened_pts, a_ps, check_pts);
 }
 
