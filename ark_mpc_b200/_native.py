@@ -75,6 +75,10 @@ _PROTOS = {
     "arkmpc_fr_to_mont": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_fr_from_mont": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_fr_random": [_vp, _i, _u64, _u64, _sz, _vp],
+    "arkmpc_ipc_export": [_vp, _vp, _vp],
+    "arkmpc_ipc_import": [_vp, _vp, C.POINTER(_vp)],
+    "arkmpc_ipc_release": [_vp, _vp],
+    "arkmpc_fr_beaver_recombine_gather": [_vp, _i, _i, _vp, _sz] + [_vp] * 12 + [_i, _i, _vp, _vp],
     "arkmpc_point_bytes": [_i],
     "arkmpc_pt_add": [_vp, _i, _sz, _vp, _vp, _vp],
     "arkmpc_pt_sub": [_vp, _i, _sz, _vp, _vp, _vp],

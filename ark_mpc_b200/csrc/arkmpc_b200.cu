@@ -273,6 +273,66 @@ int arkmpc_fr_beaver_recombine(arkmpc_ctx* ctx, int field, int party_id, const u
   return ARKMPC_OK;
 }
 
+// ---- multi-GPU open gather ----
+int arkmpc_ipc_export(arkmpc_ctx* ctx, void* dev_ptr, uint8_t* handle_out) {
+  ARK_CHECK_CTX(ctx);
+  ARK_REQUIRE(ctx, dev_ptr && handle_out, "null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == ARKMPC_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  ARK_CUDA(ctx, cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle_out, &h, sizeof h);
+  return ARKMPC_OK;
+}
+int arkmpc_ipc_import(arkmpc_ctx* ctx, const uint8_t* handle, void** peer_dev_ptr) {
+  ARK_CHECK_CTX(ctx);
+  ARK_REQUIRE(ctx, handle && peer_dev_ptr, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  *peer_dev_ptr = nullptr;
+  ARK_CUDA(ctx, cudaIpcOpenMemHandle(peer_dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return ARKMPC_OK;
+}
+int arkmpc_ipc_release(arkmpc_ctx* ctx, void* peer_dev_ptr) {
+  ARK_CHECK_CTX(ctx);
+  if (peer_dev_ptr) ARK_CUDA(ctx, cudaIpcCloseMemHandle(peer_dev_ptr));
+  return ARKMPC_OK;
+}
+
+int arkmpc_fr_beaver_recombine_gather(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                                      const uint64_t* d_mine, const uint64_t* e_mine, const uint64_t* d_peer, const uint64_t* e_peer,
+                                      const uint64_t* a_share, const uint64_t* a_mac, const uint64_t* b_share, const uint64_t* b_mac,
+                                      const uint64_t* c_share, const uint64_t* c_mac, uint64_t* out_share, uint64_t* out_mac,
+                                      int world, int rank, uint64_t* const* gather_d, uint64_t* const* gather_e) {
+  ARK_CHECK_CTX(ctx);
+  ARK_REQUIRE(ctx, party_id == 0 || party_id == 1, "party_id must be 0 or 1");
+  ARK_REQUIRE(ctx, world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "bad world / rank");
+  if (n == 0) return ARKMPC_OK;
+  ARK_REQUIRE(ctx, key_host && gather_d && gather_e, "null pointer");
+  const void* ptrs[] = {d_mine, e_mine, d_peer, e_peer, a_share, a_mac, b_share, b_mac, c_share, c_mac, out_share, out_mac};
+  for (const void* p : ptrs) ARK_REQUIRE(ctx, p && aligned32(p), "null or misaligned plane");
+  RecombineArgs g;
+  g.d_mine = vec(d_mine); g.e_mine = vec(e_mine); g.d_peer = vec(d_peer); g.e_peer = vec(e_peer);
+  g.a_s = vec(a_share); g.a_m = vec(a_mac); g.b_s = vec(b_share); g.b_m = vec(b_mac); g.c_s = vec(c_share); g.c_m = vec(c_mac);
+  g.out_s = mvec(out_share); g.out_m = mvec(out_mac); g.d_open = mvec(nullptr); g.e_open = mvec(nullptr);
+  g.key = load_host_fe(key_host);
+  GatherArgs q;
+  q.world = world;
+  for (int k = 0; k < kMaxPeers; k++) {
+    q.d[k] = q.e[k] = nullptr;
+    if (k < world) {
+      ARK_REQUIRE(ctx, gather_d[k] && gather_e[k] && aligned32(gather_d[k]) && aligned32(gather_e[k]), "null or misaligned gather plane");
+      q.d[k] = reinterpret_cast<char*>(gather_d[k]) + (size_t)rank * n * 32;
+      q.e[k] = reinterpret_cast<char*>(gather_e[k]) + (size_t)rank * n * 32;
+    }
+  }
+  const unsigned grid = grid_for(ctx, n, 2);
+  ARK_FIELD_SWITCH(ctx, field, {
+    if (party_id == 0) beaver_recombine_gather_kernel<F, 0><<<grid, kBlock, 0, ctx->stream>>>(n, g, q);
+    else beaver_recombine_gather_kernel<F, 1><<<grid, kBlock, 0, ctx->stream>>>(n, g, q);
+  });
+  return post_launch(ctx, "beaver_recombine_gather_kernel");
+}
+
 // ---- public-scalar vector gates ----
 #define ARK_BINARY_ENTRY(NAME, OP)                                                                                         \
   int NAME(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, const uint64_t* b, uint64_t* out) {                   \

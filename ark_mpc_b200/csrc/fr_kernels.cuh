@@ -93,6 +93,49 @@ __global__ void __launch_bounds__(kBlock, 2) beaver_recombine_kernel(size_t n, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Beaver phase 2 with the batch_open all-gather fused into the stores (multi-GPU): the opened d and e of
+// this rank's shard are written straight into rows [rank*n, (rank+1)*n) of EVERY rank's gathered planes through
+// peer pointers (CUDA IPC mappings over NVLink / NVSwitch), so the transfer overlaps the arithmetic gate by gate and
+// the separate d_open/e_open round trip through local HBM plus the NCCL launch disappear.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+struct GatherArgs {
+  char* d[kMaxPeers];  // rank k's gathered d plane, already offset to this rank's row block
+  char* e[kMaxPeers];
+  int world;
+};
+
+template <class F, int PARTY>
+__global__ void __launch_bounds__(kBlock, 2) beaver_recombine_gather_kernel(size_t n, const __grid_constant__ RecombineArgs g,
+                                                                            const __grid_constant__ GatherArgs q) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 dm, em, dp, ep, as, am, bs, bm, cs, cm;
+    ld_fe(dm, g.d_mine, i);
+    ld_fe(dp, g.d_peer, i);
+    ld_fe(em, g.e_mine, i);
+    ld_fe(ep, g.e_peer, i);
+    ld_fe(bs, g.b_s, i);
+    ld_fe(as, g.a_s, i);
+    ld_fe(bm, g.b_m, i);
+    ld_fe(am, g.a_m, i);
+    ld_fe(cs, g.c_s, i);
+    ld_fe(cm, g.c_m, i);
+    fe8 os, om, d, e;
+    beaver_recombine_elem<F>(os, om, d, e, PARTY, g.key, dm, em, dp, ep, as, am, bs, bm, cs, cm);
+    st_fe(g.out_s, i, os);
+    st_fe(g.out_m, i, om);
+#pragma unroll
+    for (int k = 0; k < kMaxPeers; k++) {
+      if (k < q.world) {
+        st_fe(MVec{q.d[k], 32}, i, d);
+        st_fe(MVec{q.e[k], 32}, i, e);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Beaver phase 2, TMA-staged variant for planar (stride-32) operands.
 //
 // The LDG kernel above keeps only ~16 warps x 320 B in flight per SM and every warp stalls on its ten loads before

@@ -1,0 +1,145 @@
+"""Multi-GPU: a batch of independent gates sharded by contiguous index range, one process per GPU.
+
+Every gate of the hot path is element-wise (/root/reference/online-phase/src/algebra/scalar/authenticated_scalar.rs:479-484,
+:517-523, :679-684, :906-911), so K1/K2 need no inter-GPU traffic; the two-party exchange is shard-aligned.  The one
+collective north_star names is an all-gather of the opened d || e of `batch_open` when every device needs the whole vector:
+
+  * `all_gather_rows`            torch.distributed all-gather (NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests)
+  * `OpenGather.recombine_gather` the fused form: the recombine kernel stores this rank's opened rows into every rank's
+                                 gathered planes through CUDA IPC peer mappings (arkmpc_fr_beaver_recombine_gather)
+
+Field elements cannot be summed by a collective (no modular `ncclSum`): cross-GPU sums all-gather the per-rank partial
+ScalarShares (64 B each) and add them mod p locally (`all_reduce_share_sum`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as nat
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous index range [k*n/G, (k+1)*n/G) of rank k."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def shard_sizes(n: int, world: int) -> List[int]:
+    return [shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0] for r in range(world)]
+
+
+def all_gather_rows(local: torch.Tensor, group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Concatenate every rank's rows along dim 0 (equal shard sizes).  Works on CUDA (NCCL) and CPU (gloo) tensors."""
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    else:
+        chunks = list(out.chunk(world, dim=0))
+        dist.all_gather(chunks, local.contiguous(), group=group)
+    return out
+
+
+def all_gather_rows_ragged(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """As above for shard sizes that differ by one (n not divisible by world): pad to the largest shard, gather, trim."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = shard_sizes(n_total, world)
+    assert local.shape[0] == sizes[rank], "local shard does not match shard_bounds"
+    m = max(sizes)
+    pad = torch.zeros((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    full = all_gather_rows(pad, group)
+    return torch.cat([full[r * m: r * m + sizes[r]] for r in range(world)], dim=0)
+
+
+def all_reduce_share_sum(engine, partial, group=None):
+    """Sum of per-rank partial ScalarShares: all-gather of the (1,4) share and mac planes, then a local modular sum."""
+    s = all_gather_rows(partial[0], group)
+    m = all_gather_rows(partial[1], group)
+    return engine.share_sum((s, m))
+
+
+class _DevArray:
+    """Exposes a raw device allocation to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+class OpenGather:
+    """Per-rank gathered planes for the opened d and e of a sharded batch_mul, plus the peer mappings of every other
+    rank's planes.  `planes()` are (world*n, 4) int64 CUDA tensors over memory owned by this object."""
+
+    def __init__(self, engine, n_local: int, group=None):
+        self.E, self.n, self.group = engine, n_local, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("OpenGather supports up to 8 ranks (one NVSwitch domain)")
+        lib, ctx = engine.lib, engine.ctx
+        self._own, self._peers = [], []
+        handles = []
+        for _ in range(2):
+            p = C.c_void_p()
+            nat.check(lib.arkmpc_malloc(ctx, self.world * n_local * 32, C.byref(p)), "arkmpc_malloc", ctx)
+            self._own.append(p)
+            h = (C.c_uint8 * 64)()
+            nat.check(lib.arkmpc_ipc_export(ctx, p, h), "arkmpc_ipc_export", ctx)
+            handles.append(bytes(h))
+        everyone: List[object] = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=group)
+        self._ptrs = [[None] * self.world, [None] * self.world]  # [d|e][rank]
+        for r in range(self.world):
+            for which in range(2):
+                if r == self.rank:
+                    self._ptrs[which][r] = self._own[which].value
+                else:
+                    q = C.c_void_p()
+                    buf = (C.c_uint8 * 64).from_buffer_copy(everyone[r][which])
+                    nat.check(lib.arkmpc_ipc_import(ctx, buf, C.byref(q)), "arkmpc_ipc_import", ctx)
+                    self._peers.append(q)
+                    self._ptrs[which][r] = q.value
+        self._arr = [(C.c_void_p * self.world)(*self._ptrs[which]) for which in range(2)]
+        shape = (self.world * n_local, 4)
+        self.d_all = torch.as_tensor(_DevArray(self._own[0].value, shape), device=engine.tdev)
+        self.e_all = torch.as_tensor(_DevArray(self._own[1].value, shape), device=engine.tdev)
+        dist.barrier(group=group)
+
+    def planes(self):
+        return self.d_all, self.e_all
+
+    def my_rows(self):
+        lo, hi = self.rank * self.n, (self.rank + 1) * self.n
+        return self.d_all[lo:hi], self.e_all[lo:hi]
+
+    def recombine_gather(self, party: int, key, d_mine, e_mine, d_peer, e_peer, a, b, c, out):
+        """Fused K2 + all-gather.  The caller synchronises (stream sync + barrier) before reading rows written by peers."""
+        E = self.E
+        k = E.key_limbs(key)
+        E._call("arkmpc_fr_beaver_recombine_gather", E.field, int(party), k.ctypes.data_as(C.c_void_p), self.n, E._p(d_mine), E._p(e_mine),
+                E._p(d_peer), E._p(e_peer), E._p(a[0]), E._p(a[1]), E._p(b[0]), E._p(b[1]), E._p(c[0]), E._p(c[1]), E._p(out[0]), E._p(out[1]),
+                self.world, self.rank, self._arr[0], self._arr[1])
+
+    def recombine_then_nccl(self, party: int, key, d_mine, e_mine, d_peer, e_peer, a, b, c, out):
+        """Baseline: K2 writes this rank's opened rows, then two NCCL all-gathers (in place on the gathered planes)."""
+        E = self.E
+        dr, er = self.my_rows()
+        E.beaver_recombine(party, key, d_mine, e_mine, d_peer, e_peer, a, b, c, out=out, open_out=(dr, er))
+        dist.all_gather_into_tensor(self.d_all, dr, group=self.group)
+        dist.all_gather_into_tensor(self.e_all, er, group=self.group)
+
+    def close(self):
+        lib, ctx = self.E.lib, self.E.ctx
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.d_all = self.e_all = None
+        for q in self._peers:
+            lib.arkmpc_ipc_release(ctx, q)
+        dist.barrier(group=self.group)
+        for p in self._own:
+            lib.arkmpc_free(ctx, p)
+        self._peers, self._own = [], []

@@ -156,6 +156,30 @@ int arkmpc_fr_from_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* mo
  * (`Scalar::random` stand-in for benches, scalar.rs:76-78); identical to oracle synth generators. */
 int arkmpc_fr_random(arkmpc_ctx* ctx, int field, uint64_t seed, uint64_t first_index, size_t n, uint64_t* out);
 
+/* ---- multi-GPU: batch_open results gathered on every device (north_star's one collective) ----
+ * The batch is sharded by contiguous index range, one process per GPU; gates need no inter-GPU traffic.  When the
+ * opened d || e of a batch_mul must exist on every device, each rank owns two gathered planes of world*n scalars.
+ * Either run arkmpc_fr_beaver_recombine with d_open/e_open pointing at this rank's row block and then an NCCL
+ * all-gather (host side: torch.distributed), or use the fused entry point below, which stores the opened values into
+ * every rank's planes from inside the kernel through CUDA IPC peer mappings.  Buffers exported with arkmpc_ipc_export
+ * must come from arkmpc_malloc (whole allocations).  The caller synchronises ranks (stream sync + barrier) before
+ * reading gathered rows written by peers. */
+#define ARKMPC_IPC_HANDLE_BYTES 64
+#define ARKMPC_MAX_PEERS 8
+int arkmpc_ipc_export(arkmpc_ctx* ctx, void* dev_ptr, uint8_t* handle_out /* ARKMPC_IPC_HANDLE_BYTES */);
+int arkmpc_ipc_import(arkmpc_ctx* ctx, const uint8_t* handle, void** peer_dev_ptr);
+int arkmpc_ipc_release(arkmpc_ctx* ctx, void* peer_dev_ptr);
+int arkmpc_fr_beaver_recombine_gather(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                                      const uint64_t* d_mine, const uint64_t* e_mine,
+                                      const uint64_t* d_peer, const uint64_t* e_peer,
+                                      const uint64_t* a_share, const uint64_t* a_mac,
+                                      const uint64_t* b_share, const uint64_t* b_mac,
+                                      const uint64_t* c_share, const uint64_t* c_mac,
+                                      uint64_t* out_share, uint64_t* out_mac,
+                                      int world, int rank,
+                                      uint64_t* const* gather_d /* [world] base of rank k's (world*n)-scalar plane */,
+                                      uint64_t* const* gather_e);
+
 /* ---- point gates (algebra/curve/authenticated_curve.rs, curve/share.rs, curve/curve.rs) ----
  * Points are DEVICE arrays in the reference's AoS memory image: BN254 `G1Projective` {x,y,z} = 96 B (Jacobian,
  * identity z = 0); Curve25519 `EdwardsProjective` {x,y,t,z} = 128 B (extended twisted Edwards); every coordinate a

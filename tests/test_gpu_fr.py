@@ -1,5 +1,7 @@
 """GPU parity tests of the scalar-field gates: every call goes through the C ABI (libarkmpc_b200.so)
 and is compared limb-for-limb with the CPU oracle on the same inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -227,3 +229,21 @@ def test_invalid_arguments_are_rejected(engines):
         E.beaver_recombine(2, k, a, a, a, a, (a, a), (a, a), (a, a))  # bad party id
     # n == 0 is a no-op (authenticated_scalar.rs:854-856 returns an empty vector)
     E._call("arkmpc_fr_add", 0, 0, None, None, None)
+
+
+def test_multi_gpu_open_gather():
+    """Needs >= 2 GPUs on the box (skipped otherwise): tests/multi_gpu_check.py under torchrun, one rank per GPU."""
+    import subprocess
+    import sys
+
+    import torch
+
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n_dev, 8)}", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(root, "tests", "multi_gpu_check.py"), "20000"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("multi-GPU open gather OK") == min(n_dev, 8)
