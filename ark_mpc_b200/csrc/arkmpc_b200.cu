@@ -7,6 +7,12 @@ using namespace arkctx;
 
 namespace {
 
+// one gate per thread (the grid-stride loop in the kernels still covers n beyond the grid limit)
+inline unsigned full_grid(size_t n) {
+  size_t need = (n + kBlock - 1) / kBlock;
+  return (unsigned)(need < (1u << 30) ? (need ? need : 1) : (1u << 30));
+}
+
 // ---- launch helpers shared by the device-pointer ABI and the host-buffer path ----
 template <class F>
 int launch_mask(arkmpc_ctx* ctx, cudaStream_t s, size_t n, Vec x, Vec y, Vec a, Vec b, MVec d, MVec e) {
@@ -48,7 +54,7 @@ int launch_recombine(arkmpc_ctx* ctx, cudaStream_t s, int party, size_t n, const
     if (party == 0) return open ? launch_recombine_tma<F, 0, true>(ctx, s, n, g) : launch_recombine_tma<F, 0, false>(ctx, s, n, g);
     return open ? launch_recombine_tma<F, 1, true>(ctx, s, n, g) : launch_recombine_tma<F, 1, false>(ctx, s, n, g);
   }
-  const unsigned grid = grid_for(ctx, n, 2);
+  const unsigned grid = full_grid(n);
   if (party == 0) {
     if (open) beaver_recombine_kernel<F, 0, true><<<grid, kBlock, 0, s>>>(n, g);
     else beaver_recombine_kernel<F, 0, false><<<grid, kBlock, 0, s>>>(n, g);
@@ -325,7 +331,7 @@ int arkmpc_fr_beaver_recombine_gather(arkmpc_ctx* ctx, int field, int party_id, 
       q.e[k] = reinterpret_cast<char*>(gather_e[k]) + (size_t)rank * n * 32;
     }
   }
-  const unsigned grid = grid_for(ctx, n, 2);
+  const unsigned grid = full_grid(n);
   ARK_FIELD_SWITCH(ctx, field, {
     if (party_id == 0) beaver_recombine_gather_kernel<F, 0><<<grid, kBlock, 0, ctx->stream>>>(n, g, q);
     else beaver_recombine_gather_kernel<F, 1><<<grid, kBlock, 0, ctx->stream>>>(n, g, q);

@@ -66,8 +66,13 @@ struct RecombineArgs {
   fe8 key;
 };
 
+// Launch shape (measured on B200, tools/_k2v.cu, profiles/r01d_k2_launch_shapes.txt): the kernel is bound by the IMAD.WIDE
+// pipe, not by occupancy, but a one-gate-per-thread grid (hardware block scheduling instead of a persistent grid-stride
+// wave) with 3 resident blocks of 256 (78 registers) is 10 % faster than 2 persistent blocks per SM: 74.9 vs 82.7 us.
+constexpr int kRecombineMinBlocks = 3;
+
 template <class F, int PARTY, bool OPEN>
-__global__ void __launch_bounds__(kBlock, 2) beaver_recombine_kernel(size_t n, const __grid_constant__ RecombineArgs g) {
+__global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_kernel(size_t n, const __grid_constant__ RecombineArgs g) {
   const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
     fe8 dm, em, dp, ep, as, am, bs, bm, cs, cm;
@@ -106,7 +111,7 @@ struct GatherArgs {
 };
 
 template <class F, int PARTY>
-__global__ void __launch_bounds__(kBlock, 2) beaver_recombine_gather_kernel(size_t n, const __grid_constant__ RecombineArgs g,
+__global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_gather_kernel(size_t n, const __grid_constant__ RecombineArgs g,
                                                                             const __grid_constant__ GatherArgs q) {
   const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {

@@ -44,6 +44,26 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(kernel_substr="beaver_recombine_kernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
+    `ncu --set full` summary under profiles/ (tools/ncu_summary.py writes the 'traffic ... per launch' lines)."""
+    import glob
+    import re
+
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*recombine_full.txt"))):
+        vals, cur = [], None
+        for line in open(path):
+            if line.startswith("## "):
+                cur = line
+            m = re.search(r"traffic \(dram read\+write\) bytes per launch\s+(\d+)", line)
+            if m and cur and kernel_substr in cur:
+                vals.append(int(m.group(1)))
+        if vals:
+            best = (sum(vals) / len(vals), os.path.relpath(path, ROOT))
+    return best
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons; rows are time-stamped on arrival so that only the
     samples that fall inside the timed region are summarised."""
@@ -284,26 +304,49 @@ def main():
         clocks = sampler.stop(t_begin, t_end)
 
         # ---- e2e: host AoS buffers through the C ABI, copies inside the timed region ----
+        # One host thread and one native context per party (the reference runs the parties as two tasks, benches/batch_ops.rs:20-40):
+        # begin (upload x,y,a,b,c; mask; download d||e) -> exchange by pointer -> finish (upload the peer's d||e; recombine; download).
         e2e = None
         if args.e2e_steps > 0:
+            E1 = Engine(local_rank, args.field)
+            engines = (E, E1)
             host = []
             for p in (0, 1):
                 hp = {}
                 for nm in ("x", "y", "a", "b", "c"):
-                    buf = E.pinned_empty((n, 8))
+                    buf = engines[p].pinned_empty((n, 8))
                     buf[:] = E.download(E.share_zip(P[p][nm]))
                     hp[nm] = buf
-                hp["de"] = E.pinned_empty((2 * n, 4))
-                hp["out"] = E.pinned_empty((n, 8))
+                hp["de"] = engines[p].pinned_empty((2 * n, 4))
+                hp["out"] = engines[p].pinned_empty((n, 8))
                 host.append(hp)
+            gate = threading.Barrier(2)
+            errs = []
 
-            def e2e_step():
-                sess = [E.batch_mul_begin_host(p, P[p]["key"], host[p]["x"], host[p]["y"], host[p]["a"], host[p]["b"], host[p]["c"],
-                                               host[p]["de"]) for p in (0, 1)]
-                for p in (0, 1):
-                    E.batch_mul_finish_host(sess[p], host[1 - p]["de"], host[p]["out"])
+            def party_steps(p, reps):
+                try:
+                    torch.cuda.set_device(local_rank)
+                    Ep = engines[p]
+                    for _ in range(reps):
+                        sess = Ep.batch_mul_begin_host(p, P[p]["key"], host[p]["x"], host[p]["y"], host[p]["a"], host[p]["b"], host[p]["c"],
+                                                       host[p]["de"])
+                        gate.wait()  # both parties' d||e are in host memory: the mock network hands over the pointer
+                        Ep.batch_mul_finish_host(sess, host[1 - p]["de"], host[p]["out"])
+                        gate.wait()
+                except BaseException as e:  # noqa: BLE001
+                    errs.append(e)
+                    gate.abort()
 
-            e2e_step()
+            def e2e_run(reps):
+                th = [threading.Thread(target=party_steps, args=(p, reps)) for p in (0, 1)]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                if errs:
+                    raise errs[0]
+
+            e2e_run(1)
             ref = E.download(E.share_zip(out[0]))
             if not np.array_equal(host[0]["out"], ref):
                 raise SystemExit("e2e path result differs from the device-resident path")
@@ -311,8 +354,7 @@ def main():
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                e2e_step()
+            e2e_run(args.e2e_steps)
             torch.cuda.synchronize()
             e2e_ms = 1e3 * (time.perf_counter() - t0) / args.e2e_steps
             if world > 1:
@@ -321,7 +363,42 @@ def main():
                 e2e_ms = float(t.item())
             e2e = {"value": n * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": 2 * (5 * 64 + 64) * n, "d2h_bytes_per_step": 2 * (64 + 64) * n,
-                   "api": "arkmpc_fr_batch_mul_begin_host / arkmpc_fr_batch_mul_finish_host (pinned host AoS buffers)"}
+                   "api": "arkmpc_fr_batch_mul_begin_host / arkmpc_fr_batch_mul_finish_host (pinned host AoS buffers, one host thread per party)"}
+            E1.close()
+
+        # ---- N > 1: the batch_open all-gather (north_star's one collective), NCCL vs fused into the kernel's stores ----
+        open_allgather = None
+        if world > 1:
+            from ark_mpc_b200 import sharding as sh
+
+            G = sh.OpenGather(E, n)
+            modes = {}
+            for mode in ("nccl", "fused"):
+                fn = G.recombine_then_nccl if mode == "nccl" else G.recombine_gather
+                call = lambda: fn(0, P[0]["key"], de[0][0], de[0][1], de[1][0], de[1][1], P[0]["a"], P[0]["b"], P[0]["c"], out[0])
+                for _ in range(3):
+                    call()
+                torch.cuda.synchronize()
+                dist.barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = max(5, min(args.steps, 50))
+                a0.record(stream)
+                for _ in range(reps):
+                    call()
+                a1.record(stream)
+                stream.synchronize()
+                t = torch.tensor([a0.elapsed_time(a1) / reps], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                modes[mode] = float(t.item())
+                dist.barrier()
+            if not (torch.equal(G.my_rows()[0], E.add(de[0][0], de[1][0]))):
+                raise SystemExit("gathered rows differ from the local opened values")
+            gathered = 64 * n * world
+            open_allgather = {"what": "party 0's fused recombine + all-gather of the opened d||e (64 B x 2^%d rows per rank) onto every rank" % args.log2_batch,
+                              "recombine_plus_nccl_allgather_ms": modes["nccl"], "fused_recombine_gather_ms": modes["fused"],
+                              "bytes_gathered_per_rank": gathered,
+                              "fused_recv_gbs_per_rank": gathered * (world - 1) / world / (modes["fused"] * 1e-3) / 1e9}
+            G.close()
 
     if rank != 0:
         if world > 1:
@@ -329,6 +406,7 @@ def main():
         return
 
     peak, peak_src = load_peaks()
+    traffic = load_traffic() if (args.field == "bn254_fr" and args.log2_batch == 20) else None
     ms_per_step = ms / args.steps
     value = n * world / (ms_per_step * 1e-3)
     achieved = BYTES_RECOMBINE * n / (k2_ms * 1e-3) / 1e9
@@ -340,13 +418,16 @@ def main():
         "party_gates_per_sec": 2 * value,
         "step_hbm_gbs": (2 * (BYTES_MASK + BYTES_RECOMBINE) * n) / (ms_per_step * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": "beaver_recombine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_us": 1e3 * k2_ms,
+                     "frac": achieved / peak, "traffic": traffic[0] if traffic else None,
+                     "traffic_source": traffic[1] if traffic else None, "peak_source": peak_src, "kernel_us": 1e3 * k2_ms,
                      "algorithmic_bytes_per_launch": BYTES_RECOMBINE * n,
                      "modmul_equiv_per_sec": 6 * n / (k2_ms * 1e-3)},
         "clocks": clocks, "gpu_launches": int(launches) * world,
     }
     if e2e:
         line["e2e"] = e2e
+    if open_allgather:
+        line["open_allgather"] = open_allgather
     if not args.no_cpu_baseline and world == 1:
         from oracle import coracle as co
         from tests.util import aos
