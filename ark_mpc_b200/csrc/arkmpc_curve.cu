@@ -134,6 +134,26 @@ int arkmpc_pt_sum_is_identity(arkmpc_ctx* ctx, int curve, size_t n, const uint64
   return ARKMPC_OK;
 }
 
+int arkmpc_pt_share_split(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_ps, uint64_t* share_pts, uint64_t* mac_pts) {
+  ARK_PT_PROLOGUE(a_ps);
+  ARK_REQUIRE(ctx, aligned32(share_pts) && aligned32(mac_pts), "arrays must be 32-byte aligned");
+  const uint32_t pb = ops->point_bytes;
+  if (share_pts) {
+    int rc = ops->copy(ctx, n, a_ps, 2 * pb, share_pts, pb);
+    if (rc != ARKMPC_OK) return rc;
+  }
+  if (mac_pts) return ops->copy(ctx, n, reinterpret_cast<const char*>(a_ps) + pb, 2 * pb, mac_pts, pb);
+  return ARKMPC_OK;
+}
+
+int arkmpc_pt_share_join(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* share_pts, const uint64_t* mac_pts, uint64_t* out_ps) {
+  ARK_PT_PROLOGUE(share_pts, mac_pts, out_ps);
+  const uint32_t pb = ops->point_bytes;
+  int rc = ops->copy(ctx, n, share_pts, pb, out_ps, 2 * pb);
+  if (rc != ARKMPC_OK) return rc;
+  return ops->copy(ctx, n, mac_pts, pb, reinterpret_cast<char*>(out_ps) + pb, 2 * pb);
+}
+
 int arkmpc_pt_normalize(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, uint64_t* out_xy) {
   ARK_PT_PROLOGUE(pts, out_xy);
   return ops->normalize(ctx, n, pts, out_xy);

@@ -43,6 +43,17 @@ __global__ void __launch_bounds__(64) pt_gtab_kernel(typename C::Aff* gtab) {
   if (j < kWindows) build_gtab_row<C>(gtab + j * kTabEntries, j);
 }
 
+// strided point copy: PointShare vector <-> separate share / mac point vectors
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_copy_kernel(size_t n, PVec in, PMVec out) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt x;
+    ld_pt<C>(x, in, i);
+    st_pt<C>(out, i, x);
+  }
+}
+
 enum class PtBin { Add, Sub };
 
 // out[i] = a[i] (+|-) b[i]   (open-add :98-108, batch_add/batch_sub on the 2n points of n PointShares :396-465)

@@ -21,6 +21,7 @@ struct CurveOps {
   int (*mac_check)(arkmpc_ctx*, const ark::fe8& key, size_t n, const void* opened, const void* a_ps, void* check);
   int (*sum_is_identity)(arkmpc_ctx*, size_t n, const void* mine, const void* peer, int* flag_dev);
   int (*normalize)(arkmpc_ctx*, size_t n, const void* pts, void* out_xy);
+  int (*copy)(arkmpc_ctx*, size_t n, const void* in, uint32_t in_stride, void* out, uint32_t out_stride);
 };
 
 const CurveOps* curve_ops_bn254();
@@ -143,8 +144,13 @@ struct CurveLaunch {
     return post_launch(ctx, "pt_normalize_kernel");
   }
 
+  static int copy(arkmpc_ctx* ctx, size_t n, const void* in, uint32_t in_stride, void* out, uint32_t out_stride) {
+    pt_copy_kernel<C><<<pt_grid(ctx, n, 8), kPtBlock, 0, ctx->stream>>>(n, pvec(in, in_stride), pmvec(out, out_stride));
+    return post_launch(ctx, "pt_copy_kernel");
+  }
+
   static const CurveOps* ops() {
-    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, normalize};
+    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, normalize, copy};
     return &t;
   }
 };

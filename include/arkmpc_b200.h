@@ -229,6 +229,9 @@ int arkmpc_pt_mac_check(arkmpc_ctx* ctx, int curve, const uint64_t* key_host, si
                         const uint64_t* a_ps, uint64_t* check_pts);
 /* *all_identity_host = 1 iff mine[i] + peer[i] is the identity for every i (:128-131).  Synchronous. */
 int arkmpc_pt_sum_is_identity(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* mine_pts, const uint64_t* peer_pts, int* all_identity_host);
+/* PointShare vector <-> separate vectors of share points and mac points (either output of split may be NULL) */
+int arkmpc_pt_share_split(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_ps, uint64_t* share_pts, uint64_t* mac_pts);
+int arkmpc_pt_share_join(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* share_pts, const uint64_t* mac_pts, uint64_t* out_ps);
 /* Canonical affine form: out_xy[i] = (x, y) Montgomery, 64 B; the BN254 identity maps to (0,0), the Edwards identity is (0,1). */
 int arkmpc_pt_normalize(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, uint64_t* out_xy);
 
