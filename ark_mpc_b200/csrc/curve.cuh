@@ -18,6 +18,7 @@
 //
 // Dual-target like fp256.cuh: compiles under g++ for the host-emulation tests.
 #pragma once
+#include "f25519.cuh"
 #include "fp256.cuh"
 
 namespace ark {
@@ -25,11 +26,6 @@ namespace ark {
 // ----------------------------------------------------------------------------------------------
 // Base-field helpers (canonical Montgomery residues throughout; in-place aliasing is allowed)
 // ----------------------------------------------------------------------------------------------
-#if defined(__CUDACC__)
-#define ARK_FQ_MUL ARK_DM
-#else
-#define ARK_FQ_MUL __attribute__((noinline))  // keeps the host-emulation build small and fast to compile
-#endif
 template <class Q>
 struct Fq {
   using F = Fp<Q>;
@@ -88,6 +84,9 @@ struct Bn254G1 {
   static constexpr int kPointBytes = 96;
   static constexpr int kAffWords = 16;  // u32 words per fixed-table entry
 
+  // reference memory image <-> internal representation: the same (canonical Montgomery residues)
+  ARK_DM static void from_image(Pt&) {}
+  ARK_DM static void to_image(Pt&) {}
   ARK_DM static void set_identity(Pt& p) { K::one(p.X); K::one(p.Y); K::zero(p.Z); }  // ark-ec: (1,1,0)
   ARK_DM static bool is_identity(const Pt& p) { return K::is_zero(p.Z); }
   ARK_DM static void set_generator(Pt& p) {  // (1, 2)
@@ -229,22 +228,24 @@ struct Ed25519 {
   using Pt = PtTE;
   using Cached = CachedTE;
   using Aff = NielsTE;
-  using K = Fq<Q>;
+  using K = F25519;  // plain residues mod 2p with special-form reduction (f25519.cuh); images are converted on load / store
   static constexpr int kCoords = 4;
   static constexpr int kPointBytes = 128;
   static constexpr int kAffWords = 24;
 
-  ARK_DM static void set_2d(fe8& r) {
-    r.v[0] = 0xbe8fd3f4u; r.v[1] = 0x01db17fdu; r.v[2] = 0x5f8c52e7u; r.v[3] = 0x21430eefu;
-    r.v[4] = 0x78310d20u; r.v[5] = 0xcb27240fu; r.v[6] = 0xe53f8a4du; r.v[7] = 0x590456b4u;
+  ARK_DM static void from_image(Pt& p) { K::from_image(p.X, p.X); K::from_image(p.Y, p.Y); K::from_image(p.T, p.T); K::from_image(p.Z, p.Z); }
+  ARK_DM static void to_image(Pt& p) { K::to_image(p.X, p.X); K::to_image(p.Y, p.Y); K::to_image(p.T, p.T); K::to_image(p.Z, p.Z); }
+  ARK_DM static void set_2d(fe8& r) {  // 2d, plain
+    r.v[0] = 0x26b2f159u; r.v[1] = 0xebd69b94u; r.v[2] = 0x8283b156u; r.v[3] = 0x00e0149au;
+    r.v[4] = 0xeef3d130u; r.v[5] = 0x198e80f2u; r.v[6] = 0x56dffce7u; r.v[7] = 0x2406d9dcu;
   }
   ARK_DM static void set_identity(Pt& p) { K::zero(p.X); K::one(p.Y); K::zero(p.T); K::one(p.Z); }
   ARK_DM static bool is_identity(const Pt& p) { return K::is_zero(p.X) && K::eq(p.Y, p.Z); }
-  ARK_DM static void set_generator(Pt& p) {  // RFC 8032 base point, Montgomery images
-    p.X.v[0] = 0x3f9da287u; p.X.v[1] = 0xe2cabc55u; p.X.v[2] = 0x2396e489u; p.X.v[3] = 0x9ca59856u;
-    p.X.v[4] = 0xade4b5b7u; p.X.v[5] = 0x9879936bu; p.X.v[6] = 0x7e6077d0u; p.X.v[7] = 0x759e2370u;
-    p.Y.v[0] = 0x3333334au;
-    ARK_UNROLL for (int j = 1; j < 8; j++) p.Y.v[j] = 0x33333333u;
+  ARK_DM static void set_generator(Pt& p) {  // RFC 8032 base point, plain residues
+    p.X.v[0] = 0x8f25d51au; p.X.v[1] = 0xc9562d60u; p.X.v[2] = 0x9525a7b2u; p.X.v[3] = 0x692cc760u;
+    p.X.v[4] = 0xfdd6dc5cu; p.X.v[5] = 0xc0a4e231u; p.X.v[6] = 0xcd6e53feu; p.X.v[7] = 0x216936d3u;
+    p.Y.v[0] = 0x66666658u;
+    ARK_UNROLL for (int j = 1; j < 8; j++) p.Y.v[j] = 0x66666666u;
     K::one(p.Z);
     K::mul(p.T, p.X, p.Y);
   }
@@ -321,15 +322,22 @@ struct Ed25519 {
     K::mul(p.Z, F, G);
   }
 
-  ARK_DM static void normalize(fe8& x, fe8& y, const Pt& p) {
+  // affine (x, y) as internal residues
+  ARK_DM static void affine(fe8& x, fe8& y, const Pt& p) {
     fe8 zi;
     K::inv(zi, p.Z);
     K::mul(x, p.X, zi);
     K::mul(y, p.Y, zi);
   }
+  // canonical affine form in the reference's image (Montgomery residues)
+  ARK_DM static void normalize(fe8& x, fe8& y, const Pt& p) {
+    affine(x, y, p);
+    K::to_image(x, x);
+    K::to_image(y, y);
+  }
   ARK_DM static void to_aff(Aff& a, const Pt& p) {
     fe8 x, y, k;
-    normalize(x, y, p);
+    affine(x, y, p);
     set_2d(k);
     K::add(a.ypx, y, x);
     K::sub(a.ymx, y, x);

@@ -27,10 +27,13 @@ __device__ __forceinline__ void ld_pt(typename C::Pt& r, const PVec& v, size_t i
   fe8* f = reinterpret_cast<fe8*>(&r);
 #pragma unroll
   for (int k = 0; k < C::kCoords; k++) ld_fe(f[k], c, k);
+  C::from_image(r);
 }
 template <class C>
-__device__ __forceinline__ void st_pt(const PMVec& v, size_t i, const typename C::Pt& r) {
+__device__ __forceinline__ void st_pt(const PMVec& v, size_t i, const typename C::Pt& r_in) {
   const MVec c{v.p + i * (size_t)v.stride, 32};
+  typename C::Pt r = r_in;
+  C::to_image(r);
   const fe8* f = reinterpret_cast<const fe8*>(&r);
 #pragma unroll
   for (int k = 0; k < C::kCoords; k++) st_fe(c, k, f[k]);
@@ -48,9 +51,14 @@ template <class C>
 __global__ void __launch_bounds__(kPtBlock) pt_copy_kernel(size_t n, PVec in, PMVec out) {
   const size_t step = (size_t)gridDim.x * kPtBlock;
   for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
-    typename C::Pt x;
-    ld_pt<C>(x, in, i);
-    st_pt<C>(out, i, x);
+    const Vec ci{in.p + i * (size_t)in.stride, 32};
+    const MVec co{out.p + i * (size_t)out.stride, 32};
+#pragma unroll
+    for (int k = 0; k < C::kCoords; k++) {
+      fe8 x;
+      ld_fe(x, ci, k);
+      st_fe(co, k, x);
+    }
   }
 }
 

@@ -59,8 +59,9 @@ template <class C> static void run_curve(int op, const uint32_t* in, uint32_t* o
   const fe8* v = reinterpret_cast<const fe8*>(in);
   fe8* o = reinterpret_cast<fe8*>(out);
   constexpr int K = C::kCoords;
-  auto pt = [&](int at) { Pt p; memcpy(&p, v + at, sizeof(Pt)); return p; };
-  auto put = [&](int at, const Pt& p) { memcpy(o + at, &p, sizeof(Pt)); };
+  // points cross the harness in the reference's memory image, exactly as they cross the kernels' loads and stores
+  auto pt = [&](int at) { Pt p; memcpy(&p, v + at, sizeof(Pt)); C::from_image(p); return p; };
+  auto put = [&](int at, const Pt& p_in) { Pt p = p_in; C::to_image(p); memcpy(o + at, &p, sizeof(Pt)); };
   switch (op) {
     case 0: { Pt p = pt(0); C::add(p, pt(K)); put(0, p); } break;
     case 1: { Pt p = pt(0); C::dbl(p); put(0, p); } break;
@@ -81,6 +82,25 @@ template <class C> static void run_curve(int op, const uint32_t* in, uint32_t* o
     case 11: { Pt p; C::set_generator(p); put(0, p); C::set_identity(p); put(K, p); } break;
     case 12: { Pt p = pt(0); C::neg(p); put(0, p); } break;
   }
+}
+
+// F25519 (special-form arithmetic modulo 2p): in = plain 256-bit values, out = raw results (and canonical forms)
+extern "C" int emu_f25519(int op, const uint32_t* in, uint32_t* out) {
+  const fe8* v = reinterpret_cast<const fe8*>(in);
+  fe8* o = reinterpret_cast<fe8*>(out);
+  switch (op) {
+    case 0: F25519::add(o[0], v[0], v[1]); break;
+    case 1: F25519::sub(o[0], v[0], v[1]); break;
+    case 2: F25519::mul(o[0], v[0], v[1]); break;
+    case 3: F25519::neg(o[0], v[0]); break;
+    case 4: F25519::canon(o[0], v[0]); break;
+    case 5: F25519::inv(o[0], v[0]); break;
+    case 6: F25519::from_image(o[0], v[0]); break;
+    case 7: F25519::to_image(o[0], v[0]); break;
+    case 8: o[0].v[0] = F25519::is_zero(v[0]); o[0].v[1] = F25519::eq(v[0], v[1]); break;
+    default: return -1;
+  }
+  return 0;
 }
 
 extern "C" int emu_curve(int curve, int op, int party, const uint32_t* in, uint32_t* out) {

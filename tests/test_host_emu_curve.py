@@ -49,7 +49,7 @@ def from_proj(Cv, c):
 def emu():
     so = os.path.join(HERE, "host_emu", "libark_emu.so")
     csrc = os.path.join(ROOT, "ark_mpc_b200", "csrc")
-    srcs = [os.path.join(HERE, "host_emu", "emu.cpp")] + [os.path.join(csrc, f) for f in ("fp256.cuh", "beaver.cuh", "curve.cuh", "curve_gates.cuh")]
+    srcs = [os.path.join(HERE, "host_emu", "emu.cpp")] + [os.path.join(csrc, f) for f in ("fp256.cuh", "f25519.cuh", "beaver.cuh", "curve.cuh", "curve_gates.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])
     lib = C.CDLL(so)
@@ -180,3 +180,44 @@ def test_point_share_public_gates(emu, Cv, cid):
             assert (from_proj(Cv, out[:K]), from_proj(Cv, out[K:])) == want
     out = fq_out(Cv, emu(Cv, cid, 9, [key], [to_proj(Cv, P, rng), to_proj(Cv, M, rng)], K))
     assert from_proj(Cv, out) == Cv.sub(Cv.mul(P, key), M)
+
+
+def test_f25519_special_form_field(emu):
+    """f25519.cuh: arithmetic modulo 2p on loosely reduced 256-bit values, checked against big-int arithmetic mod p."""
+    so = os.path.join(HERE, "host_emu", "libark_emu.so")
+    lib = C.CDLL(so)
+    lib.emu_violations.restype = C.c_uint64
+    p = (1 << 255) - 19
+    rng = random.Random(2519)
+
+    def run(op, ins, n_out=1):
+        buf = np.zeros(8 * max(len(ins), 1), dtype=np.uint32)
+        for k, v in enumerate(ins):
+            for j in range(8):
+                buf[8 * k + j] = (v >> (32 * j)) & 0xFFFFFFFF
+        out = np.zeros(8 * n_out, dtype=np.uint32)
+        assert lib.emu_f25519(op, buf.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 0
+        assert lib.emu_violations() == 0
+        return [sum(int(out[8 * k + j]) << (32 * j) for j in range(8)) for k in range(n_out)]
+
+    top = (1 << 256) - 1
+    edge = [0, 1, 18, 19, 37, 38, 39, p - 1, p, p + 1, 2 * p - 1, 2 * p, 2 * p + 1, top, top - 37, top - 38, 1 << 255, (1 << 255) - 1,
+            (1 << 255) + 18, (1 << 255) + 19, (1 << 32) - 1, 1 << 224]
+    vals = edge + [rng.randrange(1 << 256) for _ in range(60)]
+    for a in vals:
+        assert run(4, [a])[0] == a % p                                   # canon
+        assert run(3, [a])[0] % p == (-a) % p                             # neg
+        assert run(7, [a])[0] == a * 38 % p                               # to_image is canonical
+        assert run(6, [a])[0] % p == a * pow(38, -1, p) % p               # from_image
+        z = run(8, [a, a])[0]
+        assert (z & 0xFFFFFFFF) == (1 if a % p == 0 else 0) and ((z >> 32) & 0xFFFFFFFF) == 1
+    for _ in range(400):
+        a, b = rng.choice(vals), rng.choice(vals)
+        assert run(0, [a, b])[0] % p == (a + b) % p
+        assert run(1, [a, b])[0] % p == (a - b) % p
+        assert run(2, [a, b])[0] % p == (a * b) % p
+        z = run(8, [a, b])[0]
+        assert ((z >> 32) & 0xFFFFFFFF) == (1 if (a - b) % p == 0 else 0)
+    for a in vals[:12] + vals[-6:]:
+        inv = run(5, [a])[0]
+        assert inv % p == (pow(a, -1, p) if a % p else 0)
