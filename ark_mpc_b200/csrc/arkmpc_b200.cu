@@ -132,6 +132,8 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
   {
     const char* v = getenv("ARKMPC_RECOMBINE");
     ctx->use_tma = v && strcmp(v, "tma") == 0;
+    const char* c = getenv("ARKMPC_CHUNK_LOG2");
+    if (c && atoi(c) >= 10 && atoi(c) <= 24) ctx->chunk_elems = (size_t)1 << atoi(c);
   }
   *out = ctx;
   return ARKMPC_OK;
@@ -587,7 +589,7 @@ int arkmpc_fr_batch_mul_begin_host(arkmpc_ctx* ctx, int field, int party_id, con
   if (!s) return fail(ctx, ARKMPC_ERR_OOM, "session alloc");
   s->ctx = ctx; s->field = field; s->party = party_id; s->n = n;
   memcpy(s->key, key_host, 32);
-  s->chunk = n < kChunkElems ? (n ? n : 1) : kChunkElems;
+  s->chunk = n < ctx->chunk_elems ? (n ? n : 1) : ctx->chunk_elems;
   *session = s;
   if (n == 0) return ARKMPC_OK;
   cudaStream_t cs = ctx->stream;

@@ -17,7 +17,7 @@
 
 namespace arkctx {
 constexpr int kSlots = 3;                 // chunk pipeline depth of the host-buffer path
-constexpr size_t kChunkElems = 1u << 16;  // elements per staged chunk
+constexpr size_t kChunkElems = 1u << 18;  // elements per staged chunk (tools/e2e_sweep.sh: 2^16 17.6 ms, 2^18 16.6 ms per 2^20-gate step)
 constexpr int kMaxPartialBlocks = 1024;
 constexpr int kNumCurves = 2;
 }  // namespace arkctx
@@ -34,6 +34,7 @@ struct arkmpc_ctx {
   int* flag_dev = nullptr;
   int* flag_host = nullptr;  // pinned
   bool use_tma = false;      // ARKMPC_RECOMBINE=tma
+  size_t chunk_elems = arkctx::kChunkElems;  // host-buffer path staging granularity (ARKMPC_CHUNK_LOG2 overrides)
   void* gtab[arkctx::kNumCurves] = {nullptr, nullptr};  // fixed-base tables, built on first use (arkmpc_curve.cu)
   std::mutex gtab_mutex;
   std::string last_error;

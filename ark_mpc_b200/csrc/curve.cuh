@@ -98,7 +98,7 @@ struct Bn254G1 {
   ARK_DM static void cache(Cached& c, const Pt& p) { c = p; }
 
   // dbl-2009-l (2M + 5S); Z = 0 stays Z = 0
-  ARK_DM static void dbl(Pt& p) {
+  ARK_DM static void dbl(Pt& p, bool = true) {
     fe8 A, B, C, D, E, F, t;
     K::sqr(A, p.X);
     K::sqr(B, p.Y);
@@ -259,8 +259,9 @@ struct Ed25519 {
     K::mul(c.T2d, p.T, k);
   }
 
-  // dbl-2008-hwcd with a = -1 (4M + 4S)
-  ARK_DM static void dbl(Pt& p) {
+  // dbl-2008-hwcd with a = -1 (4M + 4S).  T is consumed only by additions, so inside a run of doublings it is computed
+  // for the last one only (`need_t`), saving one multiplication per skipped T.
+  ARK_DM static void dbl(Pt& p, bool need_t = true) {
     fe8 A, B, C, E, G, F, H;
     K::sqr(A, p.X);
     K::sqr(B, p.Y);
@@ -276,7 +277,7 @@ struct Ed25519 {
     K::neg(H, H);      // D - B = -(A + B)
     K::mul(p.X, E, F);
     K::mul(p.Y, G, H);
-    K::mul(p.T, E, H);
+    if (need_t) K::mul(p.T, E, H);
     K::mul(p.Z, F, G);
   }
 
@@ -377,7 +378,7 @@ ARK_D void var_mul(typename C::Pt& acc, const typename C::Cached* tab, const uin
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-      for (int j = 0; j < 4; j++) C::dbl(acc);
+      for (int j = 0; j < 4; j++) C::dbl(acc, j == 3);  // every window ends in (possibly) an addition; the final T is part of the result
     }
     const uint32_t w = window4(k, i);
     if (w) C::add_cached(acc, tab[w]);

@@ -189,6 +189,169 @@ def workload_config(args, world):
             "l2_hygiene": "inputs larger than L2: ~0.9 GB touched per step vs 126 MB L2"}
 
 
+def run_supplementary(args, rank, world, local_rank):
+    """configs[2] (2^20 AuthenticatedPoint scalar-muls) and configs[3] (inner product = batch_mul + Sum + open_authenticated pieces)
+    as bench lines of the same shape; one process per GPU, index-range sharding, no data-path collective."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ark_mpc_b200.engine import Engine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    points = args.workload == "point_mul"
+    field = args.field if not points or args.field != "bn254_fr" or "--field" in sys.argv else "curve25519_fr"
+    if points and "--log2-batch" not in sys.argv:
+        args.log2_batch = 20
+    if not points and "--log2-batch" not in sys.argv:
+        args.log2_batch = 22
+    n = 1 << args.log2_batch
+    steps = args.steps if "--steps" in sys.argv else (10 if points else 200)
+    warmup = max(3, args.warmup if "--warmup" in sys.argv else 3)
+    fid = {"bn254_fr": 0, "curve25519_fr": 1}[field]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        E = Engine(local_rank, field)
+        seed = 0xC0FFEE + 7919 * rank
+        key0, key1 = (E.download(E.random(seed + 900 + p, 0, 1))[0].copy() for p in (0, 1))
+        key = E.download(E.add(E.upload(key0.reshape(1, 4)), E.upload(key1.reshape(1, 4))))[0].copy()
+        keys = (key0, key1)
+
+        def shared(s, val=None):
+            v = E.random(s, 0, n) if val is None else val
+            s0, m0 = E.random(s + 1, 0, n), E.random(s + 2, 0, n)
+            return v, (s0, m0), (E.sub(v, s0), E.sub(E.scale(v, key), m0))
+
+        xv, x0, x1 = shared(seed + 10)
+        yv, y0, y1 = shared(seed + 20)
+        av, a0, a1 = shared(seed + 30)
+        bv, b0, b1 = shared(seed + 40)
+        _, c0, c1 = shared(seed + 50, E.mul(av, bv))
+        X, Y, A, B, Cc = (x0, x1), (y0, y1), (a0, a1), (b0, b1), (c0, c1)
+        if points:
+            # P = y*G shared in the exponent: PointShares (share*G, mac*G)
+            Pt = [E.pt_mul_generator(Y[p]) for p in (0, 1)]
+            masks = [(E.empty(n), E.empty_points(n)) for _ in (0, 1)]
+            outs = [E.empty_points(n, share=True) for _ in (0, 1)]
+
+            def step():
+                for p in (0, 1):
+                    E.pt_beaver_mask(X[p][0], Pt[p], A[p][0], B[p][0], out=masks[p])
+                for p in (0, 1):
+                    E.pt_beaver_recombine(p, keys[p], masks[p][0], masks[1 - p][0], masks[p][1], masks[1 - p][1], A[p], B[p], Cc[p], out=outs[p])
+
+            step()
+            # correctness gate: the outputs open to (x*y)*G and the MAC shares to key*(x*y)*G, whole batch, affine form
+            xy = E.mul(xv, yv)
+            opened = E.pt_normalize(E.pt_add(outs[0], outs[1])).reshape(n, 2, 8)
+            ok = torch.equal(opened[:, 0, :], E.pt_normalize(E.pt_mul_generator_public(xy))) and \
+                torch.equal(opened[:, 1, :], E.pt_normalize(E.pt_mul_generator_public(E.scale(xy, key))))
+            pw = E.point_words * 8
+            alg_bytes = 2 * ((3 * 32 + 2 * pw + 32 + pw) + (2 * 32 + 2 * pw + 6 * 32 + 2 * pw))  # both parties, K1 + K2
+            metric, unit = "authenticated_point_mults_per_sec", "point mults/s"
+            wl = f"2^{args.log2_batch} AuthenticatedPoint scalar-muls over {E.field_name.replace('_fr', '')} per GPU, both parties, mock net (BASELINE.json configs[2])"
+        else:
+            de = [(E.empty(n), E.empty(n)) for _ in (0, 1)]
+            outs = [(E.empty(n), E.empty(n)) for _ in (0, 1)]
+            sums = [None, None]
+
+            def step():
+                for p in (0, 1):
+                    E.beaver_mask(X[p][0], Y[p][0], A[p][0], B[p][0], out=de[p])
+                for p in (0, 1):
+                    E.beaver_recombine(p, keys[p], de[p][0], de[p][1], de[1 - p][0], de[1 - p][1], A[p], B[p], Cc[p], out=outs[p])
+                for p in (0, 1):
+                    sums[p] = E.share_sum(outs[p])
+                opened = E.add(sums[0][0], sums[1][0])            # open of the single result
+                chk = [E.mac_check(keys[p], opened, sums[p][1]) for p in (0, 1)]  # MAC-check shares (commitment hash is host-side)
+                return opened, chk
+
+            opened, chk = step()
+            ok = torch.equal(opened, E.sum(E.mul(xv, yv))) and E.sum_is_zero(chk[0], chk[1])
+            alg_bytes = 2 * (192 + 384 + 64)
+            metric, unit = "inner_product_elements_per_sec", "elements/s"
+            wl = f"secret-shared inner product of length-2^{args.log2_batch} vectors per GPU (batch_mul + tree-sum + open with MAC check), both parties (BASELINE.json configs[3])"
+        if not ok:
+            raise SystemExit("correctness gate failed")
+        for _ in range(warmup):
+            step()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler.wait_first()
+        t_begin = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = E.launches
+        ev0.record(stream)
+        for _ in range(steps):
+            step()
+        ev1.record(stream)
+        stream.synchronize()
+        t_end = time.perf_counter()
+        launches = E.launches - l0
+        ms = ev0.elapsed_time(ev1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        clocks = sampler.stop(t_begin, t_end)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peaks()
+    achieved = alg_bytes * n / (ms * 1e-3) / 1e9
+    line = {"metric": metric, "value": n * world / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (8x32; Montgomery for BN254, special-form 2^255-19 for Curve25519)", "data": "synthetic",
+            "config": {"workload": wl, "field": field, "log2_batch_per_gpu": args.log2_batch, "parties": 2,
+                       "sharding": f"index-range x{world}, no data-path collective",
+                       "l2_hygiene": "inputs larger than L2" if n * 64 > (126 << 20) else "step touches more than L2 in total"},
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": ("compute-bound (INT32 multiply pipe): ~6.7k base-field multiplications per party-gate; the HBM fraction is "
+                                  "reported for completeness") if points else "HBM-bound streaming: 640 algorithmic B per party-element"},
+            "clocks": clocks, "gpu_launches": int(launches) * world}
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import coracle as co
+        from tests.util import aos
+
+        cores = os.cpu_count() or 1
+        m = min(n, 4096 if points else 1 << 18)
+        torch.cuda.synchronize()
+        cut = lambda pl: aos(E.download(pl[0][:m].contiguous()), E.download(pl[1][:m].contiguous()))
+        if points:
+            cv = fid
+            Ph = tuple(E.download(Pt[p][:m].contiguous()) for p in (0, 1))
+            ins = (keys, (cut(x0), cut(x1)), Ph, (cut(a0), cut(a1)), (cut(b0), cut(b1)), (cut(c0), cut(c1)))
+            co.two_party_point_mul(cv, cores, *ins, want_open=False)
+            t0 = time.perf_counter()
+            o0, _, _, _ = co.two_party_point_mul(cv, cores, *ins, want_open=False)
+            dt = time.perf_counter() - t0
+            with torch.cuda.stream(stream):  # the engine launches on the bench stream: download on the same one
+                got = E.download(E.pt_normalize(outs[0][:m].contiguous()))
+            same = np.array_equal(co.pt_normalize(cv, o0.reshape(2 * m, -1)), got)
+            if not same:
+                raise SystemExit("GPU result differs from the CPU oracle on the benchmark inputs")
+        else:
+            ins = (keys, (cut(x0), cut(x1)), (cut(y0), cut(y1)), (cut(a0), cut(a1)), (cut(b0), cut(b1)), (cut(c0), cut(c1)))
+            co.two_party_batch_mul(fid, cores, *ins, want_open=False)
+            t0 = time.perf_counter()
+            o0, o1, _, _ = co.two_party_batch_mul(fid, cores, *ins, want_open=False)
+            co.share_sum(fid, o0), co.share_sum(fid, o1)
+            dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": m / dt, "unit": unit, "cores": cores, "kind": "port",
+                                "sample": f"the first {m} elements of the same batch, unfused reference gate sequence (oracle/ark_oracle.c), all host threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,6 +363,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="beaver_fr", choices=["beaver_fr", "point_mul", "inner_product"],
+                    help="beaver_fr = BASELINE.json's metric (configs[1]); point_mul = configs[2]; inner_product = configs[3] "
+                         "(supplementary lines, same JSON shape)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -210,6 +376,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.workload != "beaver_fr":
+        return run_supplementary(args, rank, world, local_rank)
 
     import numpy as np
     import torch
