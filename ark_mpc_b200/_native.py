@@ -72,6 +72,9 @@ _PROTOS = {
     "arkmpc_fr_to_bytes_be": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_fr_share_sum": [_vp, _i, _sz, _vp, _vp, _vp, _vp],
     "arkmpc_fr_sum": [_vp, _i, _sz, _vp, _vp],
+    "arkmpc_fr_batch_inverse": [_vp, _i, _sz, _vp, _vp],
+    "arkmpc_fr_fft": [_vp, _i, _i, _i, _vp, _vp],
+    "arkmpc_fr_share_fft": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "arkmpc_fr_to_mont": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_fr_from_mont": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_fr_random": [_vp, _i, _u64, _u64, _sz, _vp],

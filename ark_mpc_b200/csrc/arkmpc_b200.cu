@@ -152,6 +152,7 @@ int arkmpc_ctx_destroy(arkmpc_ctx* ctx) {
   if (ctx->flag_host) cudaFreeHost(ctx->flag_host);
   for (int c = 0; c < kNumCurves; c++)
     if (ctx->gtab[c]) cudaFree(ctx->gtab[c]);
+  if (ctx->ntt_tw) cudaFree(ctx->ntt_tw);
   delete ctx;
   return ARKMPC_OK;
 }

@@ -1,0 +1,96 @@
+// C ABI: batch inversion and NTT over the scalar field (declared in include/arkmpc_b200.h); kernels in fr_ntt.cuh.
+#include "ctx.hpp"
+#include "fr_ntt.cuh"
+
+using namespace ark;
+using namespace arkctx;
+
+namespace {
+
+// Twiddles w^k (k < n/2) followed by the two constants {w, n^-1}; cached for the last (field, log2n, direction).
+template <class F>
+int ntt_table(arkmpc_ctx* ctx, int field, int log2n, int inverse, const char** tw, const fe8** consts) {
+  const size_t half = log2n ? (size_t)1 << (log2n - 1) : 1;
+  const long key = ((long)field << 16) | ((long)log2n << 1) | (inverse ? 1 : 0);
+  if (ctx->ntt_key != key) {
+    if (ctx->ntt_tw) {
+      ARK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      ARK_CUDA(ctx, cudaFree(ctx->ntt_tw));
+      ctx->ntt_tw = nullptr;
+      ctx->ntt_key = -1;
+    }
+    void* mem = nullptr;
+    ARK_CUDA(ctx, cudaMalloc(&mem, (half + 2) * 32));
+    fe8* c = reinterpret_cast<fe8*>(static_cast<char*>(mem) + half * 32);
+    fr_ntt_setup_kernel<F><<<1, 1, 0, ctx->stream>>>(log2n, inverse, c);
+    ctx->launches++;
+    fr_ntt_twiddle_kernel<F><<<grid_for(ctx, half, 4), kBlock, 0, ctx->stream>>>(half, c, mvec(mem));
+    int rc = post_launch(ctx, "fr_ntt_twiddle_kernel");
+    if (rc != ARKMPC_OK) { cudaFree(mem); return rc; }
+    ctx->ntt_tw = mem;
+    ctx->ntt_key = key;
+  }
+  *tw = static_cast<const char*>(ctx->ntt_tw);
+  *consts = reinterpret_cast<const fe8*>(*tw + half * 32);
+  return ARKMPC_OK;
+}
+
+template <class F>
+int ntt_plane(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t* in, uint64_t* out) {
+  const char* tw;
+  const fe8* consts;
+  int rc = ntt_table<F>(ctx, field, log2n, inverse, &tw, &consts);
+  if (rc != ARKMPC_OK) return rc;
+  const size_t n = (size_t)1 << log2n;
+  const int tile_log = log2n < kNttTileLog ? log2n : kNttTileLog;
+  const size_t tiles = n >> tile_log;
+  fr_ntt_tile_kernel<F><<<(unsigned)tiles, kNttThreads, ((size_t)32 << tile_log), ctx->stream>>>(log2n, vec(in), vec(tw), mvec(out));
+  rc = post_launch(ctx, "fr_ntt_tile_kernel");
+  for (int s = kNttTileLog + 1; rc == ARKMPC_OK && s <= log2n; s++) {
+    fr_ntt_stage_kernel<F><<<grid_for(ctx, n / 2, 8), kBlock, 0, ctx->stream>>>(log2n, s, vec(tw), mvec(out));
+    rc = post_launch(ctx, "fr_ntt_stage_kernel");
+  }
+  if (rc == ARKMPC_OK && inverse) {
+    fr_scale_dev_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(out), consts + 1, mvec(out));
+    rc = post_launch(ctx, "fr_scale_dev_kernel");
+  }
+  return rc;
+}
+
+int fft_impl(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t* in0, const uint64_t* in1, uint64_t* out0, uint64_t* out1) {
+  ARK_CHECK_CTX(ctx);
+  ARK_REQUIRE(ctx, field == ARKMPC_BN254_FR || field == ARKMPC_CURVE25519_FR, "unknown field id");
+  // ark-ff: Curve25519 Fr has two-adicity 2 and no reference test instantiates it; only BN254 Fr (two-adicity 28) is supported
+  if (field != ARKMPC_BN254_FR) return fail(ctx, ARKMPC_ERR_UNSUPPORTED, "FFT domains exist for BN254 Fr only");
+  ARK_REQUIRE(ctx, log2n >= 0 && log2n <= NttRoot::kTwoAdicity, "domain size must be 2^0 .. 2^28");
+  ARK_REQUIRE(ctx, in0 && out0 && aligned32(in0) && aligned32(out0) && in0 != out0, "null, misaligned or aliased plane (the transform is out of place)");
+  if (in1 || out1) ARK_REQUIRE(ctx, in1 && out1 && aligned32(in1) && aligned32(out1) && in1 != out1, "null, misaligned or aliased plane");
+  int rc = ntt_plane<Bn254Fr>(ctx, field, log2n, inverse, in0, out0);
+  if (rc == ARKMPC_OK && in1) rc = ntt_plane<Bn254Fr>(ctx, field, log2n, inverse, in1, out1);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, uint64_t* out) {
+  ARK_CHECK_CTX(ctx);
+  if (n == 0) return ARKMPC_OK;
+  ARK_REQUIRE(ctx, a && out && aligned32(a) && aligned32(out), "null or misaligned plane");
+  const size_t groups = (n + kInvGroup - 1) / kInvGroup;
+  ARK_FIELD_SWITCH(ctx, field, (fr_batch_inverse_kernel<F><<<grid_for(ctx, groups, 4), kBlock, 0, ctx->stream>>>(n, groups, vec(a), mvec(out))));
+  return post_launch(ctx, "arkmpc_fr_batch_inverse");
+}
+
+int arkmpc_fr_fft(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t* in, uint64_t* out) {
+  return fft_impl(ctx, field, log2n, inverse, in, nullptr, out, nullptr);
+}
+
+int arkmpc_fr_share_fft(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t* in_share, const uint64_t* in_mac, uint64_t* out_share,
+                        uint64_t* out_mac) {
+  if (!in_mac || !out_mac) return fail(ctx, ARKMPC_ERR_INVALID, "null pointer");
+  return fft_impl(ctx, field, log2n, inverse, in_share, in_mac, out_share, out_mac);
+}
+
+}  // extern "C"

@@ -37,6 +37,8 @@ struct arkmpc_ctx {
   size_t chunk_elems = arkctx::kChunkElems;  // host-buffer path staging granularity (ARKMPC_CHUNK_LOG2 overrides)
   void* gtab[arkctx::kNumCurves] = {nullptr, nullptr};  // fixed-base tables, built on first use (arkmpc_curve.cu)
   std::mutex gtab_mutex;
+  void* ntt_tw = nullptr;    // twiddle table + constants of the last (field, log2n, direction) transform (arkmpc_ntt.cu)
+  long ntt_key = -1;
   std::string last_error;
 };
 

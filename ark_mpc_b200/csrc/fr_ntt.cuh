@@ -1,0 +1,183 @@
+// Batch inversion and radix-2 NTT over the scalar field: the other element-parallel callers of the hot path
+// (SURVEY §8f rank 3).  Reference behaviour restated (paths under /root/reference/online-phase/src/algebra/scalar):
+//   Scalar::batch_inverse            scalar.rs:93-100  -> ark_ff::batch_inversion (zeros stay zero)
+//   ScalarShare::fft_helper          share.rs:162-192  -> ark-poly `EvaluationDomain::fft / ifft` on the share and mac planes
+//   AuthenticatedScalarResult::fft   authenticated_scalar.rs:1011-1070
+// ark-poly's Radix2EvaluationDomain of size n = 2^k evaluates X_j = sum_i x_i w^(ij) with w = TWO_ADIC_ROOT_OF_UNITY^(2^(s-k))
+// (s = 28, generator 5 for BN254 Fr) and returns the result in natural order; ifft is its inverse (w^-1, scaled by n^-1).
+// The transform is a function of w alone, so any correct algorithm is bit-identical on canonical residues.
+#pragma once
+#include "curve.cuh"  // Fq<>::inv: Fermat inversion for any of the Montgomery fields
+#include "fr_kernels.cuh"
+
+namespace ark {
+
+// ---------------------------------------------------------------------------------------------
+// Batch inversion, Montgomery's trick per thread: K elements share one Fermat inversion (~380 multiplications),
+// so an element costs 3 + 380/K multiplications.  Element j of group g is a[g + j*groups]: coalesced across threads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kInvGroup = 16;
+
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_batch_inverse_kernel(size_t n, size_t groups, Vec a, MVec out) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  fe8 one;
+  Fp<F>::set_one(one);
+  for (size_t g = (size_t)blockIdx.x * kBlock + threadIdx.x; g < groups; g += step) {
+    fe8 prefix[kInvGroup];
+    fe8 acc = one;
+#pragma unroll 1
+    for (int j = 0; j < kInvGroup; j++) {
+      const size_t i = g + (size_t)j * groups;
+      if (i < n) {
+        fe8 x;
+        ld_fe(x, a, i);
+        if (!Fp<F>::is_zero(x)) Fp<F>::mul(acc, acc, x);
+      }
+      prefix[j] = acc;
+    }
+    fe8 inv;
+    Fq<F>::inv(inv, acc);
+#pragma unroll 1
+    for (int j = kInvGroup - 1; j >= 0; j--) {
+      const size_t i = g + (size_t)j * groups;
+      if (i >= n) continue;
+      fe8 x, r;
+      ld_fe(x, a, i);
+      if (Fp<F>::is_zero(x)) {  // ark_ff::batch_inversion leaves zeros untouched
+        st_fe(out, i, x);
+        continue;
+      }
+      if (j == 0) r = inv; else Fp<F>::mul(r, inv, prefix[j - 1]);
+      Fp<F>::mul(inv, inv, x);
+      st_fe(out, i, r);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NTT
+// ---------------------------------------------------------------------------------------------
+// The 2^28-th root of unity of BN254 Fr that ark-ff fixes: TWO_ADIC_ROOT_OF_UNITY = 5^((p-1)/2^28)
+// = 19103219067921713944291392827692070036145651957329286315305642004821462161904 (Montgomery image below).
+struct NttRoot {
+  static constexpr int kTwoAdicity = 28;
+  __device__ __forceinline__ static void set(fe8& r) {
+    r.v[0] = 0x80d13d9cu; r.v[1] = 0x636e7355u; r.v[2] = 0x2445ffd6u; r.v[3] = 0xa22bf374u;
+    r.v[4] = 0x1eb203d8u; r.v[5] = 0x56452ac0u; r.v[6] = 0x2963f9e7u; r.v[7] = 0x1860ef94u;
+  }
+};
+
+// consts[0] = w = root^(2^(28 - log2n)) (inverted for the inverse transform), consts[1] = (2^log2n)^-1.  One thread.
+template <class F>
+__global__ void fr_ntt_setup_kernel(int log2n, int inverse, fe8* consts) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  fe8 w;
+  NttRoot::set(w);
+  for (int i = log2n; i < NttRoot::kTwoAdicity; i++) Fp<F>::mul(w, w, w);
+  if (inverse) Fq<F>::inv(w, w);
+  fe8 two, nn;
+  Fp<F>::set_one(two);
+  Fp<F>::add(two, two, two);
+  Fp<F>::set_one(nn);
+  for (int i = 0; i < log2n; i++) Fp<F>::mul(nn, nn, two);
+  Fq<F>::inv(nn, nn);
+  consts[0] = w;
+  consts[1] = nn;
+}
+
+// out = a * (*s): the n^-1 scaling of the inverse transform, scalar taken from device memory
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_scale_dev_kernel(size_t n, Vec a, const fe8* s, MVec out) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  const fe8 k = *s;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 x, r;
+    ld_fe(x, a, i);
+    Fp<F>::mul(r, x, k);
+    st_fe(out, i, r);
+  }
+}
+
+// tw[k] = w^k for k < half (left-to-right square-and-multiply on the bits of k)
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_ntt_twiddle_kernel(size_t half, const fe8* wp, MVec tw) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  const fe8 w = *wp;
+  for (size_t k = (size_t)blockIdx.x * kBlock + threadIdx.x; k < half; k += step) {
+    fe8 acc;
+    Fp<F>::set_one(acc);
+    for (int b = 63 - __clzll((unsigned long long)(k | 1)); b >= 0; b--) {
+      Fp<F>::mul(acc, acc, acc);
+      if ((k >> b) & 1) Fp<F>::mul(acc, acc, w);
+    }
+    st_fe(tw, k, acc);
+  }
+}
+
+constexpr int kNttTileLog = 10;               // 1024 elements (32 KiB) per block in shared memory
+constexpr int kNttTile = 1 << kNttTileLog;
+constexpr int kNttThreads = kNttTile / 2;     // one butterfly per thread per stage
+
+template <class F>
+__device__ __forceinline__ void ntt_butterfly(fe8& lo, fe8& hi, const fe8& w) {
+  fe8 v, s, d;
+  Fp<F>::mul(v, hi, w);
+  Fp<F>::add(s, lo, v);
+  Fp<F>::sub(d, lo, v);
+  lo = s;
+  hi = d;
+}
+
+// Stages 1..min(log2n, 10): a bit-reversed gather of one tile into shared memory, the butterflies in place, a coalesced store.
+// Twiddle of butterfly j in stage s: w^(j * n / 2^s) = tw[j << (log2n - s)].
+template <class F>
+__global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec in, Vec tw, MVec out) {
+  extern __shared__ __align__(32) unsigned char ntt_smem[];
+  fe8* x = reinterpret_cast<fe8*>(ntt_smem);
+  const int tile_log = log2n < kNttTileLog ? log2n : kNttTileLog;
+  const size_t tile = (size_t)1 << tile_log;
+  const size_t base = (size_t)blockIdx.x * tile;
+  const int t = threadIdx.x;
+  // gather: out position p <- in[bitrev(p)]
+  for (size_t e = t; e < tile; e += kNttThreads) {
+    const size_t p = base + e;
+    const size_t src = log2n ? (size_t)(__brevll((unsigned long long)p) >> (64 - log2n)) : 0;
+    ld_fe(x[e], in, src);
+  }
+  __syncthreads();
+  for (int s = 1; s <= tile_log; s++) {
+    const size_t half = (size_t)1 << (s - 1);
+    for (size_t b = t; b < tile / 2; b += kNttThreads) {
+      const size_t j = b & (half - 1);
+      const size_t i0 = ((b >> (s - 1)) << s) + j;
+      fe8 w;
+      ld_fe(w, tw, j << (log2n - s));
+      ntt_butterfly<F>(x[i0], x[i0 + half], w);
+    }
+    __syncthreads();
+  }
+  for (size_t e = t; e < tile; e += kNttThreads) st_fe(out, base + e, x[e]);
+}
+
+// One stage s > 10 in global memory, in place
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_ntt_stage_kernel(int log2n, int s, Vec tw, MVec x) {
+  const size_t nb = (size_t)1 << (log2n - 1);
+  const size_t half = (size_t)1 << (s - 1);
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t b = (size_t)blockIdx.x * kBlock + threadIdx.x; b < nb; b += step) {
+    const size_t j = b & (half - 1);
+    const size_t i0 = ((b >> (s - 1)) << s) + j;
+    fe8 w, lo, hi;
+    ld_fe(w, tw, j << (log2n - s));
+    const Vec xr{x.p, x.stride};
+    ld_fe(lo, xr, i0);
+    ld_fe(hi, xr, i0 + half);
+    ntt_butterfly<F>(lo, hi, w);
+    st_fe(x, i0, lo);
+    st_fe(x, i0 + half, hi);
+  }
+}
+
+}  // namespace ark

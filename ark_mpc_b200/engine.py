@@ -151,6 +151,26 @@ class Engine:
         self._call("arkmpc_fr_from_mont", self.field, mont.shape[0], self._p(mont), self._p(out))
         return out
 
+    def batch_inverse(self, a, out=None):
+        out = out if out is not None else self.empty(a.shape[0])
+        self._call("arkmpc_fr_batch_inverse", self.field, a.shape[0], self._p(a), self._p(out))
+        return out
+
+    def fft(self, a, inverse: bool = False):
+        """ark-poly Radix2EvaluationDomain fft / ifft of one plane whose length is a power of two."""
+        n = a.shape[0]
+        assert n > 0 and n & (n - 1) == 0, "the caller pads to the domain size (a power of two)"
+        out = self.empty(n)
+        self._call("arkmpc_fr_fft", self.field, n.bit_length() - 1, int(inverse), self._p(a), self._p(out))
+        return out
+
+    def share_fft(self, a: Planes, inverse: bool = False) -> Planes:
+        n = a[0].shape[0]
+        assert n > 0 and n & (n - 1) == 0, "the caller pads to the domain size (a power of two)"
+        o = (self.empty(n), self.empty(n))
+        self._call("arkmpc_fr_share_fft", self.field, n.bit_length() - 1, int(inverse), self._p(a[0]), self._p(a[1]), self._p(o[0]), self._p(o[1]))
+        return o
+
     def random(self, seed: int, first: int, n: int):
         out = self.empty(n)
         self._call("arkmpc_fr_random", self.field, C.c_uint64(seed & (2**64 - 1)), C.c_uint64(first), n, self._p(out))

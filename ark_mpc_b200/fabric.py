@@ -111,6 +111,9 @@ class PreprocessingPhase:
     def next_shared_bit_batch(self, n: int):
         raise NotImplementedError
 
+    def next_shared_value_batch(self, n: int):
+        raise NotImplementedError
+
 
 class PartyIDBeaverSource(PreprocessingPhase):
     """offline_prep.rs:88-170: a = 2, b = 3, c = 6 with [a] = (1,1), [b] = (3,0), [c] = (2,4); the MAC key is a sharing of 1
@@ -141,6 +144,9 @@ class PartyIDBeaverSource(PreprocessingPhase):
         return self._share(v, self.party_id * v, n)
 
     def next_shared_bit_batch(self, n: int):
+        return self._share(self.party_id, self.party_id, n)
+
+    def next_shared_value_batch(self, n: int):  # offline_prep.rs:166-168: every shared value is a sharing of 1 under key 1
         return self._share(self.party_id, self.party_id, n)
 
 
@@ -188,6 +194,10 @@ class DeviceTripleSource(PreprocessingPhase):
 
     def next_counterparty_input_mask_batch(self, n: int):
         return self._mask(n, 1 - self.party_id)[1]
+
+    def next_shared_value_batch(self, n: int):
+        E, s = self.E, self._next_seed()
+        return self.share_of(E.random(s + 10, 0, n), s + 100)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -250,6 +260,11 @@ class MpcFabric:
         with self._offline_lock:
             a, b, c = self.offline_phase.next_triplet_batch(n)
         return tuple(self.allocate_scalar_shares(t) for t in (a, b, c))
+
+    def random_shared_scalars(self, n: int) -> "AuthenticatedScalarResult":  # fabric.rs:950-965
+        with self._offline_lock:
+            v = self.offline_phase.next_shared_value_batch(n)
+        return self.allocate_scalar_shares(v)
 
     # -- network --------------------------------------------------------------------------------
     def _send(self, t: torch.Tensor) -> None:
@@ -358,6 +373,11 @@ class ScalarResult:
     def batch_neg(a):
         a.fabric.n_gates += 1
         return ScalarResult(a.fabric, a.fabric.engine.neg(a.values))
+
+    @staticmethod
+    def batch_inverse(a):  # scalar_result.rs (batch_inverse) -> Scalar::batch_inverse scalar.rs:93-100
+        a.fabric.n_gates += 1
+        return ScalarResult(a.fabric, a.fabric.engine.batch_inverse(a.values))
 
     def to_limbs(self) -> np.ndarray:
         return self.fabric.engine.download(self.values)
@@ -504,6 +524,41 @@ class AuthenticatedScalarResult:
         ok = ok and E.sum_is_zero(mac_checks, peer_checks)
         f.n_gates += 3
         return AuthenticatedScalarOpenResult(opened, bool(ok))
+
+    # -- inversion (:55-82) and FFT (:1011-1070) ---------------------------------------------------
+    @staticmethod
+    def batch_inverse(values):
+        """Two-round protocol of Bar-Ilan & Beaver as the reference implements it: mask with shared randomness, open with the
+        MAC check, invert the public values, unmask."""
+        n = len(values)
+        assert n > 0, "cannot invert empty batch of scalars"
+        f = values.fabric
+        shared = f.random_shared_scalars(n)
+        masked = AuthenticatedScalarResult.batch_mul(values, shared)
+        opened = AuthenticatedScalarResult.open_authenticated_batch(masked).result()
+        inverted = ScalarResult.batch_inverse(opened)
+        return AuthenticatedScalarResult.batch_mul_public(shared, inverted)
+
+    @staticmethod
+    def _fft(x, inverse: bool):
+        assert len(x) > 0, "Cannot compute FFT of empty vector"
+        f = x.fabric
+        n = len(x)
+        size = 1 << (n - 1).bit_length()   # D::new(x.len()): the smallest power-of-two domain that fits
+        share, mac = x.share, x.mac
+        if size != n:                       # ark-poly zero-pads the coefficient vector
+            pad = torch.zeros((size - n, 4), dtype=torch.int64, device=share.device)
+            share, mac = torch.cat([share, pad]), torch.cat([mac, pad])
+        f.n_gates += 1
+        return AuthenticatedScalarResult(f, *f.engine.share_fft((share, mac), inverse=inverse))
+
+    @staticmethod
+    def fft(x):
+        return AuthenticatedScalarResult._fft(x, False)
+
+    @staticmethod
+    def ifft(x):
+        return AuthenticatedScalarResult._fft(x, True)
 
     # -- Sum (:563-576) --------------------------------------------------------------------------
     def sum(self) -> "AuthenticatedScalarResult":

@@ -149,6 +149,18 @@ int arkmpc_fr_share_sum(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a_
                         uint64_t* out_share, uint64_t* out_mac);
 int arkmpc_fr_sum(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, uint64_t* out);
 
+/* ---- batch inversion and FFT on shares ----
+ * out[i] = a[i]^-1, zeros stay zero: `Scalar::batch_inverse` (scalar.rs:93-100 -> ark_ff::batch_inversion), the public step of
+ * AuthenticatedScalarResult::batch_inverse (authenticated_scalar.rs:55-82). */
+int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, uint64_t* out);
+/* ark-poly Radix2EvaluationDomain::fft / ifft over a domain of size 2^log2n (the caller zero-pads, as `D::new(x.len())` does):
+ * out[j] = sum_i in[i] w^(ij), w = TWO_ADIC_ROOT_OF_UNITY^(2^(28-log2n)); inverse != 0 gives the inverse transform (scaled by n^-1).
+ * Out of place (in != out); natural order in and out.  BN254 Fr only (ARKMPC_ERR_UNSUPPORTED otherwise: Curve25519 Fr has
+ * two-adicity 2).  arkmpc_fr_share_fft transforms the share and the mac plane (share.rs:162-192, authenticated_scalar.rs:1011-1070). */
+int arkmpc_fr_fft(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t* in, uint64_t* out);
+int arkmpc_fr_share_fft(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t* in_share, const uint64_t* in_mac,
+                        uint64_t* out_share, uint64_t* out_mac);
+
 /* ---- representation helpers ---- */
 int arkmpc_fr_to_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* plain, uint64_t* mont);   /* x -> x*R */
 int arkmpc_fr_from_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* mont, uint64_t* plain); /* x*R -> x */

@@ -579,3 +579,58 @@ int orc_two_party_point_mul(int cv, size_t n, int threads, const uint64_t* key0,
   for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
   return 0;
 }
+
+/* ====================================================================================================
+ * Batch inversion and FFT on shares: Scalar::batch_inverse (scalar.rs:93-100 -> ark_ff::batch_inversion,
+ * zeros stay zero) and ark-poly Radix2EvaluationDomain::fft / ifft as used by ScalarShare::fft_helper (share.rs:162-192):
+ * X_j = sum_i x_i w^(ij), w = TWO_ADIC_ROOT_OF_UNITY^(2^(28 - log2n)), natural order; ifft = inverse, scaled by n^-1.
+ * BN254 Fr only: ark-bn254 fixes GENERATOR = 5, TWO_ADICITY = 28 (crate not vendored; the root below is the widely published
+ * 19103219067921713944291392827692070036145651957329286315305642004821462161904, checked in tests/test_oracle_ntt.py).
+ * ==================================================================================================== */
+static const fe BN254_FR_ROOT28 = {{0x636e735580d13d9cull, 0xa22bf3742445ffd6ull, 0x56452ac01eb203d8ull, 0x1860ef942963f9e7ull}};
+
+void orc_batch_inverse(int f, size_t n, uint64_t* out, const uint64_t* in) {
+  const field_t* F = &FIELDS[f];
+  for (size_t i = 0; i < n; i++) {
+    const fe* x = (const fe*)in + i;
+    if (fe_is_zero(x)) ((fe*)out)[i] = *x; else fe_inv(F, (fe*)out + i, x);
+  }
+}
+
+int orc_fft(int f, int log2n, int inverse, const uint64_t* in, uint64_t* out) {
+  if (f != 0 || log2n < 0 || log2n > 28) return -1;
+  const field_t* F = &FIELDS[f];
+  const size_t n = (size_t)1 << log2n;
+  fe w = BN254_FR_ROOT28;
+  for (int i = log2n; i < 28; i++) fe_mul(F, &w, &w, &w);
+  if (inverse) fe_inv(F, &w, &w);
+  fe* x = (fe*)out;
+  for (size_t p = 0; p < n; p++) { /* bit-reversed copy */
+    size_t r = 0;
+    for (int b = 0; b < log2n; b++) r |= ((p >> b) & 1) << (log2n - 1 - b);
+    x[p] = ((const fe*)in)[r];
+  }
+  for (int s = 1; s <= log2n; s++) {
+    const size_t m = (size_t)1 << s, half = m >> 1;
+    fe wm = w; /* w^(n/m) */
+    for (int i = s; i < log2n; i++) fe_mul(F, &wm, &wm, &wm);
+    for (size_t k = 0; k < n; k += m) {
+      fe wj = F->r;
+      for (size_t j = 0; j < half; j++) {
+        fe t, u = x[k + j];
+        fe_mul(F, &t, &wj, &x[k + j + half]);
+        fe_add(F, &x[k + j], &u, &t);
+        fe_sub(F, &x[k + j + half], &u, &t);
+        fe_mul(F, &wj, &wj, &wm);
+      }
+    }
+  }
+  if (inverse) {
+    fe two, nn = F->r, ninv;
+    fe_add(F, &two, &F->r, &F->r);
+    for (int i = 0; i < log2n; i++) fe_mul(F, &nn, &nn, &two);
+    fe_inv(F, &ninv, &nn);
+    for (size_t i = 0; i < n; i++) fe_mul(F, &x[i], &x[i], &ninv);
+  }
+  return 0;
+}

@@ -237,3 +237,23 @@ def two_party_point_mul(cv, threads, keys, x, P, a, b, c, want_open=True):
                                        _p(d) if want_open else None, _p(E) if want_open else None)
     assert rc == 0
     return out0, out1, d, E
+
+
+# ---------------------------------------------------------------------------------------------
+# Batch inversion and FFT (BN254 Fr)
+# ---------------------------------------------------------------------------------------------
+def batch_inverse(f: int, a: np.ndarray) -> np.ndarray:
+    a = _u64(a)
+    out = np.empty_like(a)
+    lib().orc_batch_inverse(f, C.c_size_t(a.shape[0]), _p(out), _p(a))
+    return out
+
+
+def fft(f: int, a: np.ndarray, inverse: bool = False) -> np.ndarray:
+    a = _u64(a)
+    n = a.shape[0]
+    assert n & (n - 1) == 0 and n > 0
+    out = np.empty_like(a)
+    rc = lib().orc_fft(f, n.bit_length() - 1, int(inverse), _p(a), _p(out))
+    assert rc == 0, "orc_fft: unsupported field or size"
+    return out

@@ -503,3 +503,35 @@ def synth_element(F: Field, seed: int, index: int) -> int:
         if m < F.p:
             return m
         t += 1
+
+
+# ---------------------------------------------------------------------------
+# FFT on shares (share.rs:162-192 -> ark-poly Radix2EvaluationDomain) and batch inversion (scalar.rs:93-100)
+# ---------------------------------------------------------------------------
+BN254_FR_GENERATOR = 5       # ark-bn254 FrConfig (crate not vendored)
+BN254_FR_TWO_ADICITY = 28
+
+
+def root_of_unity(F: Field, n: int) -> int:
+    """ark-ff `get_root_of_unity(n)`: TWO_ADIC_ROOT_OF_UNITY squared down to order n (n a power of two)."""
+    assert F is BN254_FR and n & (n - 1) == 0 and n <= 1 << BN254_FR_TWO_ADICITY
+    w = pow(BN254_FR_GENERATOR, (F.p - 1) >> BN254_FR_TWO_ADICITY, F.p)
+    return pow(w, (1 << BN254_FR_TWO_ADICITY) // n, F.p)
+
+
+def naive_dft(F: Field, xs: Sequence[int], inverse: bool = False) -> List[int]:
+    """Definition of ark-poly's fft / ifft on a domain of size len(xs): X_j = sum_i x_i w^(ij); ifft uses w^-1 and n^-1."""
+    n = len(xs)
+    w = root_of_unity(F, n)
+    if inverse:
+        w = pow(w, -1, F.p)
+    out = [sum(x * pow(w, i * j, F.p) for i, x in enumerate(xs)) % F.p for j in range(n)]
+    if inverse:
+        ninv = pow(n, -1, F.p)
+        out = [v * ninv % F.p for v in out]
+    return out
+
+
+def batch_inverse(F: Field, xs: Sequence[int]) -> List[int]:
+    """ark_ff::batch_inversion: zeros are left untouched."""
+    return [pow(x, -1, F.p) if x % F.p else 0 for x in xs]
