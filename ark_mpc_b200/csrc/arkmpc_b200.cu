@@ -16,7 +16,7 @@ inline unsigned full_grid(size_t n) {
 // ---- launch helpers shared by the device-pointer ABI and the host-buffer path ----
 template <class F>
 int launch_mask(arkmpc_ctx* ctx, cudaStream_t s, size_t n, Vec x, Vec y, Vec a, Vec b, MVec d, MVec e) {
-  beaver_mask_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, s>>>(n, x, y, a, b, d, e);
+  beaver_mask_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, s>>>(n, x, y, a, b, d, e);
   return post_launch(ctx, "beaver_mask_kernel");
 }
 
@@ -132,6 +132,8 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
   {
     const char* v = getenv("ARKMPC_RECOMBINE");
     ctx->use_tma = v && strcmp(v, "tma") == 0;
+    const char* gm = getenv("ARKMPC_GRID");
+    if (gm && strcmp(gm, "persistent") == 0) ctx->full_grids = false;
     const char* c = getenv("ARKMPC_CHUNK_LOG2");
     if (c && atoi(c) >= 10 && atoi(c) <= 24) ctx->chunk_elems = (size_t)1 << atoi(c);
   }
@@ -235,7 +237,7 @@ int arkmpc_share_unzip(arkmpc_ctx* ctx, size_t n, const uint64_t* aos_dev, uint6
   ARK_REQUIRE(ctx, aos_dev && share_plane && mac_plane, "null pointer");
   ARK_REQUIRE(ctx, aligned32(aos_dev) && aligned32(share_plane) && aligned32(mac_plane), "planes must be 32-byte aligned");
   const char* base = reinterpret_cast<const char*>(aos_dev);
-  copy_planes_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(base, 64), vec(base + 32, 64), mvec(share_plane), mvec(mac_plane));
+  copy_planes_kernel<<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(base, 64), vec(base + 32, 64), mvec(share_plane), mvec(mac_plane));
   return post_launch(ctx, "share_unzip");
 }
 int arkmpc_share_zip(arkmpc_ctx* ctx, size_t n, const uint64_t* share_plane, const uint64_t* mac_plane, uint64_t* aos_dev) {
@@ -244,7 +246,7 @@ int arkmpc_share_zip(arkmpc_ctx* ctx, size_t n, const uint64_t* share_plane, con
   ARK_REQUIRE(ctx, aos_dev && share_plane && mac_plane, "null pointer");
   ARK_REQUIRE(ctx, aligned32(aos_dev) && aligned32(share_plane) && aligned32(mac_plane), "planes must be 32-byte aligned");
   char* base = reinterpret_cast<char*>(aos_dev);
-  copy_planes_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(share_plane), vec(mac_plane), mvec(base, 64), mvec(base + 32, 64));
+  copy_planes_kernel<<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(share_plane), vec(mac_plane), mvec(base, 64), mvec(base + 32, 64));
   return post_launch(ctx, "share_zip");
 }
 
@@ -349,7 +351,7 @@ int arkmpc_fr_beaver_recombine_gather(arkmpc_ctx* ctx, int field, int party_id, 
     if (n == 0) return ARKMPC_OK;                                                                                          \
     ARK_REQUIRE(ctx, a && b && out, "null pointer");                                                                       \
     ARK_REQUIRE(ctx, aligned32(a) && aligned32(b) && aligned32(out), "planes must be 32-byte aligned");                    \
-    ARK_FIELD_SWITCH(ctx, field, (fr_binary_kernel<F, OP><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), vec(b), mvec(out)))); \
+    ARK_FIELD_SWITCH(ctx, field, (fr_binary_kernel<F, OP><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), vec(b), mvec(out)))); \
     return post_launch(ctx, #NAME);                                                                                        \
   }
 ARK_BINARY_ENTRY(arkmpc_fr_add, Bin::Add)
@@ -362,7 +364,7 @@ int arkmpc_fr_neg(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, uint6
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, a && out, "null pointer");
   ARK_REQUIRE(ctx, aligned32(a) && aligned32(out), "planes must be 32-byte aligned");
-  ARK_FIELD_SWITCH(ctx, field, (fr_neg_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), mvec(out))));
+  ARK_FIELD_SWITCH(ctx, field, (fr_neg_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), mvec(out))));
   return post_launch(ctx, "arkmpc_fr_neg");
 }
 
@@ -372,7 +374,7 @@ int arkmpc_fr_scale(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, con
   ARK_REQUIRE(ctx, a && out && s_host, "null pointer");
   ARK_REQUIRE(ctx, aligned32(a) && aligned32(out), "planes must be 32-byte aligned");
   const fe8 s = load_host_fe(s_host);
-  ARK_FIELD_SWITCH(ctx, field, (fr_scale_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), s, mvec(out))));
+  ARK_FIELD_SWITCH(ctx, field, (fr_scale_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), s, mvec(out))));
   return post_launch(ctx, "arkmpc_fr_scale");
 }
 
@@ -384,7 +386,7 @@ int arkmpc_fr_to_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* plai
   ARK_FIELD_SWITCH(ctx, field, {
     fe8 r2;
     Fp<F>::set_r2(r2);
-    fr_scale_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(plain), r2, mvec(mont));
+    fr_scale_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(plain), r2, mvec(mont));
   });
   return post_launch(ctx, "arkmpc_fr_to_mont");
 }
@@ -397,7 +399,7 @@ int arkmpc_fr_from_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* mo
   fe8 one;
   for (int j = 0; j < 8; j++) one.v[j] = 0;
   one.v[0] = 1;
-  ARK_FIELD_SWITCH(ctx, field, (fr_scale_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(mont), one, mvec(plain))));
+  ARK_FIELD_SWITCH(ctx, field, (fr_scale_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(mont), one, mvec(plain))));
   return post_launch(ctx, "arkmpc_fr_from_mont");
 }
 
@@ -410,7 +412,7 @@ int arkmpc_fr_from_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* mo
     ARK_REQUIRE(ctx, a_share && a_mac && b_share && b_mac && out_share && out_mac, "null pointer");                        \
     ARK_REQUIRE(ctx, aligned32(a_share) && aligned32(a_mac) && aligned32(b_share) && aligned32(b_mac) && aligned32(out_share) && aligned32(out_mac), \
                 "planes must be 32-byte aligned");                                                                         \
-    ARK_FIELD_SWITCH(ctx, field, (fr_share_binary_kernel<F, OP><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(          \
+    ARK_FIELD_SWITCH(ctx, field, (fr_share_binary_kernel<F, OP><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(          \
                                      n, vec(a_share), vec(a_mac), vec(b_share), vec(b_mac), mvec(out_share), mvec(out_mac)))); \
     return post_launch(ctx, #NAME);                                                                                        \
   }
@@ -433,7 +435,7 @@ static int share_add_public_impl(arkmpc_ctx* ctx, int field, int party_id, const
   ARK_REQUIRE(ctx, key_host && a_share && a_mac && v && out_share && out_mac, "null pointer");
   ARK_REQUIRE(ctx, aligned32(a_share) && aligned32(a_mac) && aligned32(v) && aligned32(out_share) && aligned32(out_mac), "planes must be 32-byte aligned");
   const fe8 key = load_host_fe(key_host);
-  const unsigned grid = grid_for(ctx, n, 8);
+  const unsigned grid = grid_stream(ctx, n, 8);
   cudaStream_t s = ctx->stream;
   ARK_FIELD_SWITCH(ctx, field, {
     if (party_id == 0) {
@@ -461,7 +463,7 @@ int arkmpc_fr_share_mul_public(arkmpc_ctx* ctx, int field, size_t n, const uint6
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, a_share && a_mac && v && out_share && out_mac, "null pointer");
   ARK_REQUIRE(ctx, aligned32(a_share) && aligned32(a_mac) && aligned32(v) && aligned32(out_share) && aligned32(out_mac), "planes must be 32-byte aligned");
-  ARK_FIELD_SWITCH(ctx, field, (fr_share_mul_public_kernel<F><<<grid_for(ctx, n, 4), kBlock, 0, ctx->stream>>>(
+  ARK_FIELD_SWITCH(ctx, field, (fr_share_mul_public_kernel<F><<<grid_stream(ctx, n, 4), kBlock, 0, ctx->stream>>>(
                                    n, vec(a_share), vec(a_mac), vec(v), mvec(out_share), mvec(out_mac))));
   return post_launch(ctx, "arkmpc_fr_share_mul_public");
 }
@@ -473,7 +475,7 @@ int arkmpc_fr_mac_check(arkmpc_ctx* ctx, int field, const uint64_t* key_host, si
   ARK_REQUIRE(ctx, key_host && opened && mac && check, "null pointer");
   ARK_REQUIRE(ctx, aligned32(opened) && aligned32(mac) && aligned32(check), "planes must be 32-byte aligned");
   const fe8 key = load_host_fe(key_host);
-  ARK_FIELD_SWITCH(ctx, field, (fr_mac_check_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(opened), vec(mac), key, mvec(check))));
+  ARK_FIELD_SWITCH(ctx, field, (fr_mac_check_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(opened), vec(mac), key, mvec(check))));
   return post_launch(ctx, "arkmpc_fr_mac_check");
 }
 
@@ -486,7 +488,7 @@ int arkmpc_fr_sum_is_zero(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* 
   ARK_REQUIRE(ctx, aligned32(mine) && aligned32(peer), "planes must be 32-byte aligned");
   *ctx->flag_host = 1;
   ARK_CUDA(ctx, cudaMemcpyAsync(ctx->flag_dev, ctx->flag_host, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  ARK_FIELD_SWITCH(ctx, field, (fr_sum_is_zero_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(mine), vec(peer), ctx->flag_dev)));
+  ARK_FIELD_SWITCH(ctx, field, (fr_sum_is_zero_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(mine), vec(peer), ctx->flag_dev)));
   int rc = post_launch(ctx, "arkmpc_fr_sum_is_zero");
   if (rc != ARKMPC_OK) return rc;
   ARK_CUDA(ctx, cudaMemcpyAsync(ctx->flag_host, ctx->flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -500,7 +502,7 @@ int arkmpc_fr_to_bytes_be(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* 
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, a && out_dev, "null pointer");
   ARK_REQUIRE(ctx, aligned32(a) && aligned32(out_dev), "planes must be 32-byte aligned");
-  ARK_FIELD_SWITCH(ctx, field, (fr_to_bytes_be_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), mvec(out_dev))));
+  ARK_FIELD_SWITCH(ctx, field, (fr_to_bytes_be_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), mvec(out_dev))));
   return post_launch(ctx, "arkmpc_fr_to_bytes_be");
 }
 

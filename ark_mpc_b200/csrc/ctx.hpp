@@ -34,6 +34,7 @@ struct arkmpc_ctx {
   int* flag_dev = nullptr;
   int* flag_host = nullptr;  // pinned
   bool use_tma = false;      // ARKMPC_RECOMBINE=tma
+  bool full_grids = true;    // element-wise kernels: one element per thread instead of a persistent wave (ARKMPC_GRID=persistent reverts)
   size_t chunk_elems = arkctx::kChunkElems;  // host-buffer path staging granularity (ARKMPC_CHUNK_LOG2 overrides)
   void* gtab[arkctx::kNumCurves] = {nullptr, nullptr};  // fixed-base tables, built on first use (arkmpc_curve.cu)
   std::mutex gtab_mutex;
@@ -82,6 +83,14 @@ inline unsigned grid_for(const arkmpc_ctx* ctx, size_t n, int blocks_per_sm, int
   size_t need = (n + block - 1) / block;
   size_t cap = (size_t)ctx->sm_count * blocks_per_sm;
   return (unsigned)(need < cap ? (need ? need : 1) : cap);
+}
+// Streaming element-wise kernels: one element per thread by default (the hardware block scheduler refills SMs as blocks
+// retire; measured faster than a persistent wave for every kernel with a multiplication, profiles/r01e_grid_ab.txt); the
+// grid-stride loops in the kernels still cover any n.
+inline unsigned grid_stream(const arkmpc_ctx* ctx, size_t n, int blocks_per_sm, int block = ark::kBlock) {
+  if (!ctx->full_grids) return grid_for(ctx, n, blocks_per_sm, block);
+  size_t need = (n + block - 1) / block;
+  return (unsigned)(need < (1u << 30) ? (need ? need : 1) : (1u << 30));
 }
 
 inline int post_launch(arkmpc_ctx* ctx, const char* what) {
