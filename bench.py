@@ -189,6 +189,27 @@ def workload_config(args, world):
             "l2_hygiene": "inputs larger than L2: ~0.9 GB touched per step vs 126 MB L2"}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU e2e: run this rank's host threads on the CPUs of the NUMA node its GPU hangs off, so that the pinned
+    staging buffers (first touch) and the H2D/D2H traffic stay on the local socket.  Best effort; returns the node or None."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(f"{base}/numa_node").read().strip())
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_supplementary(args, rank, world, local_rank):
     """configs[2] (2^20 AuthenticatedPoint scalar-muls) and configs[3] (inner product = batch_mul + Sum + open_authenticated pieces)
     as bench lines of the same shape; one process per GPU, index-range sharding, no data-path collective."""
@@ -388,6 +409,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl ours) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -531,7 +553,8 @@ def main():
                 e2e_ms = float(t.item())
             e2e = {"value": n * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": 2 * (5 * 64 + 64) * n, "d2h_bytes_per_step": 2 * (64 + 64) * n,
-                   "api": "arkmpc_fr_batch_mul_begin_host / arkmpc_fr_batch_mul_finish_host (pinned host AoS buffers, one host thread per party)"}
+                   "api": "arkmpc_fr_batch_mul_begin_host / arkmpc_fr_batch_mul_finish_host (pinned host AoS buffers, one host thread per party)",
+                   "host_numa_node": numa}
             E1.close()
 
         # ---- N > 1: the batch_open all-gather (north_star's one collective), NCCL vs fused into the kernel's stores ----
