@@ -37,7 +37,15 @@ using namespace ark;
 
 inline PVec pvec(const void* p, uint32_t stride) { return PVec{static_cast<const char*>(p), stride}; }
 inline PMVec pmvec(void* p, uint32_t stride) { return PMVec{static_cast<char*>(p), stride}; }
-inline unsigned pt_grid(const arkmpc_ctx* ctx, size_t n, int blocks_per_sm) { return grid_for(ctx, n, blocks_per_sm, kPtBlock); }
+// One element per thread (hardware block scheduling): measured 6-8 % faster than persistent grids capped at 2-4 resident
+// blocks per SM for the scalar-multiplication kernels (profiles/r01e_pt_grid_ab.txt).  ARKMPC_PT_BLOCKS=k (k > 0) selects a
+// persistent grid of k blocks per SM instead.
+inline unsigned pt_grid(const arkmpc_ctx* ctx, size_t n, int /*blocks_per_sm_hint*/) {
+  static const int persistent_blocks = [] { const char* v = getenv("ARKMPC_PT_BLOCKS"); return v ? atoi(v) : 0; }();
+  if (persistent_blocks > 0) return grid_for(ctx, n, persistent_blocks, kPtBlock);
+  size_t need = (n + kPtBlock - 1) / kPtBlock;
+  return (unsigned)(need < (1u << 30) ? (need ? need : 1) : (1u << 30));
+}
 
 template <class C>
 struct CurveLaunch {
