@@ -12,8 +12,8 @@
 //
 // Scalar multiplication: the reference does a per-element MSB-first double-and-add (`self.0 * rhs.0`).  Here:
 //   variable base  4-bit fixed windows over a per-thread table {1..15}P kept in local memory (252 doublings + <=64 adds)
-//   fixed base G   table {w * 16^j * G : j < 64, 1 <= w <= 15} in global memory, built once per context
-//                  (no doublings, <= 64 mixed additions)
+//   fixed base G   table {w * 256^j * G : j < 32, 1 <= w <= 255} in global memory, built once per context
+//                  (no doublings, <= 32 mixed additions)
 // and the callers regroup sums of products that share a base into one pass (see curve_kernels.cuh).
 //
 // Dual-target like fp256.cuh: compiles under g++ for the host-emulation tests.
@@ -385,32 +385,37 @@ ARK_D void var_mul(typename C::Pt& acc, const typename C::Cached* tab, const uin
   }
 }
 
-// acc += k * G with the fixed-base table gtab[j*16 + w] = w * 16^j * G
+// Fixed base: 8-bit windows, gtab[j*256 + w] = w * 256^j * G for j < 32, 1 <= w <= 255 (entry 0 unused): no doublings and
+// at most 32 mixed additions per multiplication.  The table (32 x 256 affine entries, 0.5-0.8 MB) lives in global memory, is
+// built once per context and is served from L2.
+constexpr int kFixWindows = 32;
+constexpr int kFixEntries = 256;
+ARK_D uint32_t window8(const uint32_t* k, int i) { return (k[i >> 2] >> ((i & 3) * 8)) & 255u; }
+
+// acc += k * G
 template <class C>
 ARK_D void fix_mul_acc(typename C::Pt& acc, const typename C::Aff* gtab, const uint32_t* k) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-  for (int j = 0; j < kWindows; j++) {
-    const uint32_t w = window4(k, j);
-    if (w) C::madd(acc, gtab[j * kTabEntries + w]);
+  for (int j = 0; j < kFixWindows; j++) {
+    const uint32_t w = window8(k, j);
+    if (w) C::madd(acc, gtab[j * kFixEntries + w]);
   }
 }
 
-// One row of the fixed-base table: out[w] = w * 16^j * G for w = 1..15 (out[0] unused).  Run once per context.
+// One table entry: out = w * 256^j * G (w != 0), by 8j doublings of G and a double-and-add over the 8 bits of w.
 template <class C>
-ARK_D void build_gtab_row(typename C::Aff* out, int j) {
-  typename C::Pt base;
+ARK_D void build_gtab_entry(typename C::Aff& out, int j, uint32_t w) {
+  typename C::Pt base, acc;
   C::set_generator(base);
-  for (int i = 0; i < 4 * j; i++) C::dbl(base);
-  typename C::Cached cb;
-  C::cache(cb, base);
-  typename C::Pt t = base;
-  C::to_aff(out[1], t);
-  for (int w = 2; w < kTabEntries; w++) {
-    C::add_cached(t, cb);
-    C::to_aff(out[w], t);
+  for (int i = 0; i < 8 * j; i++) C::dbl(base);
+  C::set_identity(acc);
+  for (int b = 7; b >= 0; b--) {
+    C::dbl(acc);
+    if ((w >> b) & 1u) C::add(acc, base);
   }
+  C::to_aff(out, acc);
 }
 
 }  // namespace ark

@@ -39,11 +39,12 @@ __device__ __forceinline__ void st_pt(const PMVec& v, size_t i, const typename C
   for (int k = 0; k < C::kCoords; k++) st_fe(c, k, f[k]);
 }
 
-// fixed-base table: 64 rows x 16 entries, one thread per row
+// fixed-base table: 32 windows x 256 entries, one thread per entry (entry 0 of each window is unused)
 template <class C>
-__global__ void __launch_bounds__(64) pt_gtab_kernel(typename C::Aff* gtab) {
-  const int j = threadIdx.x;
-  if (j < kWindows) build_gtab_row<C>(gtab + j * kTabEntries, j);
+__global__ void __launch_bounds__(kFixEntries) pt_gtab_kernel(typename C::Aff* gtab) {
+  const int j = blockIdx.x;
+  const uint32_t w = threadIdx.x;
+  if (j < kFixWindows && w != 0) build_gtab_entry<C>(gtab[j * kFixEntries + w], j, w);
 }
 
 // strided point copy: PointShare vector <-> separate share / mac point vectors

@@ -58,10 +58,10 @@ struct CurveLaunch {
     void*& slot = ctx->gtab[C::kId];
     if (!slot) {
       void* mem = nullptr;
-      ARK_CUDA(ctx, cudaMalloc(&mem, sizeof(Aff) * kWindows * kTabEntries));
-      cudaError_t e = cudaMemsetAsync(mem, 0, sizeof(Aff) * kWindows * kTabEntries, ctx->stream);
+      ARK_CUDA(ctx, cudaMalloc(&mem, sizeof(Aff) * kFixWindows * kFixEntries));
+      cudaError_t e = cudaMemsetAsync(mem, 0, sizeof(Aff) * kFixWindows * kFixEntries, ctx->stream);
       if (e == cudaSuccess) {
-        pt_gtab_kernel<C><<<1, 64, 0, ctx->stream>>>(static_cast<Aff*>(mem));
+        pt_gtab_kernel<C><<<kFixWindows, kFixEntries, 0, ctx->stream>>>(static_cast<Aff*>(mem));
         ctx->launches++;
         e = cudaGetLastError();
       }

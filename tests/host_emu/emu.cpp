@@ -48,8 +48,9 @@ extern "C" int emu_run(int field, int op, int party, const uint32_t* in, uint32_
 template <class C> static const typename C::Aff* host_gtab() {
   static std::vector<typename C::Aff> tab;
   if (tab.empty()) {
-    tab.resize(kWindows * kTabEntries);
-    for (int j = 0; j < kWindows; j++) build_gtab_row<C>(tab.data() + j * kTabEntries, j);
+    tab.resize(kFixWindows * kFixEntries);
+    for (int j = 0; j < kFixWindows; j++)
+      for (uint32_t w = 1; w < (uint32_t)kFixEntries; w++) build_gtab_entry<C>(tab[j * kFixEntries + w], j, w);
   }
   return tab.data();
 }
