@@ -30,6 +30,9 @@ template <class Q>
 struct Fq {
   using F = Fp<Q>;
   ARK_FQ_MUL static void mul(fe8& r, const fe8& a, const fe8& b) { F::mul(r, a, b); }
+  // Fp::sqr (dedicated 512-bit square + separate word-serial reduction, 100 multiply-adds) measured SLOWER than the
+  // interleaved CIOS product on B200 (BN254 point Beaver 3.95 M -> 3.66 M mults/s: the un-interleaved reduction's carry ripples
+  // cost more than the 28 multiplies saved), so the Montgomery fields square with mul; F25519 keeps its dedicated square (+6 %).
   ARK_FQ_MUL static void sqr(fe8& r, const fe8& a) { F::mul(r, a, a); }
   ARK_DM static void add(fe8& r, const fe8& a, const fe8& b) { F::add(r, a, b); }
   ARK_DM static void sub(fe8& r, const fe8& a, const fe8& b) { F::sub(r, a, b); }

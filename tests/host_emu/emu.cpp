@@ -26,6 +26,7 @@ template <class F> static void run(int op, const uint32_t* in, uint32_t* out, in
     case 10: mac_check_elem<F>(o[0], v[0], v[1], v[2]); break;
     case 11: o[0] = v[0]; Fp<F>::csub_p(o[0]); break;
     case 12: Fp<F>::set_one(o[0]); Fp<F>::set_r2(o[1]); break;
+    case 13: Fp<F>::sqr(o[0], v[0]); break;
   }
 }
 
@@ -99,6 +100,8 @@ extern "C" int emu_f25519(int op, const uint32_t* in, uint32_t* out) {
     case 6: F25519::from_image(o[0], v[0]); break;
     case 7: F25519::to_image(o[0], v[0]); break;
     case 8: o[0].v[0] = F25519::is_zero(v[0]); o[0].v[1] = F25519::eq(v[0], v[1]); break;
+    case 9: F25519::sqr(o[0], v[0]); break;
+    case 10: sqr512(reinterpret_cast<uint32_t*>(o), v[0].v); break;
     default: return -1;
   }
   return 0;

@@ -152,3 +152,14 @@ def test_linear_gate_elements(emu, name, fid):
             w = po.share_sub_public(F, (s, m), v, key, party)
             assert emu(fid, 9, [M(key), M(s), M(m), M(v)], 2, party) == [M(w[0]), M(w[1])]
         assert emu(fid, 10, [M(key), M(v), M(m)], 1)[0] == M((key * v - m) % F.p)
+
+
+@pytest.mark.parametrize("name,fid", FIELDS)
+def test_dedicated_square(emu, name, fid):
+    """Fp::sqr (512-bit square with 36 multiply-adds + word-serial Montgomery reduction) == canonical a*a/R mod p."""
+    F = po.FIELDS[name]
+    rng = random.Random(40 + fid)
+    hard = [F.p - 1, F.p - 2, (F.p - 1) // 2, int("ffffffff00000000" * 4, 16) % F.p, int("00000000ffffffff" * 4, 16) % F.p,
+            int("ffffffff" * 7 + "00000000", 16) % F.p, int("80000000" * 8, 16) % F.p]
+    for a in samples(F, rng, 300) + hard:
+        assert emu(fid, 13, [a], 1)[0] == a * a * F.rinv % F.p

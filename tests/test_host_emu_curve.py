@@ -218,6 +218,12 @@ def test_f25519_special_form_field(emu):
         assert run(2, [a, b])[0] % p == (a * b) % p
         z = run(8, [a, b])[0]
         assert ((z >> 32) & 0xFFFFFFFF) == (1 if (a - b) % p == 0 else 0)
+    hard = [top, top - 1, (1 << 256) - (1 << 32), int("ffffffff00000000" * 4, 16), int("00000000ffffffff" * 4, 16), int("80000000" * 8, 16),
+            int("7fffffff" * 8, 16), int("ffffffff" * 7 + "00000000", 16)]
+    for a in vals + hard:
+        lo, hi = run(10, [a], 2)
+        assert lo + (hi << 256) == a * a                                   # the 512-bit square itself
+        assert run(9, [a])[0] % p == a * a % p
     for a in vals[:12] + vals[-6:]:
         inv = run(5, [a])[0]
         assert inv % p == (pow(a, -1, p) if a % p else 0)
