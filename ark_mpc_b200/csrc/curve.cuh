@@ -85,6 +85,9 @@ struct Bn254G1 {
   using K = Fq<Q>;
   static constexpr int kCoords = 3;
   static constexpr int kPointBytes = 96;
+  // resident 128-thread blocks per SM the scalar-multiplication kernels are compiled for: the Montgomery field needs ~220
+  // registers, capping them spills and measured slower (profiles/r01f_pt_minblocks_ab.txt)
+  static constexpr int kMinBlocks = 1;
   static constexpr int kAffWords = 16;  // u32 words per fixed-table entry
 
   // reference memory image <-> internal representation: the same (canonical Montgomery residues)
@@ -234,6 +237,7 @@ struct Ed25519 {
   using K = F25519;  // plain residues mod 2p with special-form reduction (f25519.cuh); images are converted on load / store
   static constexpr int kCoords = 4;
   static constexpr int kPointBytes = 128;
+  static constexpr int kMinBlocks = 4;  // 128 registers, <= 216 B of spills, +5 % over the unconstrained 230-register build
   static constexpr int kAffWords = 24;
 
   ARK_DM static void from_image(Pt& p) { K::from_image(p.X, p.X); K::from_image(p.Y, p.Y); K::from_image(p.T, p.T); K::from_image(p.Z, p.Z); }

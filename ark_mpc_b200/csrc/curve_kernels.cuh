@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kPtBlock) pt_neg_kernel(size_t n, PVec a, PMVe
 // out[i] = s[i >> sshift] * P[i]   (CurvePointResult::batch_mul curve.rs:459-479; batch_mul_public :718-751 with
 // sshift = 1 over the 2n points of n PointShares)
 template <class C>
-__global__ void __launch_bounds__(kPtBlock) pt_mul_kernel(size_t n, Vec s, int sshift, PVec P, PMVec out) {
+__global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_mul_kernel(size_t n, Vec s, int sshift, PVec P, PMVec out) {
   const size_t step = (size_t)gridDim.x * kPtBlock;
   for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
     typename C::Pt x, r;
@@ -222,7 +222,7 @@ struct PtRecombineArgs {
 };
 
 template <class C>
-__global__ void __launch_bounds__(kPtBlock) pt_beaver_recombine_kernel(size_t n, const __grid_constant__ PtRecombineArgs g,
+__global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_beaver_recombine_kernel(size_t n, const __grid_constant__ PtRecombineArgs g,
                                                                       const typename C::Aff* __restrict__ gtab) {
   const size_t step = (size_t)gridDim.x * kPtBlock;
   for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
