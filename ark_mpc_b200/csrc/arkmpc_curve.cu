@@ -154,6 +154,33 @@ int arkmpc_pt_share_join(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* s
   return ops->copy(ctx, n, mac_pts, pb, reinterpret_cast<char*>(out_ps) + pb, 2 * pb);
 }
 
+int arkmpc_pt_sum(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, uint64_t* out_pt) {
+  ARK_CHECK_CTX(ctx);
+  const CurveOps* ops = ops_for(curve);
+  ARK_REQUIRE(ctx, ops != nullptr, "unknown curve id");
+  ARK_REQUIRE(ctx, out_pt && aligned32(out_pt) && (n == 0 || (pts && aligned32(pts))), "null or misaligned array");
+  return ops->sum(ctx, n, n ? pts : out_pt, ops->point_bytes, out_pt);  // n == 0 gives the identity, like an empty Rust sum()
+}
+
+int arkmpc_pt_share_sum(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_ps, uint64_t* out_ps) {
+  ARK_CHECK_CTX(ctx);
+  const CurveOps* ops = ops_for(curve);
+  ARK_REQUIRE(ctx, ops != nullptr, "unknown curve id");
+  ARK_REQUIRE(ctx, out_ps && aligned32(out_ps) && (n == 0 || (a_ps && aligned32(a_ps))), "null or misaligned array");
+  const uint32_t pb = ops->point_bytes;
+  const char* a = reinterpret_cast<const char*>(n ? a_ps : out_ps);
+  int rc = ops->sum(ctx, n, a, 2 * pb, out_ps);
+  if (rc != ARKMPC_OK) return rc;
+  return ops->sum(ctx, n, a + pb, 2 * pb, reinterpret_cast<char*>(out_ps) + pb);
+}
+
+int arkmpc_pt_msm(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* scalars, const uint64_t* pts, uint64_t* scratch_pts, uint64_t* out_pt) {
+  ARK_PT_PROLOGUE(scalars, pts, scratch_pts, out_pt);
+  int rc = ops->mul(ctx, n, scalars, 0, pts, scratch_pts);
+  if (rc != ARKMPC_OK) return rc;
+  return ops->sum(ctx, n, scratch_pts, ops->point_bytes, out_pt);
+}
+
 int arkmpc_pt_normalize(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, uint64_t* out_xy) {
   ARK_PT_PROLOGUE(pts, out_xy);
   return ops->normalize(ctx, n, pts, out_xy);

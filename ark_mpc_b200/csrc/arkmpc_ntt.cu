@@ -46,9 +46,14 @@ int ntt_plane(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t
   const size_t tiles = n >> tile_log;
   fr_ntt_tile_kernel<F><<<(unsigned)tiles, kNttThreads, ((size_t)32 << tile_log), ctx->stream>>>(log2n, vec(in), vec(tw), mvec(out));
   rc = post_launch(ctx, "fr_ntt_tile_kernel");
-  for (int s = kNttTileLog + 1; rc == ARKMPC_OK && s <= log2n; s++) {
-    fr_ntt_stage_kernel<F><<<grid_for(ctx, n / 2, 8), kBlock, 0, ctx->stream>>>(log2n, s, vec(tw), mvec(out));
-    rc = post_launch(ctx, "fr_ntt_stage_kernel");
+  const int rest = log2n > kNttTileLog ? log2n - kNttTileLog : 0;
+  int passes = (rest + kNttStrideLog - 1) / kNttStrideLog;
+  for (int s0 = kNttTileLog; rc == ARKMPC_OK && s0 < log2n; passes--) {  // the remaining stages, spread evenly over <= 5-stage passes
+    const int T = (log2n - s0 + passes - 1) / passes;
+    const size_t blocks = n >> (5 + T);
+    fr_ntt_strided_kernel<F><<<(unsigned)blocks, kNttStrideThreads, 0, ctx->stream>>>(log2n, s0, T, vec(tw), mvec(out));
+    rc = post_launch(ctx, "fr_ntt_strided_kernel");
+    s0 += T;
   }
   if (rc == ARKMPC_OK && inverse) {
     fr_scale_dev_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(out), consts + 1, mvec(out));

@@ -247,4 +247,44 @@ __global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_beaver_recombine_k
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sum of points (the fold of AuthenticatedPointResult::msm, authenticated_curve.rs:798-803, and of CurvePoint sums): every
+// thread adds a grid-stride slice, a warp-shuffle tree and a shared-memory step fold the block, one partial per block; a
+// second single-block launch folds the partials.  `stride`-separated inputs let the share and mac halves of a PointShare
+// vector be summed in place.
+// ---------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ void pt_shfl_down(typename C::Pt& r, const typename C::Pt& p, int off) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&p);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int j = 0; j < C::kCoords * 8; j++) dst[j] = __shfl_down_sync(0xffffffffu, src[j], off);
+}
+
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_sum_kernel(size_t n, PVec a, PMVec out, int per_block) {
+  __shared__ typename C::Pt part[kPtBlock / 32];
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  typename C::Pt acc;
+  C::set_identity(acc);
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt x;
+    ld_pt<C>(x, a, i);
+    C::add(acc, x);
+  }
+#pragma unroll 1
+  for (int off = 16; off > 0; off >>= 1) {
+    typename C::Pt o;
+    pt_shfl_down<C>(o, acc, off);
+    C::add(acc, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kPtBlock / 32; w++) C::add(acc, part[w]);
+    st_pt<C>(out, per_block ? blockIdx.x : 0, acc);
+  }
+}
+
 }  // namespace ark

@@ -22,6 +22,7 @@ struct CurveOps {
   int (*sum_is_identity)(arkmpc_ctx*, size_t n, const void* mine, const void* peer, int* flag_dev);
   int (*normalize)(arkmpc_ctx*, size_t n, const void* pts, void* out_xy);
   int (*copy)(arkmpc_ctx*, size_t n, const void* in, uint32_t in_stride, void* out, uint32_t out_stride);
+  int (*sum)(arkmpc_ctx*, size_t n, const void* in, uint32_t in_stride, void* out_point);
 };
 
 const CurveOps* curve_ops_bn254();
@@ -157,8 +158,21 @@ struct CurveLaunch {
     return post_launch(ctx, "pt_copy_kernel");
   }
 
+  // scratch: ctx->partials holds 2 * kMaxPartialBlocks field elements = 64 KiB = 512 BN254 / 512 Edwards points at most
+  static int sum(arkmpc_ctx* ctx, size_t n, const void* in, uint32_t in_stride, void* out_point) {
+    const size_t cap = (size_t)2 * kMaxPartialBlocks * 32 / PB;
+    size_t blocks = (n + kPtBlock - 1) / kPtBlock;
+    if (blocks > cap) blocks = cap;
+    if (blocks > (size_t)ctx->sm_count * 2) blocks = (size_t)ctx->sm_count * 2;
+    if (blocks == 0) blocks = 1;
+    pt_sum_kernel<C><<<(unsigned)blocks, kPtBlock, 0, ctx->stream>>>(n, pvec(in, in_stride), pmvec(ctx->partials, PB), 1);
+    ctx->launches++;
+    pt_sum_kernel<C><<<1, kPtBlock, 0, ctx->stream>>>(blocks, pvec(ctx->partials, PB), pmvec(out_point, PB), 0);
+    return post_launch(ctx, "pt_sum_kernel");
+  }
+
   static const CurveOps* ops() {
-    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, normalize, copy};
+    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, normalize, copy, sum};
     return &t;
   }
 };

@@ -160,24 +160,39 @@ __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec
   for (size_t e = t; e < tile; e += kNttThreads) st_fe(out, base + e, x[e]);
 }
 
-// One stage s > 10 in global memory, in place
+// Stages s0+1 .. s0+T (s0 >= 10, T <= 5) in one pass: a block owns 32 consecutive low indices x 2^T strided positions
+// {hi*2^(s0+T) + k*2^s0 + lo : k < 2^T, lo in a 32-wide window}, i.e. 2^T rows of 1 KiB that are each contiguous in memory, so
+// loads and stores are fully coalesced; the T butterfly levels run in shared memory (32 KiB), one butterfly per thread per level.
+constexpr int kNttStrideLog = 5;                         // up to 5 stages per strided pass
+constexpr int kNttStrideThreads = 32 << (kNttStrideLog - 1);  // 512
+
 template <class F>
-__global__ void __launch_bounds__(kBlock) fr_ntt_stage_kernel(int log2n, int s, Vec tw, MVec x) {
-  const size_t nb = (size_t)1 << (log2n - 1);
-  const size_t half = (size_t)1 << (s - 1);
-  const size_t step = (size_t)gridDim.x * kBlock;
-  for (size_t b = (size_t)blockIdx.x * kBlock + threadIdx.x; b < nb; b += step) {
-    const size_t j = b & (half - 1);
-    const size_t i0 = ((b >> (s - 1)) << s) + j;
-    fe8 w, lo, hi;
-    ld_fe(w, tw, j << (log2n - s));
-    const Vec xr{x.p, x.stride};
-    ld_fe(lo, xr, i0);
-    ld_fe(hi, xr, i0 + half);
-    ntt_butterfly<F>(lo, hi, w);
-    st_fe(x, i0, lo);
-    st_fe(x, i0 + half, hi);
+__global__ void __launch_bounds__(kNttStrideThreads) fr_ntt_strided_kernel(int log2n, int s0, int T, Vec tw, MVec x) {
+  __shared__ __align__(32) fe8 sm[32 << kNttStrideLog];  // [k][lo]
+  const int lane = threadIdx.x & 31;
+  const int row = threadIdx.x >> 5;                       // 0 .. 15
+  const size_t lo_blocks = (size_t)1 << (s0 - 5);
+  const size_t hi = blockIdx.x / lo_blocks;
+  const size_t lo = (blockIdx.x % lo_blocks) * 32 + lane;
+  const size_t base = (hi << (s0 + T)) + lo;
+  const int rows = 1 << T;
+  const Vec xr{x.p, x.stride};
+  for (int k = row; k < rows; k += kNttStrideThreads / 32) ld_fe(sm[k * 32 + lane], xr, base + ((size_t)k << s0));
+  __syncthreads();
+  for (int t = 1; t <= T; t++) {
+    const int s = s0 + t;
+    const int halfk = 1 << (t - 1);
+    for (int b = row; b < rows / 2; b += kNttStrideThreads / 32) {
+      const int kl = b & (halfk - 1);
+      const int k = ((b >> (t - 1)) << t) + kl;
+      const size_t j = ((size_t)kl << s0) + lo;           // i0 mod 2^(s-1)
+      fe8 w;
+      ld_fe(w, tw, j << (log2n - s));
+      ntt_butterfly<F>(sm[k * 32 + lane], sm[(k + halfk) * 32 + lane], w);
+    }
+    __syncthreads();
   }
+  for (int k = row; k < rows; k += kNttStrideThreads / 32) st_fe(x, base + ((size_t)k << s0), sm[k * 32 + lane]);
 }
 
 }  // namespace ark

@@ -333,6 +333,23 @@ class Engine:
         self._call("arkmpc_pt_sum_is_identity", self._curve(), mine.shape[0], self._p(mine), self._p(peer), C.byref(flag))
         return bool(flag.value)
 
+    def pt_sum(self, pts) -> torch.Tensor:
+        out = self.empty_points(1)
+        n = pts.numel() * 8 // int(self.lib.arkmpc_point_bytes(self._curve()))
+        self._call("arkmpc_pt_sum", self.curve, n, self._p(pts), self._p(out))
+        return out
+
+    def pt_share_sum(self, a_ps) -> torch.Tensor:
+        out = self.empty_points(1, share=True)
+        self._call("arkmpc_pt_share_sum", self._curve(), a_ps.shape[0], self._p(a_ps), self._p(out))
+        return out
+
+    def pt_msm(self, scalars, pts) -> torch.Tensor:
+        """sum_i scalars[i] * pts[i] (public MSM)."""
+        out, scratch = self.empty_points(1), torch.empty_like(pts)
+        self._call("arkmpc_pt_msm", self._curve(), pts.shape[0], self._p(scalars), self._p(pts), self._p(scratch), self._p(out))
+        return out
+
     def pt_normalize(self, pts) -> torch.Tensor:
         """(n, words) projective -> (n, 8) canonical affine (x, y) Montgomery limbs."""
         n = pts.numel() * 8 // int(self.lib.arkmpc_point_bytes(self._curve()))

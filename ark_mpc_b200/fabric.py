@@ -606,6 +606,12 @@ class CurvePointResult:
         a.fabric.n_gates += 1
         return AuthenticatedPointResult(a.fabric, a.fabric.engine.pt_mul_authenticated(a.planes(), b.points))
 
+    @staticmethod
+    def msm(scalars: ScalarResult, points: "CurvePointResult") -> "CurvePointResult":  # curve.rs:549-560 (public MSM)
+        assert len(scalars) == len(points), "msm cannot compute on vectors of unequal length"
+        scalars.fabric.n_gates += 1
+        return CurvePointResult(scalars.fabric, scalars.fabric.engine.pt_msm(scalars.values, points.points))
+
     def to_affine_limbs(self) -> np.ndarray:
         """(n, 8) canonical affine (x, y) Montgomery limbs — the form parity is defined on."""
         E = self.fabric.engine
@@ -706,16 +712,9 @@ class AuthenticatedPointResult:
         return prod.sum()
 
     def sum(self) -> "AuthenticatedPointResult":
-        """Fold of PointShare additions (:798-803) as a pairwise tree of batched adds."""
-        E = self.fabric.engine
-        cur = self.shares
-        while cur.shape[0] > 1:
-            m = cur.shape[0]
-            h = m // 2
-            s = E.pt_add(cur[:h].contiguous(), cur[h:2 * h].contiguous())
-            cur = torch.cat([s, cur[2 * h:]], dim=0) if m % 2 else s
+        """Fold of PointShare additions (:798-803): one reduction kernel per half (share points, mac points)."""
         self.fabric.n_gates += 1
-        return AuthenticatedPointResult(self.fabric, cur)
+        return AuthenticatedPointResult(self.fabric, self.fabric.engine.pt_share_sum(self.shares))
 
     @staticmethod
     def open_batch(values) -> CurvePointResult:  # :66-109

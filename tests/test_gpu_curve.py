@@ -203,3 +203,44 @@ def test_point_empty_and_errors(engines, cv):
     assert E.pt_add(e, e).shape[0] == 0
     with pytest.raises(nat.ArkMpcError):
         E._call("arkmpc_pt_add", 7, 1, E._p(E.empty_points(1)), E._p(E.empty_points(1)), E._p(E.empty_points(1)))
+
+
+@pytest.mark.parametrize("cv", CURVES)
+@pytest.mark.parametrize("n", [0, 1, 33, 1000, 40000])
+def test_point_sums_and_msm(engines, cv, n):
+    """Sum of points / PointShares (authenticated_curve.rs:798-803) and the public MSM (curve.rs:549-560) against the oracle."""
+    E = engines[cv]
+    w = co.point_words(cv)
+    Cv = CURVE_BY_ID[cv]
+    ident = points_from_affine(cv, [Cv.identity])
+    if n == 0:
+        assert np.array_equal(norm_gpu(E, E.pt_sum(E.empty_points(0))), norm_cpu(cv, ident))
+        return
+    fr = co.CURVE_FR[cv]
+    pts, macs = rand_points(cv, 41, n), rand_points(cv, 42, n, with_identity=False)
+    acc_s, acc_m = ident.copy(), ident.copy()
+    for i in range(0, n, 1):  # the oracle folds serially, as the reference's gate does
+        acc_s = co.pt_add(cv, acc_s, pts[i:i + 1])
+        acc_m = co.pt_add(cv, acc_m, macs[i:i + 1])
+        if n > 2000 and i >= 1999:
+            break
+    m = min(n, 2000)
+    P = E.upload_points(pts[:m])
+    assert np.array_equal(norm_gpu(E, E.pt_sum(P)), norm_cpu(cv, acc_s))
+    ps = np.ascontiguousarray(np.concatenate([pts[:m], macs[:m]], axis=1))
+    got = E.download(E.pt_share_sum(E.upload_points(ps)))
+    assert np.array_equal(norm_cpu(cv, got[:, :w]), norm_cpu(cv, acc_s)) and np.array_equal(norm_cpu(cv, got[:, w:]), norm_cpu(cv, acc_m))
+    # MSM: sum_i s_i * P_i == (sum_i s_i * t_i) * G for P_i = t_i * G  (size-independent identity, checked at the full n)
+    t = co.synth(fr, 43, 0, n)
+    s = co.synth(fr, 44, 0, n)
+    T, S = E.upload(t), E.upload(s)
+    Pn = E.pt_mul_generator_public(T)
+    lhs = E.pt_msm(S, Pn)
+    rhs = E.pt_mul_generator_public(E.sum(E.mul(S, T)))
+    assert np.array_equal(norm_gpu(E, lhs), norm_gpu(E, rhs))
+    if n <= 1000:
+        want = ident.copy()
+        prods = co.pt_mul(cv, s, co.pt_mul_generator(cv, t))
+        for i in range(n):
+            want = co.pt_add(cv, want, prods[i:i + 1])
+        assert np.array_equal(norm_gpu(E, lhs), norm_cpu(cv, want))

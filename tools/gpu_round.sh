@@ -23,6 +23,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:beav
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pt_beaver_recombine -c 2 -o $OUT/prof_pt_recombine -f \
   python tools/bench_points.py 17 > $OUT/ncu_full_pt.log 2>&1; echo "ncu full pt rc=$?"
 ls -la $OUT
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fr_ntt_tile|fr_ntt_stage|fr_batch_inverse" -c 4 -o $OUT/prof_ntt -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fr_ntt_tile|fr_ntt_strided|fr_batch_inverse" -c 4 -o $OUT/prof_ntt -f \
   python tools/bench_extra.py > $OUT/ncu_full_ntt.log 2>&1; echo "ncu full ntt rc=$?"
 ls -la $OUT | head -40
