@@ -169,7 +169,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64 limbs (4x64 Montgomery, CIOS)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u64", "dtype_note": "4 x u64 limbs, Montgomery CIOS (the reference's arkworks representation)", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n} of the 2^{args.log2_batch} gates (two-party batch_mul) per step, {args.steps} steps, "
@@ -329,7 +329,7 @@ def run_supplementary(args, rank, world, local_rank):
     achieved = alg_bytes * n / (ms * 1e-3) / 1e9
     line = {"metric": metric, "value": n * world / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 limbs (8x32; Montgomery for BN254, special-form 2^255-19 for Curve25519)", "data": "synthetic",
+            "dtype": "u32", "dtype_note": "8 x u32 limbs; Montgomery for BN254, special-form 2^255-19 for Curve25519", "data": "synthetic",
             "config": {"workload": wl, "field": field, "log2_batch_per_gpu": args.log2_batch, "parties": 2,
                        "sharding": f"index-range x{world}, no data-path collective",
                        "l2_hygiene": "inputs larger than L2" if n * 64 > (126 << 20) else "step touches more than L2 in total"},
@@ -607,7 +607,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 limbs (8x32 Montgomery, IMAD.WIDE carry chains)", "data": "synthetic",
+        "dtype": "u32", "dtype_note": "256-bit field elements as 8 x u32 limbs, Montgomery form, IMAD.WIDE carry chains",
+        "data": "synthetic",
         "config": workload_config(args, world),
         "party_gates_per_sec": 2 * value,
         "step_hbm_gbs": (2 * (BYTES_MASK + BYTES_RECOMBINE) * n) / (ms_per_step * 1e-3) / 1e9,
