@@ -50,17 +50,15 @@ int main() {
   g.key.v[7] &= 0x0fffffffu;
   uint64_t s;
   for (int rep = 0; rep < 2; rep++) {
-    run<Bn254Fr, 256, 2>("baseline", n, g, sms, 2, &s);
-    run<Bn254Fr, 256, 4>("occ4 full grid", n, g, sms, 4096, &s);
-    run<Bn254Fr, 256, 3>("occ3 full grid", n, g, sms, 4096, &s);
-    run<Bn254Fr, 256, 2>("occ2 full grid", n, g, sms, 4096, &s);
-    run<Bn254Fr, 128, 8>("b128x8 full grid", n, g, sms, 8192, &s);
-    run<Bn254Fr, 128, 6>("b128x6 full grid", n, g, sms, 8192, &s);
-    run<Bn254Fr, 128, 4>("b128x4 full grid", n, g, sms, 8192, &s);
-    run<Bn254Fr, 512, 2>("b512x2 full grid", n, g, sms, 8192, &s);
-    run<Bn254Fr, 64, 16>("b64x16 full grid", n, g, sms, 16384, &s);
-    run<Curve25519Fr, 256, 4>("c25519 occ4 full grid", n, g, sms, 4096, &s);
-    run<Curve25519Fr, 256, 2>("c25519 baseline", n, g, sms, 2, &s);
+    run<Bn254Fr, 256, 3>("occ3 full grid (current)", n, g, sms, 1 << 20, &s);
+    run<Bn254Fr, 160, 5>("b160x5 (800 thr/SM)", n, g, sms, 1 << 20, &s);
+    run<Bn254Fr, 416, 2>("b416x2 (832 thr/SM)", n, g, sms, 1 << 20, &s);
+    run<Bn254Fr, 224, 3>("b224x3 (672 thr/SM)", n, g, sms, 1 << 20, &s);
+    run<Bn254Fr, 128, 6>("b128x6 (768 thr/SM)", n, g, sms, 1 << 20, &s);
+    run<Bn254Fr, 96, 8>("b96x8 (768 thr/SM)", n, g, sms, 1 << 20, &s);
+    run<Bn254Fr, 192, 4>("b192x4 (768 thr/SM)", n, g, sms, 1 << 20, &s);
+    run<Curve25519Fr, 256, 3>("c25519 occ3 (current)", n, g, sms, 1 << 20, &s);
+    run<Curve25519Fr, 160, 5>("c25519 b160x5", n, g, sms, 1 << 20, &s);
   }
   return 0;
 }
