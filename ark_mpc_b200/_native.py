@@ -99,7 +99,8 @@ _PROTOS = {
     "arkmpc_pt_sum_is_identity": [_vp, _i, _sz, _vp, _vp, C.POINTER(_i)],
     "arkmpc_pt_sum": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_pt_share_sum": [_vp, _i, _sz, _vp, _vp],
-    "arkmpc_pt_msm": [_vp, _i, _sz, _vp, _vp, _vp, _vp],
+    "arkmpc_pt_msm": [_vp, _i, _sz, _vp, _vp, _vp],
+    "arkmpc_pt_msm_authenticated": [_vp, _i, _sz, _vp, _vp, _vp, _vp],
     "arkmpc_pt_share_split": [_vp, _i, _sz, _vp, _vp, _vp],
     "arkmpc_pt_share_join": [_vp, _i, _sz, _vp, _vp, _vp],
     "arkmpc_pt_normalize": [_vp, _i, _sz, _vp, _vp],
@@ -137,11 +138,18 @@ def load() -> C.CDLL:
     return _lib
 
 
+_STATUS_TEXT = {0: "ok", -1: "invalid argument", -2: "CUDA error", -3: "no usable CUDA device", -4: "out of device memory",
+                -5: "unsupported in this build", -6: "NCCL error"}
+
+
 def _status_string(status: int) -> str:
-    try:
-        return load().arkmpc_status_string(status).decode()
-    except Exception:  # pragma: no cover
-        return "?"
+    # never calls load(): this runs while reporting that the library is MISSING (and load() holds a non-reentrant lock)
+    if _lib is not None:
+        try:
+            return _lib.arkmpc_status_string(status).decode()
+        except Exception:  # pragma: no cover
+            pass
+    return _STATUS_TEXT.get(status, "unknown status")
 
 
 def check(status: int, where: str, ctx: Optional[int] = None) -> None:

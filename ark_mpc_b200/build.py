@@ -69,7 +69,9 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=4) as pool:
         objs = list(pool.map(compile_one, sources()))
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs])
+    tmp = LIB + ".tmp"  # link beside the target and rename: a failed link must not remove a working library
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs])
+    os.replace(tmp, LIB)
     return LIB
 
 

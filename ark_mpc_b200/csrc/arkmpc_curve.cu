@@ -174,11 +174,25 @@ int arkmpc_pt_share_sum(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_
   return ops->sum(ctx, n, a + pb, 2 * pb, reinterpret_cast<char*>(out_ps) + pb);
 }
 
-int arkmpc_pt_msm(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* scalars, const uint64_t* pts, uint64_t* scratch_pts, uint64_t* out_pt) {
-  ARK_PT_PROLOGUE(scalars, pts, scratch_pts, out_pt);
-  int rc = ops->mul(ctx, n, scalars, 0, pts, scratch_pts);
+int arkmpc_pt_msm(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* scalars, const uint64_t* pts, uint64_t* out_pt) {
+  ARK_CHECK_CTX(ctx);
+  const CurveOps* ops = ops_for(curve);
+  ARK_REQUIRE(ctx, ops != nullptr, "unknown curve id");
+  ARK_REQUIRE(ctx, out_pt && aligned32(out_pt) && (n == 0 || (scalars && pts && aligned32(scalars) && aligned32(pts))), "null or misaligned array");
+  return ops->msm(ctx, n, scalars, pts, out_pt);
+}
+
+// CurvePoint::msm_authenticated (curve.rs:619-642): (sum share_i * P_i, sum mac_i * P_i)
+int arkmpc_pt_msm_authenticated(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* s_share, const uint64_t* s_mac, const uint64_t* pts,
+                                uint64_t* out_ps) {
+  ARK_CHECK_CTX(ctx);
+  const CurveOps* ops = ops_for(curve);
+  ARK_REQUIRE(ctx, ops != nullptr, "unknown curve id");
+  ARK_REQUIRE(ctx, out_ps && aligned32(out_ps) && (n == 0 || (s_share && s_mac && pts && aligned32(s_share) && aligned32(s_mac) && aligned32(pts))),
+              "null or misaligned array");
+  int rc = ops->msm(ctx, n, s_share, pts, out_ps);
   if (rc != ARKMPC_OK) return rc;
-  return ops->sum(ctx, n, scratch_pts, ops->point_bytes, out_pt);
+  return ops->msm(ctx, n, s_mac, pts, reinterpret_cast<char*>(out_ps) + ops->point_bytes);
 }
 
 int arkmpc_pt_normalize(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, uint64_t* out_xy) {

@@ -23,6 +23,7 @@ struct CurveOps {
   int (*normalize)(arkmpc_ctx*, size_t n, const void* pts, void* out_xy);
   int (*copy)(arkmpc_ctx*, size_t n, const void* in, uint32_t in_stride, void* out, uint32_t out_stride);
   int (*sum)(arkmpc_ctx*, size_t n, const void* in, uint32_t in_stride, void* out_point);
+  int (*msm)(arkmpc_ctx*, size_t n, const void* scalars, const void* pts, void* out_point);
 };
 
 const CurveOps* curve_ops_bn254();
@@ -32,6 +33,7 @@ const CurveOps* curve_ops_ed25519();
 
 #ifdef ARK_CURVE_IMPL
 #include "curve_kernels.cuh"
+#include "curve_msm.cuh"
 
 namespace arkctx {
 using namespace ark;
@@ -171,8 +173,62 @@ struct CurveLaunch {
     return post_launch(ctx, "pt_sum_kernel");
   }
 
+  // Public MSM: n parallel scalar multiplications + a sum below kMsmNaiveBelow points (the reference switches at
+  // MSM_SIZE_THRESHOLD = 10, curve.rs:34), the bucket method of curve_msm.cuh above.  Scratch is stream-ordered.
+  static constexpr size_t kMsmNaiveBelow = 256;
+  static int msm(arkmpc_ctx* ctx, size_t n, const void* scalars, const void* pts, void* out_point) {
+    cudaStream_t st = ctx->stream;
+    if (n < kMsmNaiveBelow) {
+      void* tmp = nullptr;
+      ARK_CUDA(ctx, cudaMallocAsync(&tmp, (n ? n : 1) * PB, st));
+      int rc = n ? mul(ctx, n, scalars, 0, pts, tmp) : ARKMPC_OK;
+      if (rc == ARKMPC_OK) rc = sum(ctx, n, tmp, PB, out_point);
+      cudaFreeAsync(tmp, st);
+      return rc;
+    }
+    int lg = 0;
+    while (((size_t)2 << lg) <= n) lg++;
+    int c = lg - 5;
+    c = c < 4 ? 4 : (c > 15 ? 15 : c);
+    const int bits = C::R::kBits;
+    const int W = (bits + c - 1) / c;
+    const size_t M = (size_t)W << c;
+    const size_t chunks = ((size_t)1 << c) / kMsmChunk ? ((size_t)1 << c) / kMsmChunk : 1;
+    uint32_t* counts = nullptr;
+    uint32_t* idx = nullptr;
+    char* ptmem = nullptr;
+    ARK_CUDA(ctx, cudaMallocAsync(&counts, 3 * M * sizeof(uint32_t), st));
+    uint32_t* offsets = counts + M;
+    uint32_t* cursors = counts + 2 * M;
+    cudaError_t e = cudaMallocAsync(&idx, n * (size_t)W * sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&ptmem, (M + chunks * W + W) * (size_t)PB, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, M * sizeof(uint32_t), st);
+    if (e != cudaSuccess) {
+      cudaFreeAsync(counts, st);
+      if (idx) cudaFreeAsync(idx, st);
+      if (ptmem) cudaFreeAsync(ptmem, st);
+      return fail(ctx, e == cudaErrorMemoryAllocation ? ARKMPC_ERR_OOM : ARKMPC_ERR_CUDA, std::string("msm scratch: ") + cudaGetErrorString(e));
+    }
+    char* buckets = ptmem;
+    char* partials = ptmem + M * PB;
+    char* wsum = partials + chunks * W * PB;
+    msm_count_kernel<C><<<grid_for(ctx, n, 8), kBlock, 0, st>>>(n, vec(scalars), c, W, counts);
+    msm_scan_kernel<<<1, kMsmScanThreads, 0, st>>>(M, counts, offsets, cursors);
+    msm_scatter_kernel<C><<<grid_for(ctx, n, 8), kBlock, 0, st>>>(n, vec(scalars), c, W, offsets, cursors, idx);
+    msm_bucket_kernel<C><<<(unsigned)((M + kPtBlock - 1) / kPtBlock), kPtBlock, 0, st>>>(M, offsets, counts, idx, pvec(pts, PB), pmvec(buckets, PB));
+    msm_chunk_kernel<C><<<(unsigned)((chunks * W + kPtBlock - 1) / kPtBlock), kPtBlock, 0, st>>>(c, W, pvec(buckets, PB), pmvec(partials, PB));
+    msm_window_kernel<C><<<W, kPtBlock, 0, st>>>(c, chunks, pvec(partials, PB), pmvec(wsum, PB));
+    ctx->launches += 5;
+    int rc = post_launch(ctx, "msm kernels");
+    if (rc == ARKMPC_OK) rc = sum(ctx, (size_t)W, wsum, PB, out_point);
+    cudaFreeAsync(counts, st);
+    cudaFreeAsync(idx, st);
+    cudaFreeAsync(ptmem, st);
+    return rc;
+  }
+
   static const CurveOps* ops() {
-    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, normalize, copy, sum};
+    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, normalize, copy, sum, msm};
     return &t;
   }
 };

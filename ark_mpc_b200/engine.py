@@ -345,9 +345,14 @@ class Engine:
         return out
 
     def pt_msm(self, scalars, pts) -> torch.Tensor:
-        """sum_i scalars[i] * pts[i] (public MSM)."""
-        out, scratch = self.empty_points(1), torch.empty_like(pts)
-        self._call("arkmpc_pt_msm", self._curve(), pts.shape[0], self._p(scalars), self._p(pts), self._p(scratch), self._p(out))
+        """sum_i scalars[i] * pts[i] (public MSM, bucket method)."""
+        out = self.empty_points(1)
+        self._call("arkmpc_pt_msm", self._curve(), pts.shape[0], self._p(scalars), self._p(pts), self._p(out))
+        return out
+
+    def pt_msm_authenticated(self, s: Planes, pts) -> torch.Tensor:
+        out = self.empty_points(1, share=True)
+        self._call("arkmpc_pt_msm_authenticated", self._curve(), pts.shape[0], self._p(s[0]), self._p(s[1]), self._p(pts), self._p(out))
         return out
 
     def pt_normalize(self, pts) -> torch.Tensor:

@@ -612,6 +612,12 @@ class CurvePointResult:
         scalars.fabric.n_gates += 1
         return CurvePointResult(scalars.fabric, scalars.fabric.engine.pt_msm(scalars.values, points.points))
 
+    @staticmethod
+    def msm_authenticated(scalars: "AuthenticatedScalarResult", points: "CurvePointResult") -> "AuthenticatedPointResult":  # curve.rs:619-642
+        assert len(scalars) == len(points), "msm cannot compute on vectors of unequal length"
+        scalars.fabric.n_gates += 1
+        return AuthenticatedPointResult(scalars.fabric, scalars.fabric.engine.pt_msm_authenticated(scalars.planes(), points.points))
+
     def to_affine_limbs(self) -> np.ndarray:
         """(n, 8) canonical affine (x, y) Montgomery limbs — the form parity is defined on."""
         E = self.fabric.engine

@@ -242,12 +242,15 @@ int arkmpc_pt_mac_check(arkmpc_ctx* ctx, int curve, const uint64_t* key_host, si
 /* *all_identity_host = 1 iff mine[i] + peer[i] is the identity for every i (:128-131).  Synchronous. */
 int arkmpc_pt_sum_is_identity(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* mine_pts, const uint64_t* peer_pts, int* all_identity_host);
 /* Sums (CurvePoint / PointShare `Sum`, the fold of AuthenticatedPointResult::msm :798-803): out = sum of n points (the identity for
- * n == 0); arkmpc_pt_share_sum sums the share and the mac points of n PointShares into one PointShare.  arkmpc_pt_msm is the public
- * multiscalar multiplication sum_i s[i] * P[i] (`CurvePoint::msm`, curve.rs:549-560) evaluated as n parallel windowed scalar
- * multiplications into scratch_pts (n points) followed by the sum; it replaces ark-ec's Pippenger call, not its algorithm. */
+ * n == 0); arkmpc_pt_share_sum sums the share and the mac points of n PointShares into one PointShare. */
 int arkmpc_pt_sum(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, uint64_t* out_pt);
 int arkmpc_pt_share_sum(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_ps, uint64_t* out_ps);
-int arkmpc_pt_msm(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* scalars, const uint64_t* pts, uint64_t* scratch_pts, uint64_t* out_pt);
+/* Public multiscalar multiplication sum_i s[i] * P[i]: `CurvePoint::msm` (curve.rs:549-560, which calls ark-ec's Pippenger), and
+ * `CurvePoint::msm_authenticated` (curve.rs:619-642): out = (sum share[i]*P[i], sum mac[i]*P[i]).  Bucket method on the device
+ * (csrc/curve_msm.cuh); below 256 points, parallel scalar multiplications and a sum.  Scratch is allocated stream-ordered. */
+int arkmpc_pt_msm(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* scalars, const uint64_t* pts, uint64_t* out_pt);
+int arkmpc_pt_msm_authenticated(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* s_share, const uint64_t* s_mac,
+                                const uint64_t* pts, uint64_t* out_ps);
 /* PointShare vector <-> separate vectors of share points and mac points (either output of split may be NULL) */
 int arkmpc_pt_share_split(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_ps, uint64_t* share_pts, uint64_t* mac_pts);
 int arkmpc_pt_share_join(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* share_pts, const uint64_t* mac_pts, uint64_t* out_ps);

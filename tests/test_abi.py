@@ -48,3 +48,14 @@ def test_no_device_is_reported_not_faked(has_gpu):
 
     with pytest.raises(nat.ArkMpcError):
         Engine(0, "bn254_fr")
+
+
+def test_missing_library_fails_loudly_not_silently(tmp_path, monkeypatch):
+    """No CPU fallback and no hang: with the shared library absent, load() raises an ArkMpcError that says how to build it."""
+    import pytest
+
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(nat, "LIB_PATH", str(tmp_path / "libarkmpc_b200.so"))
+    with pytest.raises(nat.ArkMpcError) as e:
+        nat.load()
+    assert "missing" in str(e.value) and "no CPU fallback" in str(e.value)

@@ -238,6 +238,11 @@ def test_point_sums_and_msm(engines, cv, n):
     lhs = E.pt_msm(S, Pn)
     rhs = E.pt_mul_generator_public(E.sum(E.mul(S, T)))
     assert np.array_equal(norm_gpu(E, lhs), norm_gpu(E, rhs))
+    # msm_authenticated (curve.rs:619-642): two MSMs over the same points
+    m2 = co.synth(fr, 45, 0, n)
+    got2 = E.download(E.pt_msm_authenticated((S, E.upload(m2)), Pn))
+    assert np.array_equal(norm_cpu(cv, got2[:, :w]), norm_gpu(E, lhs))
+    assert np.array_equal(norm_cpu(cv, got2[:, w:]), norm_gpu(E, E.pt_mul_generator_public(E.sum(E.mul(E.upload(m2), T)))))
     if n <= 1000:
         want = ident.copy()
         prods = co.pt_mul(cv, s, co.pt_mul_generator(cv, t))
