@@ -47,4 +47,6 @@ for field, curve in (("curve25519_fr", "curve25519_edwards"), ("bn254_fr", "bn25
         t2 = timed("pt_beaver_recombine", lambda: E.pt_beaver_recombine(0, key, d, d, Em, Em, (a_s, a_m), (b_s, b_m), (c_s, c_m), out=out))
         print(f"{curve:20s} two-party point Beaver mults/s (both parties on one GPU): {n / (2 * (t1 + t2)) * 1e3:,.0f}", flush=True)
         timed("pt_normalize", lambda: E.pt_normalize(pts))
+        timed("pt_sum", lambda: E.pt_sum(pts))
+        timed("pt_msm (bucket method)", lambda: E.pt_msm(xs, pts))
         E.close()
