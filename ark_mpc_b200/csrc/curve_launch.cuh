@@ -173,9 +173,11 @@ struct CurveLaunch {
     return post_launch(ctx, "pt_sum_kernel");
   }
 
-  // Public MSM: n parallel scalar multiplications + a sum below kMsmNaiveBelow points (the reference switches at
-  // MSM_SIZE_THRESHOLD = 10, curve.rs:34), the bucket method of curve_msm.cuh above.  Scratch is stream-ordered.
-  static constexpr size_t kMsmNaiveBelow = 256;
+  // Public MSM: n parallel scalar multiplications + a sum below kMsmNaiveBelow points (the reference switches to Pippenger at
+  // MSM_SIZE_THRESHOLD = 10, curve.rs:34; on the GPU the bucket method's serial tail — up to 253 dependent doublings to weight
+  // the top window, ~0.5-0.8 ms — only pays off from ~2^15 points: measured 2^12: 0.63 ms naive vs 1.09 ms buckets, 2^16: 1.82 vs
+  // 1.48 ms, 2^20: 25.5 vs 7.1 ms on Curve25519), the bucket method of curve_msm.cuh above.  Scratch is stream-ordered.
+  static constexpr size_t kMsmNaiveBelow = (size_t)1 << 15;
   static int msm(arkmpc_ctx* ctx, size_t n, const void* scalars, const void* pts, void* out_point) {
     cudaStream_t st = ctx->stream;
     if (n < kMsmNaiveBelow) {
@@ -197,12 +199,14 @@ struct CurveLaunch {
     uint32_t* counts = nullptr;
     uint32_t* idx = nullptr;
     char* ptmem = nullptr;
-    ARK_CUDA(ctx, cudaMallocAsync(&counts, 3 * M * sizeof(uint32_t), st));
+    ARK_CUDA(ctx, cudaMallocAsync(&counts, (4 * M + 1) * sizeof(uint32_t), st));
     uint32_t* offsets = counts + M;
     uint32_t* cursors = counts + 2 * M;
+    uint32_t* biglist = counts + 3 * M;  // [0] = number of over-full buckets, then their keys
     cudaError_t e = cudaMallocAsync(&idx, n * (size_t)W * sizeof(uint32_t), st);
     if (e == cudaSuccess) e = cudaMallocAsync(&ptmem, (M + chunks * W + W) * (size_t)PB, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(counts, 0, M * sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(biglist, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) {
       cudaFreeAsync(counts, st);
       if (idx) cudaFreeAsync(idx, st);
@@ -215,10 +219,11 @@ struct CurveLaunch {
     msm_count_kernel<C><<<grid_for(ctx, n, 8), kBlock, 0, st>>>(n, vec(scalars), c, W, counts);
     msm_scan_kernel<<<1, kMsmScanThreads, 0, st>>>(M, counts, offsets, cursors);
     msm_scatter_kernel<C><<<grid_for(ctx, n, 8), kBlock, 0, st>>>(n, vec(scalars), c, W, offsets, cursors, idx);
-    msm_bucket_kernel<C><<<(unsigned)((M + kPtBlock - 1) / kPtBlock), kPtBlock, 0, st>>>(M, offsets, counts, idx, pvec(pts, PB), pmvec(buckets, PB));
+    msm_bucket_kernel<C><<<(unsigned)((M + kPtBlock - 1) / kPtBlock), kPtBlock, 0, st>>>(M, offsets, counts, idx, pvec(pts, PB), pmvec(buckets, PB), biglist);
+    msm_bigbucket_kernel<C><<<(unsigned)(ctx->sm_count * 2), kPtBlock, 0, st>>>(offsets, counts, idx, pvec(pts, PB), pmvec(buckets, PB), biglist);
     msm_chunk_kernel<C><<<(unsigned)((chunks * W + kPtBlock - 1) / kPtBlock), kPtBlock, 0, st>>>(c, W, pvec(buckets, PB), pmvec(partials, PB));
     msm_window_kernel<C><<<W, kPtBlock, 0, st>>>(c, chunks, pvec(partials, PB), pmvec(wsum, PB));
-    ctx->launches += 5;
+    ctx->launches += 6;
     int rc = post_launch(ctx, "msm kernels");
     if (rc == ARKMPC_OK) rc = sum(ctx, (size_t)W, wsum, PB, out_point);
     cudaFreeAsync(counts, st);

@@ -6,7 +6,7 @@
 //   1. msm_count    histogram of the non-zero window digits of every scalar            (n threads, atomics on W * 2^c counters)
 //   2. msm_scan     exclusive prefix sum of the histogram                               (one block)
 //   3. msm_scatter  counting sort: point indices grouped by (window, digit)             (n threads)
-//   4. msm_bucket   one thread per bucket adds its points                                (W * 2^c threads, ~n*W additions in total)
+//   4. msm_bucket   one thread per bucket adds its points; over-full buckets go to msm_bigbucket (one block per bucket)
 //   5. msm_chunk    one thread per run of 32 buckets: sum_b b*B_b by running sums plus one small scalar multiple
 //   6. msm_window   one block per window folds its chunks and scales by 2^(c*w); a final point sum adds the W windows
 // ~n*W + 3*W*2^c point additions instead of n full scalar multiplications (~2600 field multiplications each).
@@ -82,15 +82,23 @@ __global__ void __launch_bounds__(kBlock) msm_scatter_kernel(size_t n, Vec s, in
   }
 }
 
-// bucket[key] = sum of the points whose digit in window (key >> c) is (key & mask)
+// bucket[key] = sum of the points whose digit in window (key >> c) is (key & mask).  One thread per bucket; buckets with more
+// than kMsmBigBucket points (the top window of a scalar field whose bit length is not a multiple of c has few, very full
+// buckets: a third of all BN254 scalars share bit 253) are queued for msm_bigbucket_kernel, where a whole block sums each.
+constexpr uint32_t kMsmBigBucket = 256;
+
 template <class C>
 __global__ void __launch_bounds__(kPtBlock) msm_bucket_kernel(size_t m, const uint32_t* offsets, const uint32_t* counts, const uint32_t* idx, PVec pts,
-                                                             PMVec buckets) {
+                                                             PMVec buckets, uint32_t* biglist /* [0] = count, then keys */) {
   const size_t step = (size_t)gridDim.x * kPtBlock;
   for (size_t key = (size_t)blockIdx.x * kPtBlock + threadIdx.x; key < m; key += step) {
+    const uint32_t off = offsets[key], cnt = counts[key];
+    if (cnt > kMsmBigBucket) {
+      biglist[1 + atomicAdd(&biglist[0], 1u)] = (uint32_t)key;
+      continue;
+    }
     typename C::Pt acc;
     C::set_identity(acc);
-    const uint32_t off = offsets[key], cnt = counts[key];
 #pragma unroll 1
     for (uint32_t j = 0; j < cnt; j++) {
       typename C::Pt x;
@@ -98,6 +106,39 @@ __global__ void __launch_bounds__(kPtBlock) msm_bucket_kernel(size_t m, const ui
       C::add(acc, x);
     }
     st_pt<C>(buckets, key, acc);
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) msm_bigbucket_kernel(const uint32_t* offsets, const uint32_t* counts, const uint32_t* idx, PVec pts, PMVec buckets,
+                                                                const uint32_t* biglist) {
+  __shared__ typename C::Pt part[kPtBlock / 32];
+  const uint32_t nbig = biglist[0];
+  for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
+    const uint32_t key = biglist[1 + b];
+    const uint32_t off = offsets[key], cnt = counts[key];
+    typename C::Pt acc;
+    C::set_identity(acc);
+#pragma unroll 1
+    for (uint32_t j = threadIdx.x; j < cnt; j += kPtBlock) {
+      typename C::Pt x;
+      ld_pt<C>(x, pts, idx[off + j]);
+      C::add(acc, x);
+    }
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+      typename C::Pt t;
+      pt_shfl_down<C>(t, acc, o);
+      C::add(acc, t);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < kPtBlock / 32; k++) C::add(acc, part[k]);
+      st_pt<C>(buckets, key, acc);
+    }
+    __syncthreads();
   }
 }
 

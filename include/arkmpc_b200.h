@@ -247,7 +247,7 @@ int arkmpc_pt_sum(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, uin
 int arkmpc_pt_share_sum(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_ps, uint64_t* out_ps);
 /* Public multiscalar multiplication sum_i s[i] * P[i]: `CurvePoint::msm` (curve.rs:549-560, which calls ark-ec's Pippenger), and
  * `CurvePoint::msm_authenticated` (curve.rs:619-642): out = (sum share[i]*P[i], sum mac[i]*P[i]).  Bucket method on the device
- * (csrc/curve_msm.cuh); below 256 points, parallel scalar multiplications and a sum.  Scratch is allocated stream-ordered. */
+ * (csrc/curve_msm.cuh); below 2^15 points, parallel scalar multiplications and a sum.  Scratch is allocated stream-ordered. */
 int arkmpc_pt_msm(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* scalars, const uint64_t* pts, uint64_t* out_pt);
 int arkmpc_pt_msm_authenticated(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* s_share, const uint64_t* s_mac,
                                 const uint64_t* pts, uint64_t* out_ps);

@@ -206,7 +206,7 @@ def test_point_empty_and_errors(engines, cv):
 
 
 @pytest.mark.parametrize("cv", CURVES)
-@pytest.mark.parametrize("n", [0, 1, 33, 1000, 40000])
+@pytest.mark.parametrize("n", [0, 1, 33, 1000, 40000, 70001])
 def test_point_sums_and_msm(engines, cv, n):
     """Sum of points / PointShares (authenticated_curve.rs:798-803) and the public MSM (curve.rs:549-560) against the oracle."""
     E = engines[cv]
