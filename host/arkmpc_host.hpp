@@ -247,6 +247,7 @@ struct ScalarResult {  // a batch of public scalars: one device plane
   static ScalarResult batch_sub(const ScalarResult& a, const ScalarResult& b);
   static ScalarResult batch_mul(const ScalarResult& a, const ScalarResult& b);  // scalar_result.rs:257-278
   static ScalarResult batch_neg(const ScalarResult& a);
+  static ScalarResult batch_inverse(const ScalarResult& a);                     // scalar.rs:93-100 (zeros stay zero)
   std::vector<uint64_t> to_host() const;  // n x 4 Montgomery limbs
 };
 
@@ -274,13 +275,18 @@ struct AuthenticatedScalarResult {  // a batch of ScalarShares: two device plane
   static ScalarResult open_batch(const AuthenticatedScalarResult& v);                                                  // :129-172
   static AuthenticatedScalarOpenResult open_authenticated_batch(const AuthenticatedScalarResult& v);                   // :278-354
   AuthenticatedScalarResult sum() const;                                                                               // :563-576
+  // ark-poly fft / ifft on the share and mac planes (:1011-1070); len() must be a power of two (the caller pads, as D::new does)
+  static AuthenticatedScalarResult fft(const AuthenticatedScalarResult& x, bool inverse = false);
 };
 
+struct AuthenticatedPointResult;
 struct CurvePointResult {  // a batch of public points, AoS projective image
   MpcFabric* fabric = nullptr;
   Buf points;
   size_t n = 0;
   size_t len() const { return n; }
+  static CurvePointResult msm(const ScalarResult& scalars, const CurvePointResult& points);                                // curve.rs:549-560
+  static AuthenticatedPointResult msm_authenticated(const AuthenticatedScalarResult& scalars, const CurvePointResult& points);  // :619-642
   std::vector<uint64_t> to_affine_host() const;  // n x 8: canonical affine (x, y)
 };
 
@@ -533,6 +539,12 @@ inline ScalarResult ScalarResult::batch_neg(const ScalarResult& a) {
   ARKMPC_F->count_gate();
   return {a.fabric, o, a.n};
 }
+inline ScalarResult ScalarResult::batch_inverse(const ScalarResult& a) {
+  Buf o = ARKMPC_F->alloc(a.n * 32);
+  ARKMPC_F->ctx()->check(arkmpc_fr_batch_inverse(ARKMPC_F->raw(), ARKMPC_F->curve().field, a.n, a.values->u64(), o->u64()), "arkmpc_fr_batch_inverse");
+  ARKMPC_F->count_gate();
+  return {a.fabric, o, a.n};
+}
 inline std::vector<uint64_t> ScalarResult::to_host() const { return fabric->download(values, n * 32); }
 
 namespace detail {
@@ -653,7 +665,26 @@ inline AuthenticatedScalarResult AuthenticatedScalarResult::sum() const {
   return {fabric, s, m, 1};
 }
 
+inline AuthenticatedScalarResult AuthenticatedScalarResult::fft(const AuthenticatedScalarResult& x, bool inverse) {
+  MpcFabric* f = x.fabric;
+  if (x.n == 0 || (x.n & (x.n - 1))) throw std::invalid_argument("fft: the length must be a non-zero power of two");
+  int log2n = 0;
+  while (((size_t)1 << log2n) < x.n) log2n++;
+  Buf s = f->alloc(x.n * 32), m = f->alloc(x.n * 32);
+  f->ctx()->check(arkmpc_fr_share_fft(f->raw(), f->curve().field, log2n, inverse ? 1 : 0, x.share->u64(), x.mac->u64(), s->u64(), m->u64()), "arkmpc_fr_share_fft");
+  f->count_gate();
+  return {f, s, m, x.n};
+}
+
 // ---- points ----
+inline CurvePointResult CurvePointResult::msm(const ScalarResult& scalars, const CurvePointResult& points) {
+  detail::same_len(scalars.n, points.n, "msm");
+  MpcFabric* f = points.fabric;
+  Buf o = f->alloc(f->curve().point_words * 8);
+  f->ctx()->check(arkmpc_pt_msm(f->raw(), f->curve().curve, points.n, scalars.values->u64(), points.points->u64(), o->u64()), "arkmpc_pt_msm");
+  f->count_gate();
+  return {f, o, 1};
+}
 inline std::vector<uint64_t> CurvePointResult::to_affine_host() const {
   Buf xy = fabric->alloc(n * 64);
   fabric->ctx()->check(arkmpc_pt_normalize(fabric->raw(), fabric->curve().curve, n, points->u64(), xy->u64()), "arkmpc_pt_normalize");
@@ -771,6 +802,15 @@ inline AuthenticatedPointOpenResult AuthenticatedPointResult::open_authenticated
   f->ctx()->check(arkmpc_pt_sum_is_identity(f->raw(), cid, n, checks->u64(), peer_checks->u64(), &ident), "arkmpc_pt_sum_is_identity");  // :128-131
   f->count_gate(3);
   return {opened, ok && ident == 1};
+}
+inline AuthenticatedPointResult CurvePointResult::msm_authenticated(const AuthenticatedScalarResult& scalars, const CurvePointResult& points) {
+  detail::same_len(scalars.n, points.n, "msm");
+  MpcFabric* f = points.fabric;
+  Buf o = f->alloc(2 * f->curve().point_words * 8);
+  f->ctx()->check(arkmpc_pt_msm_authenticated(f->raw(), f->curve().curve, points.n, scalars.share->u64(), scalars.mac->u64(), points.points->u64(), o->u64()),
+                  "arkmpc_pt_msm_authenticated");
+  f->count_gate();
+  return {f, o, 1};
 }
 #undef ARKMPC_F
 

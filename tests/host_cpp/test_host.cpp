@@ -15,6 +15,9 @@ void orc_scalar_batch_add(int f, size_t n, uint64_t* o, const uint64_t* a, const
 void orc_pt_mul_generator(int cv, size_t n, const uint64_t* scalars, uint64_t* out);
 void orc_pt_mul(int cv, size_t n, const uint64_t* scalars, const uint64_t* pts, uint64_t* out);
 void orc_pt_normalize(int cv, size_t n, const uint64_t* pts, uint64_t* out_xy);
+void orc_batch_inverse(int f, size_t n, uint64_t* out, const uint64_t* in);
+int orc_fft(int f, int log2n, int inverse, const uint64_t* in, uint64_t* out);
+void orc_pt_add(int cv, size_t n, const uint64_t* a, const uint64_t* b, uint64_t* out, int sub);
 }
 
 using namespace arkmpc;
@@ -106,6 +109,45 @@ static void test_corruption(const CurveInfo& cv) {  // integration/src/authentic
   EXPECT(res.first == 1 && res.second == 1, "a corrupted MAC makes open_authenticated fail on both parties");
 }
 
+// the "next" rows: public batch inversion, FFT on shares (BN254 only), msm_authenticated with public points
+static void test_next_rows(const CurveInfo& cv, const char* name) {
+  const size_t n = 64, w = cv.point_words;
+  HostScalars a, t;
+  a.limbs.resize(n * 4); t.limbs.resize(n * 4);
+  orc_synth(cv.field, 31, 0, n, a.limbs.data());
+  orc_synth(cv.field, 32, 0, n, t.limbs.data());
+  std::vector<uint64_t> want_inv(n * 4), want_fft(n * 4), P(n * w), prod(n * w), acc(w), tmp(w), want_msm(8);
+  orc_batch_inverse(cv.field, n, want_inv.data(), a.limbs.data());
+  const bool has_fft = orc_fft(cv.field, 6, 0, a.limbs.data(), want_fft.data()) == 0;
+  orc_pt_mul_generator(cv.curve, n, t.limbs.data(), P.data());
+  orc_pt_mul(cv.curve, n, a.limbs.data(), P.data(), prod.data());
+  memcpy(acc.data(), prod.data(), w * 8);
+  for (size_t i = 1; i < n; i++) { orc_pt_add(cv.curve, 1, acc.data(), prod.data() + i * w, tmp.data(), 0); acc = tmp; }
+  orc_pt_normalize(cv.curve, 1, acc.data(), want_msm.data());
+  using Out = std::vector<std::vector<uint64_t>>;
+  auto res = execute_mock_mpc<Out>(cv, party_id_source(cv), [&](MpcFabric& f) {
+    ScalarResult va = f.allocate_scalars(a);
+    CurvePointResult pts{&f, f.upload(P.data(), n * w * 8), n};
+    auto A = f.batch_share_scalar(f.party_id() == 0 ? &va : nullptr, n, 0);
+    using S = AuthenticatedScalarResult;
+    Out o;
+    o.push_back(ScalarResult::batch_inverse(va).to_host());
+    if (has_fft) o.push_back(S::open_authenticated_batch(S::fft(A)).result().to_host());
+    else o.push_back({});
+    auto m = AuthenticatedPointResult::open_authenticated_batch(CurvePointResult::msm_authenticated(A, pts));
+    o.push_back(m.result().to_affine_host());
+    o.push_back(CurvePointResult::msm(va, pts).to_affine_host());
+    return o;
+  });
+  for (const Out* o : {&res.first, &res.second}) {
+    EXPECT((*o)[0] == want_inv, "public batch_inverse");
+    if (has_fft) EXPECT((*o)[1] == want_fft, "fft on shares opens to the transform of the plaintext");
+    EXPECT((*o)[2] == want_msm, "msm_authenticated opens to sum a_i * P_i");
+    EXPECT((*o)[3] == want_msm, "public msm");
+  }
+  printf("%s: inverse / fft / msm done\n", name);
+}
+
 static void test_points(const CurveInfo& cv, const char* name) {
   const size_t n = 24, w = cv.point_words;
   HostScalars x, s;
@@ -146,6 +188,7 @@ int main() {
     test_party_id_kat(kv.first);
     test_corruption(kv.first);
     test_points(kv.first, kv.second);
+    test_next_rows(kv.first, kv.second);
   }
   try {  // length mismatch is a programming error, as the reference's assert (authenticated_scalar.rs:852)
     auto cv = bn254();
