@@ -616,7 +616,11 @@ def main():
                      "frac": achieved / peak, "traffic": traffic[0] if traffic else None,
                      "traffic_source": traffic[1] if traffic else None, "peak_source": peak_src, "kernel_us": 1e3 * k2_ms,
                      "algorithmic_bytes_per_launch": BYTES_RECOMBINE * n,
-                     "modmul_equiv_per_sec": 6 * n / (k2_ms * 1e-3)},
+                     "modmul_equiv_per_sec": 6 * n / (k2_ms * 1e-3),
+                     # the second bound of this kernel: 501 IMAD.WIDE per gate at the measured issue rate of
+                     # 31.5 lanes/clk/SM (tools/pipe_bench.cu, profiles/r01a_pipe_bench.txt) at the sampled SM clock
+                     "int_pipe_floor_us": (501 * n / (31.5 * E.sm_count * (clocks.get("sm_mhz") or 1965.0) * 1e6)) * 1e6,
+                     "hbm_floor_us": BYTES_RECOMBINE * n / (peak * 1e9) * 1e6},
         "clocks": clocks, "gpu_launches": int(launches) * world,
     }
     if e2e:

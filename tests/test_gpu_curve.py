@@ -249,3 +249,29 @@ def test_point_sums_and_msm(engines, cv, n):
         for i in range(n):
             want = co.pt_add(cv, want, prods[i:i + 1])
         assert np.array_equal(norm_gpu(E, lhs), norm_cpu(cv, want))
+
+
+def test_point_and_ntt_argument_errors(engines):
+    """Error behaviour at the boundary: bad curve / party ids, misaligned or missing arrays and aliased FFT planes are reported as
+    ARKMPC_ERR_INVALID with a message; nothing is computed."""
+    import ctypes as C
+
+    import ark_mpc_b200._native as nat
+
+    E = engines[0]
+    lib, ctx = E.lib, E.ctx
+    pts = E.pt_mul_generator_public(E.random(1, 0, 4))
+    s = E.random(2, 0, 4)
+    key = E.key_limbs(co.synth(0, 3, 0, 1)[0])
+    kp = key.ctypes.data_as(C.c_void_p)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    assert lib.arkmpc_pt_mul(ctx, 9, 4, p(s), p(pts), p(pts)) == nat.ERR_INVALID                      # unknown curve
+    assert lib.arkmpc_pt_mul(ctx, 0, 4, None, p(pts), p(pts)) == nat.ERR_INVALID                      # null array
+    assert lib.arkmpc_pt_mul(ctx, 0, 4, p(s), C.c_void_p(pts.data_ptr() + 8), p(pts)) == nat.ERR_INVALID  # misaligned
+    assert b"aligned" in lib.arkmpc_last_error(ctx)
+    ps = E.pt_mul_generator((s, s))
+    assert lib.arkmpc_pt_share_add_public(ctx, 0, 2, kp, 4, p(ps), p(pts), p(ps)) == nat.ERR_INVALID  # party id
+    assert lib.arkmpc_pt_beaver_recombine(ctx, 0, 0, kp, 4, p(s), p(s), p(pts), p(pts), p(s), p(s), p(s), p(s), p(s), p(s), p(ps), p(s), None) == nat.ERR_INVALID
+    assert lib.arkmpc_fr_fft(ctx, 0, 2, 0, p(s), p(s)) == nat.ERR_INVALID                             # in place is not supported
+    assert lib.arkmpc_fr_fft(ctx, 0, 40, 0, p(s), p(pts)) == nat.ERR_INVALID                          # domain too large
+    assert lib.arkmpc_pt_mul(ctx, 0, 0, None, None, None) == nat.OK                                   # empty batch is a no-op
