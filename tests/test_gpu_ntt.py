@@ -124,3 +124,26 @@ def test_two_party_polynomial_product_via_fft():
         for j, y in enumerate(pb):
             want[i + j] = (want[i + j] + x * y) % Fd.p
     assert r0 == r1 == want
+
+
+@pytest.mark.parametrize("field", ["bn254_fr", "curve25519_fr"])
+def test_two_party_div_and_add_constant(field):
+    """authenticated_scalar.rs tests `test_div` (a / b = a * b^-1, :1596-1620 region) and add/sub with a constant."""
+    from ark_mpc_b200 import fabric as F
+
+    p = po.FIELDS[field].p
+    rng = random.Random(15)
+    a = [rng.randrange(p) for _ in range(40)]
+    b = [rng.randrange(1, p) for _ in range(40)]
+
+    def party(fabric):
+        S = F.AuthenticatedScalarResult
+        A = fabric.batch_share_scalar(a if fabric.party_id() == 0 else len(a), 0)
+        B = fabric.batch_share_scalar(b if fabric.party_id() == 1 else len(b), 1)
+        quot = S.batch_mul(A, S.batch_inverse(B))
+        plus7 = S.batch_add_public(A, fabric.allocate_scalars([7] * len(a)))
+        return (S.open_authenticated_batch(quot).result().to_ints(), S.open_authenticated_batch(plus7).result().to_ints())
+
+    r0, r1 = F.execute_mock_mpc(party, field=field, beaver=lambda pid, eng: F.DeviceTripleSource(pid, eng, seed=0xD1F))
+    want = ([x * pow(y, -1, p) % p for x, y in zip(a, b)], [(x + 7) % p for x in a])
+    assert r0 == want and r1 == want
