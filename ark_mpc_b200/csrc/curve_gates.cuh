@@ -89,7 +89,7 @@ ARK_D void pt_beaver_mask_elem(fe8& d_mine, typename C::Pt& E_mine, const fe8& x
 
 // Writes the opened d and E, and the two result points through `emit(which, point)` (which = 0 share, 1 mac)
 // so that a kernel can store each as soon as its pass finishes.
-template <class C, class Emit>
+template <class C, bool DUAL, class Emit>
 ARK_D void pt_beaver_recombine_elem(fe8& d, typename C::Pt& E, int party, const fe8& key, const fe8& d_mine, const fe8& d_peer,
                                     const typename C::Pt& E_mine, const typename C::Pt& E_peer, const fe8& a_s, const fe8& a_m,
                                     const fe8& b_s, const fe8& b_m, const fe8& c_s, const fe8& c_m,
@@ -108,6 +108,22 @@ ARK_D void pt_beaver_recombine_elem(fe8& d, typename C::Pt& E, int party, const 
   FR::add(sv[1], t, a_m);
   FR::mul(t, d, b_m);
   FR::add(tv[1], t, c_m);
+  if (DUAL) {  // both variable-base passes in lock-step (two independent chains per thread), then the fixed-base parts
+    uint32_t k0[8], k1[8];
+    typename C::Pt acc0, acc1;
+    C::set_identity(acc0);
+    C::set_identity(acc1);
+    scalar_to_plain<typename C::R>(k0, sv[0]);
+    scalar_to_plain<typename C::R>(k1, sv[1]);
+    var_mul2<C>(acc0, acc1, tab, k0, k1);
+    scalar_to_plain<typename C::R>(k0, tv[0]);
+    fix_mul_acc<C>(acc0, gtab, k0);
+    emit(0, acc0);
+    scalar_to_plain<typename C::R>(k1, tv[1]);
+    fix_mul_acc<C>(acc1, gtab, k1);
+    emit(1, acc1);
+    return;
+  }
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif

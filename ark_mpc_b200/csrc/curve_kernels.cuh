@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_beaver_recombine_k
     ld_fe(bm, g.b_m, i);
     ld_fe(cs, g.c_s, i);
     ld_fe(cm, g.c_m, i);
-    pt_beaver_recombine_elem<C>(d, E, g.party, g.key, dm, dp, Em, Ep, as, am, bs, bm, cs, cm, gtab,
+    pt_beaver_recombine_elem<C, C::kDualChain>(d, E, g.party, g.key, dm, dp, Em, Ep, as, am, bs, bm, cs, cm, gtab,
                                 [&](int which, const typename C::Pt& r) { st_pt<C>(which ? g.out_m : g.out_s, i, r); });
     if (g.open) {
       st_fe(g.d_open, i, d);

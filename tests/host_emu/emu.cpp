@@ -74,13 +74,19 @@ template <class C> static void run_curve(int op, const uint32_t* in, uint32_t* o
     case 6: {
       // in: key d_mine d_peer a_s a_m b_s b_m c_s c_m E_mine E_peer ; out: d, E, out_s, out_m
       Pt E;
-      pt_beaver_recombine_elem<C>(o[0], E, party, v[0], v[1], v[2], pt(9), pt(9 + K), v[3], v[4], v[5], v[6], v[7], v[8], host_gtab<C>(),
+      pt_beaver_recombine_elem<C, false>(o[0], E, party, v[0], v[1], v[2], pt(9), pt(9 + K), v[3], v[4], v[5], v[6], v[7], v[8], host_gtab<C>(),
                                   [&](int which, const Pt& r) { put(1 + K + which * K, r); });
       put(1, E);
     } break;
     case 7: case 8: { Pt s, m; pt_share_add_public_elem<C>(s, m, party, op == 8, v[0], pt(1), pt(1 + K), pt(1 + 2 * K)); put(0, s); put(K, m); } break;
     case 9: { Pt r; pt_mac_check_elem<C>(r, v[0], pt(1), pt(1 + K)); put(0, r); } break;
     case 10: { Pt r0, r1; pt_mul2_elem<C>(r0, r1, v[0], v[1], pt(2)); put(0, r0); put(K, r1); } break;
+    case 13: {  // as case 6 with the dual-chain variable-base passes
+      Pt E;
+      pt_beaver_recombine_elem<C, true>(o[0], E, party, v[0], v[1], v[2], pt(9), pt(9 + K), v[3], v[4], v[5], v[6], v[7], v[8], host_gtab<C>(),
+                                        [&](int which, const Pt& r) { put(1 + K + which * K, r); });
+      put(1, E);
+    } break;
     case 11: { Pt p; C::set_generator(p); put(0, p); C::set_identity(p); put(K, p); } break;
     case 12: { Pt p = pt(0); C::neg(p); put(0, p); } break;
   }

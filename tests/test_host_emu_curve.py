@@ -154,6 +154,9 @@ def test_point_beaver_gate(emu, Cv, cid):
             want = po.point_beaver_recombine(Cv, p, keys[p], [d], [E], [a[p]], [b[p]], [c[p]])[0]
             sc = [keys[p], masks[p][0], masks[1 - p][0], a[p][0], a[p][1], b[p][0], b[p][1], c[p][0], c[p][1]]
             out = emu(Cv, cid, 6, sc, [masks[p][1], masks[1 - p][1]], 1 + 3 * K, party=p)
+            out_dual = emu(Cv, cid, 13, sc, [masks[p][1], masks[1 - p][1]], 1 + 3 * K, party=p)
+            assert [from_proj(Cv, fq_out(Cv, out_dual[1 + i * K:1 + (i + 1) * K])) for i in range(3)] == \
+                [from_proj(Cv, fq_out(Cv, out[1 + i * K:1 + (i + 1) * K])) for i in range(3)], "dual-chain variant differs"
             assert F.from_mont(out[0]) == d
             pts = fq_out(Cv, out[1:])
             assert from_proj(Cv, pts[:K]) == E

@@ -1,5 +1,5 @@
 #!/bin/bash
-for b in 0 3 4; do
-  echo "=== ARKMPC_PT_MINB=$b"
-  ARKMPC_PT_MINB=$b python tools/bench_points.py 18 2>&1 | grep -E "pt_mul \(var|recombine|two-party"
+for v in 0 1 2 3; do
+  echo "=== ARKMPC_PT_RECOMBINE=$v"
+  ARKMPC_PT_RECOMBINE=$v python tools/bench_points.py 18 2>&1 | grep -E "recombine|two-party"
 done
