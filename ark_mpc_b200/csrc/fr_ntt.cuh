@@ -14,9 +14,9 @@ namespace ark {
 
 // ---------------------------------------------------------------------------------------------
 // Batch inversion, Montgomery's trick per thread: K elements share one Fermat inversion (~380 multiplications),
-// so an element costs 3 + 380/K multiplications.  Element j of group g is a[g + j*groups]: coalesced across threads.
+// so an element costs 3 + 380/K multiplications (K = 32: the prefix products live in 1 KiB of local memory per thread).  Element j of group g is a[g + j*groups]: coalesced across threads.
 // ---------------------------------------------------------------------------------------------
-constexpr int kInvGroup = 16;
+constexpr int kInvGroup = 32;  // 3 + 380/32 = 15 multiplications per element (16 per group measured 1.5x slower, profiles/r01g_inverse_ab.txt)
 
 template <class F>
 __global__ void __launch_bounds__(kBlock) fr_batch_inverse_kernel(size_t n, size_t groups, Vec a, MVec out) {
