@@ -105,7 +105,9 @@ def test_scalar_mul(emu, Cv, cid):
     K = 3 if Cv.kind == "sw" else 4
     r = Cv.fr.p
     P = rand_point(Cv, rng)
-    for s in [0, 1, 2, 15, 16, 17, r - 1, r - 2, (1 << 252) - 1, rng.randrange(r), rng.randrange(r)]:
+    glv_lambda = 4407920970296243842393367215006156084916469457145843978461  # BN254: exercises the GLV split k = k1 + k2*lambda
+    for s in [0, 1, 2, 15, 16, 17, r - 1, r - 2, (1 << 252) - 1, glv_lambda, glv_lambda + 1, r - glv_lambda, (1 << 128) - 1, 1 << 128,
+              rng.randrange(r), rng.randrange(r), rng.randrange(r), rng.randrange(r)]:
         s %= r
         got = from_proj(Cv, fq_out(Cv, emu(Cv, cid, 3, [s], [to_proj(Cv, P, rng)], K)))
         assert got == Cv.mul(P, s), f"var-base s={s:x}"
