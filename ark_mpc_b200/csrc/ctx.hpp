@@ -85,7 +85,7 @@ inline unsigned grid_for(const arkmpc_ctx* ctx, size_t n, int blocks_per_sm, int
   return (unsigned)(need < cap ? (need ? need : 1) : cap);
 }
 // Streaming element-wise kernels: one element per thread by default (the hardware block scheduler refills SMs as blocks
-// retire; measured faster than a persistent wave for every kernel with a multiplication, profiles/r01e_grid_ab.txt); the
+// retire; measured faster than a persistent wave for every kernel with a multiplication, profiles/r01e_bench_extra.txt); the
 // grid-stride loops in the kernels still cover any n.
 inline unsigned grid_stream(const arkmpc_ctx* ctx, size_t n, int blocks_per_sm, int block = ark::kBlock) {
   if (!ctx->full_grids) return grid_for(ctx, n, blocks_per_sm, block);
