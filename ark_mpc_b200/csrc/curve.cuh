@@ -466,20 +466,20 @@ template <class C>
 ARK_D void var_mul(typename C::Pt& acc, const typename C::Cached* tab, const uint32_t* k) {
   if constexpr (C::kGlv) {
     var_mul_glv<C>(acc, tab, k);
-    return;
-  }
+  } else {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-  for (int i = kWindows - 1; i >= 0; i--) {
-    if (i != kWindows - 1) {
+    for (int i = kWindows - 1; i >= 0; i--) {
+      if (i != kWindows - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-      for (int j = 0; j < 4; j++) C::dbl(acc, j == 3);  // every window ends in (possibly) an addition; the final T is part of the result
+        for (int j = 0; j < 4; j++) C::dbl(acc, j == 3);  // every window ends in (possibly) an addition; the final T is part of the result
+      }
+      const uint32_t w = window4(k, i);
+      if (w) C::add_cached(acc, tab[w]);
     }
-    const uint32_t w = window4(k, i);
-    if (w) C::add_cached(acc, tab[w]);
   }
 }
 
@@ -490,24 +490,24 @@ template <class C>
 ARK_D void var_mul2(typename C::Pt& acc0, typename C::Pt& acc1, const typename C::Cached* tab, const uint32_t* k0, const uint32_t* k1) {
   if constexpr (C::kGlv) {
     var_mul2_glv<C>(acc0, acc1, tab, k0, k1);
-    return;
-  }
+  } else {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-  for (int i = kWindows - 1; i >= 0; i--) {
-    if (i != kWindows - 1) {
+    for (int i = kWindows - 1; i >= 0; i--) {
+      if (i != kWindows - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-      for (int j = 0; j < 4; j++) {
-        C::dbl(acc0, j == 3);
-        C::dbl(acc1, j == 3);
+        for (int j = 0; j < 4; j++) {
+          C::dbl(acc0, j == 3);
+          C::dbl(acc1, j == 3);
+        }
       }
+      const uint32_t w0 = window4(k0, i), w1 = window4(k1, i);
+      if (w0) C::add_cached(acc0, tab[w0]);
+      if (w1) C::add_cached(acc1, tab[w1]);
     }
-    const uint32_t w0 = window4(k0, i), w1 = window4(k1, i);
-    if (w0) C::add_cached(acc0, tab[w0]);
-    if (w1) C::add_cached(acc1, tab[w1]);
   }
 }
 

@@ -108,7 +108,7 @@ ARK_D void pt_beaver_recombine_elem(fe8& d, typename C::Pt& E, int party, const 
   FR::add(sv[1], t, a_m);
   FR::mul(t, d, b_m);
   FR::add(tv[1], t, c_m);
-  if (DUAL) {  // both variable-base passes in lock-step (two independent chains per thread), then the fixed-base parts
+  if constexpr (DUAL) {  // both variable-base passes in lock-step (two independent chains per thread), then the fixed-base parts
     uint32_t k0[8], k1[8];
     typename C::Pt acc0, acc1;
     C::set_identity(acc0);
@@ -122,20 +122,20 @@ ARK_D void pt_beaver_recombine_elem(fe8& d, typename C::Pt& E, int party, const 
     scalar_to_plain<typename C::R>(k1, tv[1]);
     fix_mul_acc<C>(acc1, gtab, k1);
     emit(1, acc1);
-    return;
-  }
+  } else {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-  for (int which = 0; which < 2; which++) {
-    uint32_t k[8];
-    typename C::Pt acc;
-    C::set_identity(acc);
-    scalar_to_plain<typename C::R>(k, sv[which]);
-    var_mul<C>(acc, tab, k);
-    scalar_to_plain<typename C::R>(k, tv[which]);
-    fix_mul_acc<C>(acc, gtab, k);
-    emit(which, acc);
+    for (int which = 0; which < 2; which++) {
+      uint32_t k[8];
+      typename C::Pt acc;
+      C::set_identity(acc);
+      scalar_to_plain<typename C::R>(k, sv[which]);
+      var_mul<C>(acc, tab, k);
+      scalar_to_plain<typename C::R>(k, tv[which]);
+      fix_mul_acc<C>(acc, gtab, k);
+      emit(which, acc);
+    }
   }
 }
 
