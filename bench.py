@@ -217,6 +217,7 @@ def run_supplementary(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
+    from ark_mpc_b200 import sharding as sh
     from ark_mpc_b200.engine import Engine
 
     torch.cuda.set_device(local_rank)
@@ -287,12 +288,17 @@ def run_supplementary(args, rank, world, local_rank):
                     E.beaver_recombine(p, keys[p], de[p][0], de[p][1], de[1 - p][0], de[1 - p][1], A[p], B[p], Cc[p], out=outs[p])
                 for p in (0, 1):
                     sums[p] = E.share_sum(outs[p])
+                    if world > 1:  # cross-GPU sum: all-gather of the per-rank partial ScalarShares (64 B), modular add locally
+                        sums[p] = sh.all_reduce_share_sum(E, sums[p])
                 opened = E.add(sums[0][0], sums[1][0])            # open of the single result
                 chk = [E.mac_check(keys[p], opened, sums[p][1]) for p in (0, 1)]  # MAC-check shares (commitment hash is host-side)
                 return opened, chk
 
             opened, chk = step()
-            ok = torch.equal(opened, E.sum(E.mul(xv, yv))) and E.sum_is_zero(chk[0], chk[1])
+            want = E.sum(E.mul(xv, yv))
+            if world > 1:
+                want = E.sum(sh.all_gather_rows(want))
+            ok = torch.equal(opened, want) and E.sum_is_zero(chk[0], chk[1])
             alg_bytes = 2 * (192 + 384 + 64)
             metric, unit = "inner_product_elements_per_sec", "elements/s"
             wl = f"secret-shared inner product of length-2^{args.log2_batch} vectors per GPU (batch_mul + tree-sum + open with MAC check), both parties (BASELINE.json configs[3])"
