@@ -239,7 +239,8 @@ def run_supplementary(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         E = Engine(local_rank, field)
         seed = 0xC0FFEE + 7919 * rank
-        key0, key1 = (E.download(E.random(seed + 900 + p, 0, 1))[0].copy() for p in (0, 1))
+        # one MAC key for the whole sharded batch (the same on every rank); everything else is generated per shard
+        key0, key1 = (E.download(E.random(0xC0FFEE + 900 + p, 0, 1))[0].copy() for p in (0, 1))
         key = E.download(E.add(E.upload(key0.reshape(1, 4)), E.upload(key1.reshape(1, 4))))[0].copy()
         keys = (key0, key1)
 
