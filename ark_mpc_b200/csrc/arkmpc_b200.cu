@@ -13,10 +13,25 @@ inline unsigned full_grid(size_t n) {
   return (unsigned)(need < (1u << 30) ? (need ? need : 1) : (1u << 30));
 }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_prologue in fr_kernels.cuh) unless disabled.
+template <class... KArgs, class... Args>
+void launch_pdl(const arkmpc_ctx* ctx, void (*kern)(KArgs...), unsigned grid, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kBlock);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, args...);  // errors surface through cudaGetLastError in post_launch
+}
+
 // ---- launch helpers shared by the device-pointer ABI and the host-buffer path ----
 template <class F>
 int launch_mask(arkmpc_ctx* ctx, cudaStream_t s, size_t n, Vec x, Vec y, Vec a, Vec b, MVec d, MVec e) {
-  beaver_mask_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, s>>>(n, x, y, a, b, d, e);
+  launch_pdl(ctx, beaver_mask_kernel<F>, grid_stream(ctx, n, 8), s, n, x, y, a, b, d, e);
   return post_launch(ctx, "beaver_mask_kernel");
 }
 
@@ -56,11 +71,11 @@ int launch_recombine(arkmpc_ctx* ctx, cudaStream_t s, int party, size_t n, const
   }
   const unsigned grid = full_grid(n);
   if (party == 0) {
-    if (open) beaver_recombine_kernel<F, 0, true><<<grid, kBlock, 0, s>>>(n, g);
-    else beaver_recombine_kernel<F, 0, false><<<grid, kBlock, 0, s>>>(n, g);
+    if (open) launch_pdl(ctx, beaver_recombine_kernel<F, 0, true>, grid, s, n, g);
+    else launch_pdl(ctx, beaver_recombine_kernel<F, 0, false>, grid, s, n, g);
   } else {
-    if (open) beaver_recombine_kernel<F, 1, true><<<grid, kBlock, 0, s>>>(n, g);
-    else beaver_recombine_kernel<F, 1, false><<<grid, kBlock, 0, s>>>(n, g);
+    if (open) launch_pdl(ctx, beaver_recombine_kernel<F, 1, true>, grid, s, n, g);
+    else launch_pdl(ctx, beaver_recombine_kernel<F, 1, false>, grid, s, n, g);
   }
   return post_launch(ctx, "beaver_recombine_kernel");
 }
@@ -132,6 +147,8 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
   {
     const char* v = getenv("ARKMPC_RECOMBINE");
     ctx->use_tma = v && strcmp(v, "tma") == 0;
+    const char* pd = getenv("ARKMPC_PDL");
+    if (pd && strcmp(pd, "0") == 0) ctx->pdl = false;
     const char* gm = getenv("ARKMPC_GRID");
     if (gm && strcmp(gm, "persistent") == 0) ctx->full_grids = false;
     const char* c = getenv("ARKMPC_CHUNK_LOG2");
@@ -338,8 +355,8 @@ int arkmpc_fr_beaver_recombine_gather(arkmpc_ctx* ctx, int field, int party_id, 
   }
   const unsigned grid = full_grid(n);
   ARK_FIELD_SWITCH(ctx, field, {
-    if (party_id == 0) beaver_recombine_gather_kernel<F, 0><<<grid, kBlock, 0, ctx->stream>>>(n, g, q);
-    else beaver_recombine_gather_kernel<F, 1><<<grid, kBlock, 0, ctx->stream>>>(n, g, q);
+    if (party_id == 0) launch_pdl(ctx, beaver_recombine_gather_kernel<F, 0>, grid, ctx->stream, n, g, q);
+    else launch_pdl(ctx, beaver_recombine_gather_kernel<F, 1>, grid, ctx->stream, n, g, q);
   });
   return post_launch(ctx, "beaver_recombine_gather_kernel");
 }

@@ -34,6 +34,7 @@ struct arkmpc_ctx {
   int* flag_dev = nullptr;
   int* flag_host = nullptr;  // pinned
   bool use_tma = false;      // ARKMPC_RECOMBINE=tma
+  bool pdl = true;           // Beaver K1/K2 launched with programmatic stream serialization (ARKMPC_PDL=0 disables)
   bool full_grids = true;    // element-wise kernels: one element per thread instead of a persistent wave (ARKMPC_GRID=persistent reverts)
   size_t chunk_elems = arkctx::kChunkElems;  // host-buffer path staging granularity (ARKMPC_CHUNK_LOG2 overrides)
   void* gtab[arkctx::kNumCurves] = {nullptr, nullptr};  // fixed-base tables, built on first use (arkmpc_curve.cu)
