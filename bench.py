@@ -178,7 +178,7 @@ def run_reference(args, rank, world):
         "note": "Rust reference unbuildable here (no cargo/rustc, arkworks not vendored): C restatement of its gate "
                 "sequence, arithmetic only (omits the reference executor's per-element bookkeeping, so it flatters the reference)",
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def workload_config(args, world):
@@ -375,9 +375,31 @@ def run_supplementary(args, rank, world, local_rank):
             dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": m / dt, "unit": unit, "cores": cores, "kind": "port",
                                 "sample": f"the first {m} elements of the same batch, unfused reference gate sequence (oracle/ark_oracle.c), all host threads"}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the one JSON line: libraries that write to fd 1 (NCCL prints its version banner there) go to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -396,6 +418,7 @@ def main():
                          "(supplementary lines, same JSON shape)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -660,7 +683,7 @@ def main():
         line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"the same 2^{args.log2_batch} two-party batch, {args.cpu_steps} reps, all host threads",
                                 "single_thread_value": n / dt1}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
