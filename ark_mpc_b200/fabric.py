@@ -379,6 +379,29 @@ class ScalarResult:
         a.fabric.n_gates += 1
         return ScalarResult(a.fabric, a.fabric.engine.batch_inverse(a.values))
 
+    @staticmethod
+    def batch_add_constant(a, consts: Sequence[int]):  # scalar_result.rs:119
+        return ScalarResult.batch_add(a, a.fabric.allocate_scalars(consts))
+
+    @staticmethod
+    def batch_sub_constant(a, consts: Sequence[int]):  # scalar_result.rs:205
+        return ScalarResult.batch_sub(a, a.fabric.allocate_scalars(consts))
+
+    @staticmethod
+    def batch_mul_constant(a, consts: Sequence[int]):  # scalar_result.rs:281
+        return ScalarResult.batch_mul(a, a.fabric.allocate_scalars(consts))
+
+    @staticmethod
+    def batch_pow(a, exp: int):  # scalar_result.rs:26-39 applied to every element: recursive squaring, pow(0) = 1
+        f = a.fabric
+        if exp == 0:
+            return f.allocate_scalars([1] * len(a))
+        if exp == 1:
+            return a
+        half = ScalarResult.batch_pow(a, exp // 2)
+        res = ScalarResult.batch_mul(half, half)
+        return ScalarResult.batch_mul(res, a) if exp % 2 else res
+
     def to_limbs(self) -> np.ndarray:
         return self.fabric.engine.download(self.values)
 
@@ -471,6 +494,10 @@ class AuthenticatedScalarResult:
         f.n_gates += 1
         return AuthenticatedScalarResult(f, f.engine.scale(a.share, k), f.engine.scale(a.mac, k))
 
+    @staticmethod
+    def batch_add_constant(a, consts: Sequence[int]):  # :531-560: add_public with host constants
+        return AuthenticatedScalarResult.batch_add_public(a, a.fabric.allocate_scalars(consts))
+
     # -- Beaver multiplication (:848-879) ----------------------------------------------------------
     @staticmethod
     def batch_mul(a, b):
@@ -538,6 +565,28 @@ class AuthenticatedScalarResult:
         opened = AuthenticatedScalarResult.open_authenticated_batch(masked).result()
         inverted = ScalarResult.batch_inverse(opened)
         return AuthenticatedScalarResult.batch_mul_public(shared, inverted)
+
+    @staticmethod
+    def batch_div(a, b):  # :974-977
+        return AuthenticatedScalarResult.batch_mul(a, AuthenticatedScalarResult.batch_inverse(b))
+
+    @staticmethod
+    def batch_div_public(a, b: ScalarResult):  # Div<&ScalarResult> :953-958, batched
+        return AuthenticatedScalarResult.batch_mul_public(a, ScalarResult.batch_inverse(b))
+
+    @staticmethod
+    def batch_pow(a, exp: int):
+        """`pow` (:86-101) on every element: recursive squaring, one Beaver batch per squaring / multiply.  As in the reference,
+        pow(0) is `zero_authenticated()` (:87-89), not one."""
+        f = a.fabric
+        if exp == 0:
+            z = torch.zeros((len(a), 4), dtype=torch.int64, device=a.share.device)
+            return AuthenticatedScalarResult(f, z, z.clone())
+        if exp == 1:
+            return a
+        half = AuthenticatedScalarResult.batch_pow(a, exp // 2)
+        res = AuthenticatedScalarResult.batch_mul(half, half)
+        return AuthenticatedScalarResult.batch_mul(res, a) if exp % 2 else res
 
     @staticmethod
     def _fft(x, inverse: bool):

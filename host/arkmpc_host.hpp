@@ -231,6 +231,7 @@ class PreprocessingPhase {
   virtual std::tuple<HostShares, HostShares, HostShares> next_triplet_batch(size_t n) = 0;
   virtual std::pair<HostScalars, HostShares> next_local_input_mask_batch(size_t n) = 0;
   virtual HostShares next_counterparty_input_mask_batch(size_t n) = 0;
+  virtual HostShares next_shared_value_batch(size_t n) = 0;  // offline_prep.rs: next_shared_value_batch
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -275,6 +276,8 @@ struct AuthenticatedScalarResult {  // a batch of ScalarShares: two device plane
   static ScalarResult open_batch(const AuthenticatedScalarResult& v);                                                  // :129-172
   static AuthenticatedScalarOpenResult open_authenticated_batch(const AuthenticatedScalarResult& v);                   // :278-354
   AuthenticatedScalarResult sum() const;                                                                               // :563-576
+  static AuthenticatedScalarResult batch_inverse(const AuthenticatedScalarResult& v);                                  // :55-82
+  static AuthenticatedScalarResult batch_div(const AuthenticatedScalarResult& a, const AuthenticatedScalarResult& b);  // :974-977
   // ark-poly fft / ifft on the share and mac planes (:1011-1070); len() must be a power of two (the caller pads, as D::new does)
   static AuthenticatedScalarResult fft(const AuthenticatedScalarResult& x, bool inverse = false);
 };
@@ -363,6 +366,12 @@ class MpcFabric {
     std::tuple<HostShares, HostShares, HostShares> t;
     { std::lock_guard<std::mutex> l(src_mu_); t = src_->next_triplet_batch(n); }
     return {allocate_scalar_shares(std::get<0>(t)), allocate_scalar_shares(std::get<1>(t)), allocate_scalar_shares(std::get<2>(t))};
+  }
+
+  AuthenticatedScalarResult random_shared_scalars(size_t n) {  // fabric.rs:950-965
+    HostShares v;
+    { std::lock_guard<std::mutex> l(src_mu_); v = src_->next_shared_value_batch(n); }
+    return allocate_scalar_shares(v);
   }
 
   // -- network: party 0 sends then receives, party 1 receives then sends (fabric.rs:751-765) --
@@ -489,6 +498,7 @@ class PartyIDBeaverSource : public PreprocessingPhase {
     return {m, fill(party_ * 3, party_ * 3, n)};
   }
   HostShares next_counterparty_input_mask_batch(size_t n) override { return fill(3 * party_, party_ * 3 * party_, n); }
+  HostShares next_shared_value_batch(size_t n) override { return fill(party_, party_, n); }  // :166-168: a sharing of 1 under key 1
 
  private:
   HostShares fill(uint64_t share, uint64_t mac, size_t n) {
@@ -629,6 +639,17 @@ inline ScalarResult AuthenticatedScalarResult::open_batch(const AuthenticatedSca
   f->ctx()->sync();
   f->count_gate();
   return {f, o, v.n};
+}
+
+// Two rounds (Bar-Ilan & Beaver): mask with shared randomness, open with the MAC check, invert in public, unmask.
+inline AuthenticatedScalarResult AuthenticatedScalarResult::batch_inverse(const AuthenticatedScalarResult& v) {
+  if (v.n == 0) throw std::invalid_argument("cannot invert empty batch of scalars");
+  AuthenticatedScalarResult r = v.fabric->random_shared_scalars(v.n);
+  ScalarResult opened = open_authenticated_batch(batch_mul(v, r)).result();
+  return batch_mul_public(r, ScalarResult::batch_inverse(opened));
+}
+inline AuthenticatedScalarResult AuthenticatedScalarResult::batch_div(const AuthenticatedScalarResult& a, const AuthenticatedScalarResult& b) {
+  return batch_mul(a, batch_inverse(b));
 }
 
 inline AuthenticatedScalarOpenResult AuthenticatedScalarResult::open_authenticated_batch(const AuthenticatedScalarResult& v) {

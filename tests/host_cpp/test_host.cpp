@@ -137,6 +137,8 @@ static void test_next_rows(const CurveInfo& cv, const char* name) {
     auto m = AuthenticatedPointResult::open_authenticated_batch(CurvePointResult::msm_authenticated(A, pts));
     o.push_back(m.result().to_affine_host());
     o.push_back(CurvePointResult::msm(va, pts).to_affine_host());
+    o.push_back(S::open_authenticated_batch(S::batch_inverse(A)).result().to_host());
+    o.push_back(S::open_authenticated_batch(S::batch_mul(S::batch_div(A, A), A)).result().to_host());  // (a / a) * a = a
     return o;
   });
   for (const Out* o : {&res.first, &res.second}) {
@@ -144,6 +146,8 @@ static void test_next_rows(const CurveInfo& cv, const char* name) {
     if (has_fft) EXPECT((*o)[1] == want_fft, "fft on shares opens to the transform of the plaintext");
     EXPECT((*o)[2] == want_msm, "msm_authenticated opens to sum a_i * P_i");
     EXPECT((*o)[3] == want_msm, "public msm");
+    EXPECT((*o)[4] == want_inv, "authenticated batch_inverse opens to the inverses");
+    EXPECT((*o)[5] == a.limbs, "batch_div: (a / a) * a opens to a");
   }
   printf("%s: inverse / fft / msm done\n", name);
 }

@@ -147,3 +147,38 @@ def test_two_party_div_and_add_constant(field):
     r0, r1 = F.execute_mock_mpc(party, field=field, beaver=lambda pid, eng: F.DeviceTripleSource(pid, eng, seed=0xD1F))
     want = ([x * pow(y, -1, p) % p for x, y in zip(a, b)], [(x + 7) % p for x in a])
     assert r0 == want and r1 == want
+
+
+@pytest.mark.parametrize("field", ["bn254_fr", "curve25519_fr"])
+def test_two_party_named_div_pow_constant_ops(field):
+    """batch_div (:974-977), division by a public value (:953-958), pow (:86-101, test_pow :1622-1640 region) and
+    batch_add_constant (:531-560) through their own entry points; public-side constant ops and pow (scalar_result.rs:26-39,119,205,281)."""
+    from ark_mpc_b200 import fabric as F
+
+    p = po.FIELDS[field].p
+    rng = random.Random(21)
+    n = 33
+    a = [rng.randrange(p) for _ in range(n)]
+    b = [rng.randrange(1, p) for _ in range(n)]
+    c = [rng.randrange(1, p) for _ in range(n)]
+
+    def party(fabric):
+        S, P = F.AuthenticatedScalarResult, F.ScalarResult
+        A = fabric.batch_share_scalar(a if fabric.party_id() == 0 else n, 0)
+        B = fabric.batch_share_scalar(b if fabric.party_id() == 1 else n, 1)
+        C = fabric.allocate_scalars(c)
+        outs = [S.batch_div(A, B), S.batch_div_public(A, C), S.batch_pow(A, 13), S.batch_pow(A, 1), S.batch_pow(A, 0),
+                S.batch_add_constant(A, c)]
+        opened = [S.open_authenticated_batch(o).result().to_ints() for o in outs]
+        pub = [P.batch_add_constant(C, a).to_ints(), P.batch_sub_constant(C, a).to_ints(), P.batch_mul_constant(C, a).to_ints(),
+               P.batch_pow(C, 11).to_ints(), P.batch_pow(C, 0).to_ints()]
+        return opened, pub
+
+    r0, r1 = F.execute_mock_mpc(party, field=field, beaver=lambda pid, eng: F.DeviceTripleSource(pid, eng, seed=0xBEE))
+    want = ([x * pow(y, -1, p) % p for x, y in zip(a, b)], [x * pow(y, -1, p) % p for x, y in zip(a, c)], [pow(x, 13, p) for x in a], a,
+            [0] * n, [(x + y) % p for x, y in zip(a, c)])
+    want_pub = ([(y + x) % p for x, y in zip(a, c)], [(y - x) % p for x, y in zip(a, c)], [y * x % p for x, y in zip(a, c)],
+                [pow(y, 11, p) for y in c], [1] * n)
+    for r in (r0, r1):
+        assert tuple(r[0]) == want
+        assert tuple(r[1]) == want_pub
