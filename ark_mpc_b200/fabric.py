@@ -114,6 +114,9 @@ class PreprocessingPhase:
     def next_shared_value_batch(self, n: int):
         raise NotImplementedError
 
+    def next_shared_inverse_pair_batch(self, n: int):  # offline_prep.rs:55-60
+        raise NotImplementedError
+
 
 class PartyIDBeaverSource(PreprocessingPhase):
     """offline_prep.rs:88-170: a = 2, b = 3, c = 6 with [a] = (1,1), [b] = (3,0), [c] = (2,4); the MAC key is a sharing of 1
@@ -148,6 +151,9 @@ class PartyIDBeaverSource(PreprocessingPhase):
 
     def next_shared_value_batch(self, n: int):  # offline_prep.rs:166-168: every shared value is a sharing of 1 under key 1
         return self._share(self.party_id, self.party_id, n)
+
+    def next_shared_inverse_pair_batch(self, n: int):  # offline_prep.rs:159-164: (1, 1)
+        return self._share(self.party_id, self.party_id, n), self._share(self.party_id, self.party_id, n)
 
 
 class DeviceTripleSource(PreprocessingPhase):
@@ -198,6 +204,16 @@ class DeviceTripleSource(PreprocessingPhase):
     def next_shared_value_batch(self, n: int):
         E, s = self.E, self._next_seed()
         return self.share_of(E.random(s + 10, 0, n), s + 100)
+
+    def next_shared_bit_batch(self, n: int):
+        E, s = self.E, self._next_seed()
+        bits = (E.random(s + 10, 0, n)[:, :1] & 1) * torch.from_numpy(fl.mont_limbs(E.field_name, 1).view(np.int64).reshape(1, 4).copy()).to(E.tdev)
+        return self.share_of(bits.contiguous(), s + 100)
+
+    def next_shared_inverse_pair_batch(self, n: int):
+        E, s = self.E, self._next_seed()
+        r = E.random(s + 10, 0, n)
+        return self.share_of(r, s + 100), self.share_of(E.batch_inverse(r), s + 200)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -265,6 +281,48 @@ class MpcFabric:
         with self._offline_lock:
             v = self.offline_phase.next_shared_value_batch(n)
         return self.allocate_scalar_shares(v)
+
+    def random_shared_bits(self, n: int) -> "AuthenticatedScalarResult":  # fabric.rs:969-978
+        with self._offline_lock:
+            v = self.offline_phase.next_shared_bit_batch(n)
+        return self.allocate_scalar_shares(v)
+
+    def random_inverse_pairs(self, n: int):  # fabric.rs:943-958
+        with self._offline_lock:
+            left, right = self.offline_phase.next_shared_inverse_pair_batch(n)
+        return self.allocate_scalar_shares(left), self.allocate_scalar_shares(right)
+
+    # -- constant wires (fabric.rs:221-247, 497-546), as batches -------------------------------------
+    def _const_plane(self, limbs: np.ndarray, n: int) -> torch.Tensor:
+        row = torch.from_numpy(np.ascontiguousarray(limbs, dtype=np.uint64).view(np.int64).reshape(1, 4).copy()).to(self.engine.tdev)
+        return row.repeat(n, 1)
+
+    def zeros(self, n: int) -> "ScalarResult":
+        return ScalarResult(self, torch.zeros((n, 4), dtype=torch.int64, device=self.engine.tdev))
+
+    def ones(self, n: int) -> "ScalarResult":
+        return ScalarResult(self, self._const_plane(fl.mont_limbs(self.field, 1), n))
+
+    def zeros_authenticated(self, n: int) -> "AuthenticatedScalarResult":  # both parties hold (0, 0)
+        z = torch.zeros((n, 4), dtype=torch.int64, device=self.engine.tdev)
+        return AuthenticatedScalarResult(self, z, z.clone())
+
+    def ones_authenticated(self, n: int) -> "AuthenticatedScalarResult":
+        """fabric.rs:234-235: share = party id, mac = this party's MAC-key share (party 0 holds zero, party 1 holds one)."""
+        return AuthenticatedScalarResult(self, self._const_plane(fl.mont_limbs(self.field, self._party_id), n), self._const_plane(self._mac_key, n))
+
+    def curve_identities(self, n: int) -> "CurvePointResult":
+        return CurvePointResult(self, self.engine.pt_mul_generator_public(self.zeros(n).values))
+
+    def curve_identities_authenticated(self, n: int) -> "AuthenticatedPointResult":  # both parties hold the identity for share and mac
+        ident = self.curve_identities(n).points
+        return AuthenticatedPointResult(self, torch.cat([ident, ident], dim=1).contiguous())
+
+    def allocate_points(self, points) -> "CurvePointResult":  # fabric.rs allocate_points: projective AoS image (n, words)
+        if isinstance(points, torch.Tensor):
+            return CurvePointResult(self, points)
+        a = np.ascontiguousarray(points, dtype=np.uint64)
+        return CurvePointResult(self, torch.from_numpy(a.view(np.int64)).to(self.engine.tdev))
 
     # -- network --------------------------------------------------------------------------------
     def _send(self, t: torch.Tensor) -> None:
@@ -401,6 +459,25 @@ class ScalarResult:
         half = ScalarResult.batch_pow(a, exp // 2)
         res = ScalarResult.batch_mul(half, half)
         return ScalarResult.batch_mul(res, a) if exp % 2 else res
+
+    @staticmethod
+    def _fft(x, inverse: bool):  # scalar_result.rs fft / ifft: ark-poly domain of the next power of two, zero-padded
+        assert len(x) > 0, "Cannot compute FFT of empty vector"
+        n = len(x)
+        size = 1 << (n - 1).bit_length()
+        v = x.values
+        if size != n:
+            v = torch.cat([v, torch.zeros((size - n, 4), dtype=torch.int64, device=v.device)])
+        x.fabric.n_gates += 1
+        return ScalarResult(x.fabric, x.fabric.engine.fft(v, inverse=inverse))
+
+    @staticmethod
+    def fft(x):
+        return ScalarResult._fft(x, False)
+
+    @staticmethod
+    def ifft(x):
+        return ScalarResult._fft(x, True)
 
     def to_limbs(self) -> np.ndarray:
         return self.fabric.engine.download(self.values)
@@ -644,6 +721,17 @@ class CurvePointResult:
         return CurvePointResult(a.fabric, a.fabric.engine.pt_add(a.points, b.points))
 
     @staticmethod
+    def batch_sub(a, b):
+        assert len(a) == len(b), "batch_sub cannot compute on vectors of unequal length"
+        a.fabric.n_gates += 1
+        return CurvePointResult(a.fabric, a.fabric.engine.pt_sub(a.points, b.points))
+
+    @staticmethod
+    def batch_neg(a):
+        a.fabric.n_gates += 1
+        return CurvePointResult(a.fabric, a.fabric.engine.pt_neg(a.points))
+
+    @staticmethod
     def batch_mul(a: ScalarResult, b: "CurvePointResult"):  # curve.rs:459-479
         assert len(a) == len(b), "batch_mul cannot compute on vectors of unequal length"
         a.fabric.n_gates += 1
@@ -811,6 +899,13 @@ class AuthenticatedPointResult:
         E = self.fabric.engine
         row = self.shares[index:index + 1, w:].contiguous()
         self.shares[index:index + 1, w:] = E.pt_add(row, row)
+
+    def modify_share(self, index: int) -> None:
+        """Corrupt one point share (test helper): replace it by its double."""
+        w = self._w()
+        E = self.fabric.engine
+        row = self.shares[index:index + 1, :w].contiguous()
+        self.shares[index:index + 1, :w] = E.pt_add(row, row)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -236,3 +236,88 @@ def test_point_open_authenticated_detects_corruption(field):
             return "auth_error"
 
     assert F.execute_mock_mpc(party, field=field) == ("auth_error", "auth_error")
+
+
+@pytest.mark.parametrize("field", FIELDS)
+@pytest.mark.parametrize("source", [None, random_source], ids=["party_id_source", "random_triples"])
+def test_constant_wires_bits_and_inverse_pairs(field, source):
+    """fabric.rs:497-546 (zero / one wires, party 0 holds 0 and party 1 holds 1 of the shared one), :943-978 (inverse pairs, shared bits)."""
+    F = fab()
+    p = po.FIELDS[field].p
+    n = 17
+    a = rand_vals(field, 5, n)
+
+    def party(fabric):
+        S = F.AuthenticatedScalarResult
+        A = fabric.batch_share_scalar(a if fabric.party_id() == 0 else n, 0)
+        left, right = fabric.random_inverse_pairs(n)
+        bits = fabric.random_shared_bits(n)
+        outs = [fabric.zeros_authenticated(n), fabric.ones_authenticated(n), S.batch_add(A, fabric.ones_authenticated(n)),
+                S.batch_mul(left, right), bits, S.batch_mul(bits, bits)]
+        opened = [S.open_authenticated_batch(o).result().to_ints() for o in outs]
+        return opened, fabric.zeros(n).to_ints(), fabric.ones(n).to_ints()
+
+    r0, r1 = F.execute_mock_mpc(party, field=field, beaver=source)
+    assert r0 == r1
+    opened, zeros, ones = r0
+    assert zeros == [0] * n and ones == [1] * n
+    assert opened[0] == [0] * n and opened[1] == [1] * n
+    assert opened[2] == [(x + 1) % p for x in a]
+    assert opened[3] == [1] * n
+    assert all(b in (0, 1) for b in opened[4]) and opened[5] == opened[4]
+    if source is not None:
+        assert 0 < sum(opened[4]) < n   # random bits, not a constant
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_public_point_gates_identities_and_share_corruption(field):
+    """curve.rs batch_sub / batch_neg on public points, the identity wires (fabric.rs:536-546), allocate_points, and a corrupted point
+    share failing the MAC check."""
+    F = fab()
+    n = 9
+    cv, Cv, scal, pts, images = point_inputs(field, n, 23)
+    _, _, _, pts2, images2 = point_inputs(field, n, 29)
+
+    def party(fabric):
+        P, C = F.AuthenticatedPointResult, F.CurvePointResult
+        A = fabric.batch_share_point(fabric.engine.upload_points(images) if fabric.party_id() == 0 else n, 0)
+        pa, pb = fabric.allocate_points(fabric.engine.upload_points(images)), fabric.allocate_points(fabric.engine.upload_points(images2))
+        pub = [C.batch_sub(pa, pb).to_affine_limbs(), C.batch_neg(pa).to_affine_limbs(),
+               C.batch_add(pa, fabric.curve_identities(n)).to_affine_limbs()]
+        same = P.open_authenticated_batch(P.batch_add(A, fabric.curve_identities_authenticated(n))).result().to_affine_limbs()
+        if fabric.party_id() == 0:
+            A.modify_share(1)
+        try:
+            P.open_authenticated_batch(A).result()
+            verdict = "ok"
+        except F.AuthenticationError:
+            verdict = "auth_error"
+        return pub, same, verdict
+
+    r0, r1 = F.execute_mock_mpc(party, field=field)
+    want = [[Cv.sub(a, b) for a, b in zip(pts, pts2)], [Cv.neg(a) for a in pts], list(pts)]
+    for r in (r0, r1):
+        for got, w in zip(r[0], want):
+            assert xy_to_affine(cv, got) == w
+        assert xy_to_affine(cv, r[1]) == list(pts)
+        assert r[2] == "auth_error"
+
+
+def test_public_fft_round_trip_and_padding():
+    """scalar_result.rs fft / ifft on public values: ifft(fft(x)) = x zero-padded to the domain size; agrees with the transform of shares."""
+    F = fab()
+    n = 24
+    a = rand_vals("bn254_fr", 31, n)
+
+    def party(fabric):
+        S, P = F.AuthenticatedScalarResult, F.ScalarResult
+        pub = fabric.allocate_scalars(a)
+        A = fabric.batch_share_scalar(a if fabric.party_id() == 0 else n, 0)
+        fa = P.fft(pub)
+        return P.ifft(fa).to_ints(), fa.to_ints(), S.open_authenticated_batch(S.fft(A)).result().to_ints()
+
+    r0, r1 = F.execute_mock_mpc(party, field="bn254_fr")
+    assert r0 == r1
+    back, fa, fa_shared = r0
+    assert back == a + [0] * (32 - n)
+    assert fa == fa_shared and len(fa) == 32
