@@ -67,8 +67,9 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     # one translation unit per thread: the point kernels take much longer to compile than the scalar ones
     from concurrent.futures import ThreadPoolExecutor
 
-    with ThreadPoolExecutor(max_workers=4) as pool:
-        objs = list(pool.map(compile_one, sources()))
+    srcs = sorted(sources(), key=lambda f: (not os.path.basename(f).startswith("curve_"), f))  # slowest units first
+    with ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 4))) as pool:
+        objs = list(pool.map(compile_one, srcs))
     tmp = LIB + ".tmp"  # link beside the target and rename: a failed link must not remove a working library
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs])
     os.replace(tmp, LIB)

@@ -1,5 +1,7 @@
 // Internal: templated launch wrappers of the point kernels and the per-curve dispatch table.  Each curve is
-// instantiated in its own translation unit (curve_bn254.cu, curve_ed25519.cu) so the two compile in parallel;
+// instantiated in four translation units (curve_<name>.cu + _beaver / _msm / _shares) so the slow-to-compile scalar
+// multiplication kernels build in parallel: a unit defines ARK_CURVE_PART and gets the bodies of that part only (the other
+// members stay declarations and resolve at link time against the unit that explicitly instantiates them).
 // arkmpc_curve.cu holds the C ABI and dispatches through `CurveOps`.
 #pragma once
 #include "ctx.hpp"
@@ -32,6 +34,11 @@ const CurveOps* curve_ops_ed25519();
 }  // namespace arkctx
 
 #ifdef ARK_CURVE_IMPL
+// parts: 0 = dispatch table, linear gates, mul, mul_gen, sum; 1 = point Beaver mask / recombine; 2 = msm; 3 = share-side scalar multiplications
+#ifndef ARK_CURVE_PART
+#error "define ARK_CURVE_PART (0..3) before including curve_launch.cuh with ARK_CURVE_IMPL"
+#endif
+#define ARK_IN_PART(k) (ARK_CURVE_PART == (k))
 #include "curve_kernels.cuh"
 #include "curve_msm.cuh"
 
@@ -80,40 +87,72 @@ struct CurveLaunch {
     return ARKMPC_OK;
   }
 
-  static int binary(arkmpc_ctx* ctx, size_t n, const void* a, const void* b, void* out, int sub) {
+  static int binary(arkmpc_ctx* ctx, size_t n, const void* a, const void* b, void* out, int sub)
+#if ARK_IN_PART(0)
+  {
     if (sub) pt_binary_kernel<C, PtBin::Sub><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, pvec(a, PB), pvec(b, PB), pmvec(out, PB));
     else pt_binary_kernel<C, PtBin::Add><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, pvec(a, PB), pvec(b, PB), pmvec(out, PB));
     return post_launch(ctx, "pt_binary_kernel");
   }
-  static int neg(arkmpc_ctx* ctx, size_t n, const void* a, void* out) {
+#else
+  ;
+#endif
+  static int neg(arkmpc_ctx* ctx, size_t n, const void* a, void* out)
+#if ARK_IN_PART(0)
+  {
     pt_neg_kernel<C><<<pt_grid(ctx, n, 8), kPtBlock, 0, ctx->stream>>>(n, pvec(a, PB), pmvec(out, PB));
     return post_launch(ctx, "pt_neg_kernel");
   }
-  static int share_add_public(arkmpc_ctx* ctx, int party, int sub, const fe8& key, size_t n, const void* a_ps, const void* pub, void* out_ps) {
+#else
+  ;
+#endif
+  static int share_add_public(arkmpc_ctx* ctx, int party, int sub, const fe8& key, size_t n, const void* a_ps, const void* pub, void* out_ps)
+#if ARK_IN_PART(3)
+  {
     const char* a = static_cast<const char*>(a_ps);
     char* o = static_cast<char*>(out_ps);
     pt_share_add_public_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, party, sub, key, pvec(a, 2 * PB), pvec(a + PB, 2 * PB), pvec(pub, PB),
                                                                                   pmvec(o, 2 * PB), pmvec(o + PB, 2 * PB));
     return post_launch(ctx, "pt_share_add_public_kernel");
   }
-  static int mul(arkmpc_ctx* ctx, size_t n_points, const void* scalars, int sshift, const void* pts, void* out) {
+#else
+  ;
+#endif
+  static int mul(arkmpc_ctx* ctx, size_t n_points, const void* scalars, int sshift, const void* pts, void* out)
+#if ARK_IN_PART(0)
+  {
     pt_mul_kernel<C><<<pt_grid(ctx, n_points, 2), kPtBlock, 0, ctx->stream>>>(n_points, vec(scalars), sshift, pvec(pts, PB), pmvec(out, PB));
     return post_launch(ctx, "pt_mul_kernel");
   }
-  static int mul_auth(arkmpc_ctx* ctx, size_t n, const void* s_share, const void* s_mac, const void* pts, void* out_ps) {
+#else
+  ;
+#endif
+  static int mul_auth(arkmpc_ctx* ctx, size_t n, const void* s_share, const void* s_mac, const void* pts, void* out_ps)
+#if ARK_IN_PART(3)
+  {
     char* o = static_cast<char*>(out_ps);
     pt_mul_auth_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, vec(s_share), vec(s_mac), pvec(pts, PB), pmvec(o, 2 * PB), pmvec(o + PB, 2 * PB));
     return post_launch(ctx, "pt_mul_auth_kernel");
   }
-  static int mul_gen(arkmpc_ctx* ctx, size_t n, const void* scalars, void* out, uint32_t out_stride) {
+#else
+  ;
+#endif
+  static int mul_gen(arkmpc_ctx* ctx, size_t n, const void* scalars, void* out, uint32_t out_stride)
+#if ARK_IN_PART(0)
+  {
     const Aff* g;
     int rc = gtab(ctx, &g);
     if (rc != ARKMPC_OK) return rc;
     pt_mul_gen_kernel<C><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, vec(scalars), g, pmvec(out, out_stride));
     return post_launch(ctx, "pt_mul_gen_kernel");
   }
+#else
+  ;
+#endif
   static int beaver_mask(arkmpc_ctx* ctx, size_t n, const void* x_share, const void* P_ps, const void* a_share, const void* b_share, void* d_mine,
-                         void* E_mine) {
+                         void* E_mine)
+#if ARK_IN_PART(1)
+  {
     const Aff* g;
     int rc = gtab(ctx, &g);
     if (rc != ARKMPC_OK) return rc;
@@ -121,9 +160,14 @@ struct CurveLaunch {
                                                                              mvec(d_mine), pmvec(E_mine, PB));
     return post_launch(ctx, "pt_beaver_mask_kernel");
   }
+#else
+  ;
+#endif
   static int beaver_recombine(arkmpc_ctx* ctx, int party, const fe8& key, size_t n, const void* d_mine, const void* d_peer, const void* E_mine,
                               const void* E_peer, const void* a_s, const void* a_m, const void* b_s, const void* b_m, const void* c_s,
-                              const void* c_m, void* out_ps, void* d_open, void* E_open) {
+                              const void* c_m, void* out_ps, void* d_open, void* E_open)
+#if ARK_IN_PART(1)
+  {
     const Aff* gt;
     int rc = gtab(ctx, &gt);
     if (rc != ARKMPC_OK) return rc;
@@ -140,28 +184,53 @@ struct CurveLaunch {
     pt_beaver_recombine_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, g, gt);
     return post_launch(ctx, "pt_beaver_recombine_kernel");
   }
-  static int mac_check(arkmpc_ctx* ctx, const fe8& key, size_t n, const void* opened, const void* a_ps, void* check) {
+#else
+  ;
+#endif
+  static int mac_check(arkmpc_ctx* ctx, const fe8& key, size_t n, const void* opened, const void* a_ps, void* check)
+#if ARK_IN_PART(3)
+  {
     const char* a = static_cast<const char*>(a_ps);
     pt_mac_check_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, key, pvec(opened, PB), pvec(a + PB, 2 * PB), pmvec(check, PB));
     return post_launch(ctx, "pt_mac_check_kernel");
   }
-  static int sum_is_identity(arkmpc_ctx* ctx, size_t n, const void* mine, const void* peer, int* flag_dev) {
+#else
+  ;
+#endif
+  static int sum_is_identity(arkmpc_ctx* ctx, size_t n, const void* mine, const void* peer, int* flag_dev)
+#if ARK_IN_PART(0)
+  {
     pt_sum_is_identity_kernel<C><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, pvec(mine, PB), pvec(peer, PB), flag_dev);
     return post_launch(ctx, "pt_sum_is_identity_kernel");
   }
-  static int normalize(arkmpc_ctx* ctx, size_t n, const void* pts, void* out_xy) {
+#else
+  ;
+#endif
+  static int normalize(arkmpc_ctx* ctx, size_t n, const void* pts, void* out_xy)
+#if ARK_IN_PART(0)
+  {
     char* o = static_cast<char*>(out_xy);
     pt_normalize_kernel<C><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, pvec(pts, PB), mvec(o, 64), mvec(o + 32, 64));
     return post_launch(ctx, "pt_normalize_kernel");
   }
+#else
+  ;
+#endif
 
-  static int copy(arkmpc_ctx* ctx, size_t n, const void* in, uint32_t in_stride, void* out, uint32_t out_stride) {
+  static int copy(arkmpc_ctx* ctx, size_t n, const void* in, uint32_t in_stride, void* out, uint32_t out_stride)
+#if ARK_IN_PART(0)
+  {
     pt_copy_kernel<C><<<pt_grid(ctx, n, 8), kPtBlock, 0, ctx->stream>>>(n, pvec(in, in_stride), pmvec(out, out_stride));
     return post_launch(ctx, "pt_copy_kernel");
   }
+#else
+  ;
+#endif
 
   // scratch: ctx->partials holds 2 * kMaxPartialBlocks field elements = 64 KiB = 512 BN254 / 512 Edwards points at most
-  static int sum(arkmpc_ctx* ctx, size_t n, const void* in, uint32_t in_stride, void* out_point) {
+  static int sum(arkmpc_ctx* ctx, size_t n, const void* in, uint32_t in_stride, void* out_point)
+#if ARK_IN_PART(0)
+  {
     const size_t cap = (size_t)2 * kMaxPartialBlocks * 32 / PB;
     size_t blocks = (n + kPtBlock - 1) / kPtBlock;
     if (blocks > cap) blocks = cap;
@@ -172,13 +241,18 @@ struct CurveLaunch {
     pt_sum_kernel<C><<<1, kPtBlock, 0, ctx->stream>>>(blocks, pvec(ctx->partials, PB), pmvec(out_point, PB), 0);
     return post_launch(ctx, "pt_sum_kernel");
   }
+#else
+  ;
+#endif
 
   // Public MSM: n parallel scalar multiplications + a sum below kMsmNaiveBelow points (the reference switches to Pippenger at
   // MSM_SIZE_THRESHOLD = 10, curve.rs:34; on the GPU the bucket method's serial tail — up to 253 dependent doublings to weight
   // the top window, ~0.5-0.8 ms — only pays off from ~2^15 points: measured 2^12: 0.63 ms naive vs 1.09 ms buckets, 2^16: 1.82 vs
   // 1.48 ms, 2^20: 25.5 vs 7.1 ms on Curve25519), the bucket method of curve_msm.cuh above.  Scratch is stream-ordered.
   static constexpr size_t kMsmNaiveBelow = (size_t)1 << 15;
-  static int msm(arkmpc_ctx* ctx, size_t n, const void* scalars, const void* pts, void* out_point) {
+  static int msm(arkmpc_ctx* ctx, size_t n, const void* scalars, const void* pts, void* out_point)
+#if ARK_IN_PART(2)
+  {
     cudaStream_t st = ctx->stream;
     if (n < kMsmNaiveBelow) {
       void* tmp = nullptr;
@@ -231,11 +305,19 @@ struct CurveLaunch {
     cudaFreeAsync(ptmem, st);
     return rc;
   }
+#else
+  ;
+#endif
 
-  static const CurveOps* ops() {
+  static const CurveOps* ops()
+#if ARK_IN_PART(0)
+  {
     static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, normalize, copy, sum, msm};
     return &t;
   }
+#else
+  ;
+#endif
 };
 
 }  // namespace arkctx
