@@ -56,6 +56,7 @@ _PROTOS = {
     "arkmpc_share_zip": [_vp, _sz, _vp, _vp, _vp],
     "arkmpc_fr_beaver_mask": [_vp, _i, _sz] + [_vp] * 6,
     "arkmpc_fr_beaver_recombine": [_vp, _i, _i, _vp, _sz] + [_vp] * 14,
+    "arkmpc_fr_beaver_recombine_sum": [_vp, _i, _i, _vp, _sz] + [_vp] * 12,
     "arkmpc_fr_add": [_vp, _i, _sz, _vp, _vp, _vp],
     "arkmpc_fr_sub": [_vp, _i, _sz, _vp, _vp, _vp],
     "arkmpc_fr_mul": [_vp, _i, _sz, _vp, _vp, _vp],

@@ -547,6 +547,41 @@ static int sum_impl(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a0, co
   ctx->launches++;
   return post_launch(ctx, "fr_sum");
 }
+int arkmpc_fr_beaver_recombine_sum(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n, const uint64_t* d_mine,
+                                   const uint64_t* e_mine, const uint64_t* d_peer, const uint64_t* e_peer, const uint64_t* a_share,
+                                   const uint64_t* a_mac, const uint64_t* b_share, const uint64_t* b_mac, const uint64_t* c_share,
+                                   const uint64_t* c_mac, uint64_t* out_share, uint64_t* out_mac) {
+  ARK_CHECK_CTX(ctx);
+  ARK_REQUIRE(ctx, party_id == 0 || party_id == 1, "party_id must be 0 or 1");
+  ARK_REQUIRE(ctx, out_share && out_mac && aligned32(out_share) && aligned32(out_mac), "null or misaligned pointer");
+  if (n == 0) return sum_impl(ctx, field, 0, out_share, out_mac, out_share, out_mac);  // the additive identity, like an empty sum()
+  ARK_REQUIRE(ctx, key_host && d_mine && e_mine && d_peer && e_peer && a_share && a_mac && b_share && b_mac && c_share && c_mac, "null pointer");
+  const void* ptrs[] = {d_mine, e_mine, d_peer, e_peer, a_share, a_mac, b_share, b_mac, c_share, c_mac};
+  for (const void* p : ptrs) ARK_REQUIRE(ctx, aligned32(p), "planes must be 32-byte aligned");
+  RecombineArgs g;
+  g.d_mine = vec(d_mine); g.e_mine = vec(e_mine); g.d_peer = vec(d_peer); g.e_peer = vec(e_peer);
+  g.a_s = vec(a_share); g.a_m = vec(a_mac); g.b_s = vec(b_share); g.b_m = vec(b_mac); g.c_s = vec(c_share); g.c_m = vec(c_mac);
+  g.out_s = mvec(nullptr); g.out_m = mvec(nullptr); g.d_open = mvec(nullptr); g.e_open = mvec(nullptr);
+  g.key = load_host_fe(key_host);
+  const size_t per_block = (size_t)kBlock * kSumGatesPerThread;
+  const size_t need = (n + per_block - 1) / per_block;
+  const unsigned grid = (unsigned)(need < (1u << 30) ? need : (1u << 30));
+  const size_t warps = (size_t)grid * (kBlock / 32);
+  cudaStream_t s = ctx->stream;
+  char* part = nullptr;  // one (share, mac) partial per warp, stream-ordered scratch
+  ARK_CUDA(ctx, cudaMallocAsync(&part, warps * 64, s));
+  char* part_m = part + warps * 32;
+  ARK_FIELD_SWITCH(ctx, field, {
+    if (party_id == 0) launch_pdl(ctx, beaver_recombine_sum_kernel<F, 0>, grid, s, n, g, mvec(part), mvec(part_m));
+    else launch_pdl(ctx, beaver_recombine_sum_kernel<F, 1>, grid, s, n, g, mvec(part), mvec(part_m));
+  });
+  int rc = post_launch(ctx, "beaver_recombine_sum_kernel");
+  if (rc == ARKMPC_OK)
+    rc = sum_impl(ctx, field, warps, reinterpret_cast<const uint64_t*>(part), reinterpret_cast<const uint64_t*>(part_m), out_share, out_mac);
+  cudaFreeAsync(part, s);
+  return rc;
+}
+
 int arkmpc_fr_share_sum(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a_share, const uint64_t* a_mac, uint64_t* out_share, uint64_t* out_mac) {
   if (!a_mac) return fail(ctx, ARKMPC_ERR_INVALID, "null pointer");
   return sum_impl(ctx, field, n, a_share, a_mac, out_share, out_mac);

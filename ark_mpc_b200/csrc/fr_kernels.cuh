@@ -461,6 +461,52 @@ __global__ void __launch_bounds__(kBlock) fr_sum_kernel(size_t n, Vec a0, Vec a1
 }
 
 // ---------------------------------------------------------------------------------------------
+// Beaver phase 2 fused with the Sum that follows it in an inner product (circuits.rs:22-50: sum_i [a_i][b_i]): the products
+// are never written; each block leaves one partial (share, mac) and fr_sum_kernel folds the partials.  Modular addition is
+// associative and commutative on canonical residues, so the result is bit-identical to batch_mul followed by sum().
+// ---------------------------------------------------------------------------------------------
+// Launch shape: kSumGatesPerThread gates per thread (grid-stride, coalesced) and one partial per WARP — no shared memory, no
+// barrier; with one gate per thread and a block-level tree the reduction cost more than the separate Sum launches it replaces.
+constexpr int kSumGatesPerThread = 4;
+
+template <class F, int PARTY>
+__global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_sum_kernel(size_t n, const __grid_constant__ RecombineArgs g,
+                                                                                         MVec part_s, MVec part_m) {
+  pdl_prologue();
+  const size_t step = (size_t)gridDim.x * kBlock;
+  fe8 acc_s, acc_m;
+  Fp<F>::set_zero(acc_s);
+  Fp<F>::set_zero(acc_m);
+#pragma unroll 1
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 dm, em, dp, ep, as, am, bs, bm, cs, cm;
+    ld_fe(dm, g.d_mine, i);
+    ld_fe(dp, g.d_peer, i);
+    ld_fe(em, g.e_mine, i);
+    ld_fe(ep, g.e_peer, i);
+    ld_fe(bs, g.b_s, i);
+    ld_fe(as, g.a_s, i);
+    ld_fe(bm, g.b_m, i);
+    ld_fe(am, g.a_m, i);
+    ld_fe(cs, g.c_s, i);
+    ld_fe(cm, g.c_m, i);
+    fe8 os, om, d, e, r;
+    beaver_recombine_elem<F>(os, om, d, e, PARTY, g.key, dm, em, dp, ep, as, am, bs, bm, cs, cm);
+    Fp<F>::add(r, acc_s, os);
+    acc_s = r;
+    Fp<F>::add(r, acc_m, om);
+    acc_m = r;
+  }
+  warp_sum<F>(acc_s);
+  warp_sum<F>(acc_m);
+  if ((threadIdx.x & 31) == 0) {
+    const size_t w = (size_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    st_fe(part_s, w, acc_s);
+    st_fe(part_m, w, acc_m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Layout conversion and synthetic data
 // ---------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(kBlock) copy_planes_kernel(size_t n, Vec in_s, Vec in_m, MVec out_s, MVec out_m) {

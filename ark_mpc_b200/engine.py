@@ -119,6 +119,17 @@ class Engine:
                    self._p(out_s), self._p(out_m), self._p(d_o), self._p(e_o))
         return (out_s, out_m), (d_o, e_o)
 
+    def beaver_recombine_sum(self, party: int, key, d_mine, e_mine, d_peer, e_peer, a: Planes, b: Planes, c: Planes) -> Planes:
+        """sum_i [x_i * y_i] as one ScalarShare (two 1-row planes): phase 2 fused with the tree-sum that follows it."""
+        n = d_mine.shape[0]
+        out_s, out_m = self.empty(1), self.empty(1)
+        k = self.key_limbs(key)
+        self._call("arkmpc_fr_beaver_recombine_sum", self.field, int(party), k.ctypes.data_as(C.c_void_p), n,
+                   self._p(d_mine), self._p(e_mine), self._p(d_peer), self._p(e_peer),
+                   self._p(a[0]), self._p(a[1]), self._p(b[0]), self._p(b[1]), self._p(c[0]), self._p(c[1]),
+                   self._p(out_s), self._p(out_m))
+        return out_s, out_m
+
     # -- public-scalar gates --------------------------------------------------------------------
     def _binary(self, name, a, b, out=None):
         n = a.shape[0]

@@ -594,6 +594,26 @@ class AuthenticatedScalarResult:
         f.n_gates += 2
         return AuthenticatedScalarResult(f, *out)
 
+    @staticmethod
+    def batch_mul_sum(a, b):
+        """`batch_mul(a, b)` followed by `sum()` (the inner product of integration/src/circuits.rs:22-50) with the second Beaver
+        phase and the tree-sum in one kernel: same triples, same messages, bit-identical result, but the n products are never
+        written."""
+        AuthenticatedScalarResult._same_len(a, b, "batch_mul")
+        f = a.fabric
+        n = len(a)
+        E = f.engine
+        if n == 0:
+            return f.zeros_authenticated(1)   # an empty sum() is the additive identity
+        ba, bb, bc = f.next_triple_batch(n)
+        de_mine = E.empty(2 * n)
+        E.beaver_mask(a.share, b.share, ba.share, bb.share, out=(de_mine[:n], de_mine[n:]))
+        de_peer = f.exchange_tensor(de_mine)
+        out = E.beaver_recombine_sum(f.party_id(), f.mac_key(), de_mine[:n], de_mine[n:], de_peer[:n], de_peer[n:], ba.planes(), bb.planes(),
+                                     bc.planes())
+        f.n_gates += 3
+        return AuthenticatedScalarResult(f, *out)
+
     # -- opening (:129-172, :278-354) ------------------------------------------------------------
     @staticmethod
     def open_batch(values) -> ScalarResult:

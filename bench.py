@@ -286,9 +286,12 @@ def run_supplementary(args, rank, world, local_rank):
                 for p in (0, 1):
                     E.beaver_mask(X[p][0], Y[p][0], A[p][0], B[p][0], out=de[p])
                 for p in (0, 1):
-                    E.beaver_recombine(p, keys[p], de[p][0], de[p][1], de[1 - p][0], de[1 - p][1], A[p], B[p], Cc[p], out=outs[p])
+                    if args.unfused_sum:
+                        E.beaver_recombine(p, keys[p], de[p][0], de[p][1], de[1 - p][0], de[1 - p][1], A[p], B[p], Cc[p], out=outs[p])
+                        sums[p] = E.share_sum(outs[p])
+                    else:  # second Beaver phase and the tree-sum in one kernel: the products are never written
+                        sums[p] = E.beaver_recombine_sum(p, keys[p], de[p][0], de[p][1], de[1 - p][0], de[1 - p][1], A[p], B[p], Cc[p])
                 for p in (0, 1):
-                    sums[p] = E.share_sum(outs[p])
                     if world > 1:  # cross-GPU sum: all-gather of the per-rank partial ScalarShares (64 B), modular add locally
                         sums[p] = sh.all_reduce_share_sum(E, sums[p])
                 opened = E.add(sums[0][0], sums[1][0])            # open of the single result
@@ -300,7 +303,7 @@ def run_supplementary(args, rank, world, local_rank):
             if world > 1:
                 want = E.sum(sh.all_gather_rows(want))
             ok = torch.equal(opened, want) and E.sum_is_zero(chk[0], chk[1])
-            alg_bytes = 2 * (192 + 384 + 64)
+            alg_bytes = 2 * (192 + 384 + 64) if args.unfused_sum else 2 * (192 + 320)
             metric, unit = "inner_product_elements_per_sec", "elements/s"
             wl = f"secret-shared inner product of length-2^{args.log2_batch} vectors per GPU (batch_mul + tree-sum + open with MAC check), both parties (BASELINE.json configs[3])"
         if not ok:
@@ -343,7 +346,8 @@ def run_supplementary(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "note": ("compute-bound (INT32 multiply pipe): ~6.7k base-field multiplications per party-gate; the HBM fraction is "
-                                  "reported for completeness") if points else "HBM-bound streaming: 640 algorithmic B per party-element"},
+                                  "reported for completeness") if points else ("HBM-bound streaming: 640 algorithmic B per party-element" if args.unfused_sum else
+                                                                   "HBM-bound streaming: 512 algorithmic B per party-element (fused recombine + sum)")},
             "clocks": clocks, "gpu_launches": int(launches) * world}
     if not args.no_cpu_baseline and world == 1:
         from oracle import coracle as co
@@ -413,6 +417,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused-sum", action="store_true", help="inner_product: separate recombine and share_sum launches (A/B)")
     ap.add_argument("--workload", default="beaver_fr", choices=["beaver_fr", "point_mul", "inner_product"],
                     help="beaver_fr = BASELINE.json's metric (configs[1]); point_mul = configs[2]; inner_product = configs[3] "
                          "(supplementary lines, same JSON shape)")

@@ -109,6 +109,19 @@ int arkmpc_fr_beaver_recombine(arkmpc_ctx* ctx, int field, int party_id, const u
                                uint64_t* out_share, uint64_t* out_mac,
                                uint64_t* d_open, uint64_t* e_open);
 
+/* Phase 2 fused with the `Sum` that follows it in an inner product (`a.iter().zip(b).map(|(a, b)| a * b).sum()`,
+ * integration/src/circuits.rs:22-50; Sum for AuthenticatedScalarResult, authenticated_scalar.rs:563-576): same inputs as
+ * arkmpc_fr_beaver_recombine, but the n products are never written; out_share / out_mac receive the ONE ScalarShare
+ * sum_i [x_i * y_i] (32 bytes each).  Bit-identical to arkmpc_fr_beaver_recombine followed by arkmpc_fr_share_sum;
+ * n == 0 gives the additive identity like an empty sum(). */
+int arkmpc_fr_beaver_recombine_sum(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                                   const uint64_t* d_mine, const uint64_t* e_mine,
+                                   const uint64_t* d_peer, const uint64_t* e_peer,
+                                   const uint64_t* a_share, const uint64_t* a_mac,
+                                   const uint64_t* b_share, const uint64_t* b_mac,
+                                   const uint64_t* c_share, const uint64_t* c_mac,
+                                   uint64_t* out_share, uint64_t* out_mac);
+
 /* ---- public-scalar vector gates (algebra/scalar/scalar_result.rs:170-278) ---- */
 int arkmpc_fr_add(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, const uint64_t* b, uint64_t* out); /* also the open-add */
 int arkmpc_fr_sub(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, const uint64_t* b, uint64_t* out);

@@ -150,10 +150,13 @@ def test_inner_product(field):
         S = F.AuthenticatedScalarResult
         A = fabric.batch_share_scalar(a if fabric.party_id() == 0 else len(a), 0)
         B = fabric.batch_share_scalar(b if fabric.party_id() == 1 else len(b), 1)
-        return S.open_authenticated_batch(S.batch_mul(A, B).sum()).result().to_ints()
+        unfused = S.open_authenticated_batch(S.batch_mul(A, B).sum()).result().to_ints()
+        fused = S.open_authenticated_batch(S.batch_mul_sum(A, B)).result().to_ints()   # recombine + sum in one kernel
+        return unfused, fused
 
     r0, r1 = F.execute_mock_mpc(party, field=field, beaver=random_source)
-    assert r0 == r1 == [sum(x * y for x, y in zip(a, b)) % p]
+    want = [sum(x * y for x, y in zip(a, b)) % p]
+    assert r0 == r1 == (want, want)
 
 
 # ---- points -------------------------------------------------------------------------------------------------------

@@ -103,6 +103,42 @@ def test_beaver_mask_and_recombine_bit_exact(engines, fid, n):
 
 
 @pytest.mark.parametrize("fid", FIDS)
+@pytest.mark.parametrize("n", SIZES + [300000])
+def test_beaver_recombine_sum_bit_exact(engines, fid, n):
+    """Phase 2 fused with the Sum that follows it (inner product, circuits.rs:22-50): one ScalarShare per party, limb-exact against the
+    oracle's batch_mul followed by its share sum, and against the unfused device path."""
+    E = engines[fid]
+    D = TwoPartyData(fid, n, seed=501 + n, edge=True)
+    o0, o1, _, _ = D.oracle_batch_mul()
+    masks = []
+    for p in (0, 1):
+        P = D.party(p)
+        masks.append(E.beaver_mask(up(E, P["x"][0]), up(E, P["y"][0]), up(E, P["a"][0]), up(E, P["b"][0])))
+    for p, want in ((0, o0), (1, o1)):
+        P = D.party(p)
+        pl = lambda t: (up(E, t[0]), up(E, t[1]))
+        args = (p, P["key"], masks[p][0], masks[p][1], masks[1 - p][0], masks[1 - p][1], pl(P["a"]), pl(P["b"]), pl(P["c"]))
+        s, m = E.beaver_recombine_sum(*args)
+        want_sum = co.share_sum(fid, want)
+        assert np.array_equal(dn(E, s)[0], want_sum[:4]), f"share sum mismatch party {p}"
+        assert np.array_equal(dn(E, m)[0], want_sum[4:]), f"mac sum mismatch party {p}"
+        unfused = E.share_sum(E.beaver_recombine(*args)[0])
+        assert np.array_equal(dn(E, unfused[0]), dn(E, s)) and np.array_equal(dn(E, unfused[1]), dn(E, m))
+
+
+def test_beaver_recombine_sum_empty_and_invalid(engines):
+    import ark_mpc_b200._native as nat
+
+    E = engines[0]
+    z = E.empty(0)
+    s, m = E.beaver_recombine_sum(0, co.synth(0, 1, 0, 1)[0], z, z, z, z, (z, z), (z, z), (z, z))
+    assert not dn(E, s).any() and not dn(E, m).any()
+    a = E.random(3, 0, 8)
+    with pytest.raises(nat.ArkMpcError):
+        E.beaver_recombine_sum(2, co.synth(0, 1, 0, 1)[0], a, a, a, a, (a, a), (a, a), (a, a))
+
+
+@pytest.mark.parametrize("fid", FIDS)
 @pytest.mark.parametrize("n", [1, 1000, 4099])
 def test_share_gates(engines, fid, n):
     E = engines[fid]
