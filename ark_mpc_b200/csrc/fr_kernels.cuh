@@ -465,9 +465,9 @@ __global__ void __launch_bounds__(kBlock) fr_sum_kernel(size_t n, Vec a0, Vec a1
 // are never written; each block leaves one partial (share, mac) and fr_sum_kernel folds the partials.  Modular addition is
 // associative and commutative on canonical residues, so the result is bit-identical to batch_mul followed by sum().
 // ---------------------------------------------------------------------------------------------
-// Launch shape: kSumGatesPerThread gates per thread (grid-stride, coalesced) and one partial per WARP — no shared memory, no
+// Launch shape (profiles/r01k_recombine_sum_ab.txt): kSumGatesPerThread gates per thread (grid-stride, coalesced) and one partial per WARP — no shared memory, no
 // barrier; with one gate per thread and a block-level tree the reduction cost more than the separate Sum launches it replaces.
-constexpr int kSumGatesPerThread = 4;
+constexpr int kSumGatesPerThread = 8;
 
 template <class F, int PARTY>
 __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_sum_kernel(size_t n, const __grid_constant__ RecombineArgs g,
