@@ -70,6 +70,7 @@ _PROTOS = {
     "arkmpc_fr_share_mul_public": [_vp, _i, _sz] + [_vp] * 5,
     "arkmpc_fr_mac_check": [_vp, _i, _vp, _sz, _vp, _vp, _vp],
     "arkmpc_fr_sum_is_zero": [_vp, _i, _sz, _vp, _vp, C.POINTER(_i)],
+    "arkmpc_fr_validate": [_vp, _i, _sz, _vp, C.POINTER(_i)],
     "arkmpc_fr_to_bytes_be": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_fr_share_sum": [_vp, _i, _sz, _vp, _vp, _vp, _vp],
     "arkmpc_fr_sum": [_vp, _i, _sz, _vp, _vp],
@@ -83,6 +84,17 @@ _PROTOS = {
     "arkmpc_ipc_import": [_vp, _vp, C.POINTER(_vp)],
     "arkmpc_ipc_release": [_vp, _vp],
     "arkmpc_fr_beaver_recombine_gather": [_vp, _i, _i, _vp, _sz] + [_vp] * 12 + [_i, _i, _vp, _vp],
+    "arkmpc_mc_supported": [_vp, C.POINTER(_i)],
+    "arkmpc_mc_open": [_vp, _sz, _i, _i, _i, _i, C.POINTER(_vp)],
+    "arkmpc_mc_export": [_vp, C.POINTER(_i), C.POINTER(_i)],
+    "arkmpc_mc_bind": [_vp, C.POINTER(_vp), C.POINTER(_vp)],
+    "arkmpc_mc_close": [_vp],
+    "arkmpc_fr_beaver_recombine_gather_mc": [_vp, _i, _i, _vp, _sz] + [_vp] * 12 + [_i, _i, _vp, _vp],
+    "arkmpc_mc_allgather_rows": [_vp, _sz, _i, _vp, _vp],
+    "arkmpc_nccl_unique_id": [_vp],
+    "arkmpc_nccl_init": [_vp, _i, _i, _vp],
+    "arkmpc_nccl_destroy": [_vp],
+    "arkmpc_allgather_open": [_vp, _sz, _vp, _vp, _vp, _vp],
     "arkmpc_point_bytes": [_i],
     "arkmpc_pt_add": [_vp, _i, _sz, _vp, _vp, _vp],
     "arkmpc_pt_sub": [_vp, _i, _sz, _vp, _vp, _vp],
@@ -108,6 +120,7 @@ _PROTOS = {
     "arkmpc_fr_batch_mul_begin_host": [_vp, _i, _i, _vp, _sz] + [_vp] * 6 + [C.POINTER(_vp)],
     "arkmpc_fr_batch_mul_finish_host": [_vp, _vp, _vp, _vp],
     "arkmpc_fr_batch_mul_abort": [_vp],
+    "arkmpc_fr_batch_mul_host_bytes": [_vp, _sz, _i, C.POINTER(_u64), C.POINTER(_u64)],
 }
 _RESTYPES = {
     "arkmpc_status_string": C.c_char_p,

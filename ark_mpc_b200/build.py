@@ -71,7 +71,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 4))) as pool:
         objs = list(pool.map(compile_one, srcs))
     tmp = LIB + ".tmp"  # link beside the target and rename: a failed link must not remove a working library
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs])
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs, "-ldl"])
     os.replace(tmp, LIB)
     return LIB
 

@@ -121,7 +121,8 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
   if (!ctx) return ARKMPC_ERR_OOM;
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  bool ok = cudaSetDevice(device) == cudaSuccess;
+  CallGuard guard(ctx);  // switches to `device`, restores the caller's current device on return
+  bool ok = guard.err == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; ok && i < kSlots; i++) {
     ok = cudaStreamCreateWithFlags(&ctx->slot_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
@@ -140,6 +141,7 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
   }
   if (!ok) {
     cudaGetLastError();
+    guard.lk.unlock();
     arkmpc_ctx_destroy(ctx);
     return ARKMPC_ERR_CUDA;
   }
@@ -151,6 +153,10 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
     if (pd && strcmp(pd, "0") == 0) ctx->pdl = false;
     const char* gm = getenv("ARKMPC_GRID");
     if (gm && strcmp(gm, "persistent") == 0) ctx->full_grids = false;
+    const char* xy = getenv("ARKMPC_XY");
+    if (xy && strcmp(xy, "flat") == 0) ctx->xy_mode = 0;
+    if (xy && strcmp(xy, "2d") == 0) ctx->xy_mode = 1;
+    if (xy && strcmp(xy, "zc") == 0) ctx->xy_mode = 2;
     const char* c = getenv("ARKMPC_CHUNK_LOG2");
     if (c && atoi(c) >= 10 && atoi(c) <= 24) ctx->chunk_elems = (size_t)1 << atoi(c);
   }
@@ -160,7 +166,9 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
 
 int arkmpc_ctx_destroy(arkmpc_ctx* ctx) {
   if (!ctx) return ARKMPC_OK;
-  cudaSetDevice(ctx->device);
+  {
+  CallGuard guard(ctx);
+  arkmpc_nccl_destroy(ctx);
   if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
   for (int i = 0; i < kSlots; i++) {
     if (ctx->slot_stream[i]) { cudaStreamSynchronize(ctx->slot_stream[i]); cudaStreamDestroy(ctx->slot_stream[i]); }
@@ -172,25 +180,28 @@ int arkmpc_ctx_destroy(arkmpc_ctx* ctx) {
   for (int c = 0; c < kNumCurves; c++)
     if (ctx->gtab[c]) cudaFree(ctx->gtab[c]);
   if (ctx->ntt_tw) cudaFree(ctx->ntt_tw);
+  }  // the guard (and the lock it holds) must be gone before the context is
   delete ctx;
   return ARKMPC_OK;
 }
 
 int arkmpc_ctx_set_stream(arkmpc_ctx* ctx, void* cuda_stream) {
   if (!ctx) return ARKMPC_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   return ARKMPC_OK;
 }
 int arkmpc_ctx_reset_stream(arkmpc_ctx* ctx) {
   if (!ctx) return ARKMPC_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   ctx->stream = ctx->own_stream;
   return ARKMPC_OK;
 }
 void* arkmpc_ctx_get_stream(arkmpc_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
 int arkmpc_ctx_device(arkmpc_ctx* ctx) { return ctx ? ctx->device : -1; }
 int arkmpc_ctx_sm_count(arkmpc_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
-uint64_t arkmpc_ctx_launch_count(arkmpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
-const char* arkmpc_last_error(arkmpc_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+uint64_t arkmpc_ctx_launch_count(arkmpc_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+const char* arkmpc_last_error(arkmpc_ctx* ctx) { return ctx ? thread_error().c_str() : "null context"; }
 
 int arkmpc_ctx_sync(arkmpc_ctx* ctx) {
   ARK_CHECK_CTX(ctx);
@@ -296,8 +307,7 @@ int arkmpc_fr_beaver_recombine(arkmpc_ctx* ctx, int field, int party_id, const u
   g.d_mine = vec(d_mine); g.e_mine = vec(e_mine); g.d_peer = vec(d_peer); g.e_peer = vec(e_peer);
   g.a_s = vec(a_share); g.a_m = vec(a_mac); g.b_s = vec(b_share); g.b_m = vec(b_mac); g.c_s = vec(c_share); g.c_m = vec(c_mac);
   g.out_s = mvec(out_share); g.out_m = mvec(out_mac); g.d_open = mvec(d_open); g.e_open = mvec(e_open);
-  g.key = load_host_fe(key_host);
-  ARK_FIELD_SWITCH(ctx, field, return launch_recombine<F>(ctx, ctx->stream, party_id, n, g, d_open != nullptr));
+  ARK_FIELD_SWITCH(ctx, field, { g.key = host_ctab<F>(key_host); return launch_recombine<F>(ctx, ctx->stream, party_id, n, g, d_open != nullptr); });
   return ARKMPC_OK;
 }
 
@@ -342,7 +352,6 @@ int arkmpc_fr_beaver_recombine_gather(arkmpc_ctx* ctx, int field, int party_id, 
   g.d_mine = vec(d_mine); g.e_mine = vec(e_mine); g.d_peer = vec(d_peer); g.e_peer = vec(e_peer);
   g.a_s = vec(a_share); g.a_m = vec(a_mac); g.b_s = vec(b_share); g.b_m = vec(b_mac); g.c_s = vec(c_share); g.c_m = vec(c_mac);
   g.out_s = mvec(out_share); g.out_m = mvec(out_mac); g.d_open = mvec(nullptr); g.e_open = mvec(nullptr);
-  g.key = load_host_fe(key_host);
   GatherArgs q;
   q.world = world;
   for (int k = 0; k < kMaxPeers; k++) {
@@ -355,6 +364,7 @@ int arkmpc_fr_beaver_recombine_gather(arkmpc_ctx* ctx, int field, int party_id, 
   }
   const unsigned grid = full_grid(n);
   ARK_FIELD_SWITCH(ctx, field, {
+    g.key = host_ctab<F>(key_host);
     if (party_id == 0) launch_pdl(ctx, beaver_recombine_gather_kernel<F, 0>, grid, ctx->stream, n, g, q);
     else launch_pdl(ctx, beaver_recombine_gather_kernel<F, 1>, grid, ctx->stream, n, g, q);
   });
@@ -390,8 +400,7 @@ int arkmpc_fr_scale(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, con
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, a && out && s_host, "null pointer");
   ARK_REQUIRE(ctx, aligned32(a) && aligned32(out), "planes must be 32-byte aligned");
-  const fe8 s = load_host_fe(s_host);
-  ARK_FIELD_SWITCH(ctx, field, (fr_scale_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), s, mvec(out))));
+  ARK_FIELD_SWITCH(ctx, field, (fr_scale_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), host_ctab<F>(s_host), mvec(out))));
   return post_launch(ctx, "arkmpc_fr_scale");
 }
 
@@ -403,7 +412,9 @@ int arkmpc_fr_to_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* plai
   ARK_FIELD_SWITCH(ctx, field, {
     fe8 r2;
     Fp<F>::set_r2(r2);
-    fr_scale_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(plain), r2, mvec(mont));
+    uint64_t r2h[4];
+    for (int j = 0; j < 4; j++) r2h[j] = (uint64_t)r2.v[2 * j] | ((uint64_t)r2.v[2 * j + 1] << 32);
+    fr_scale_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(plain), host_ctab<F>(r2h), mvec(mont));
   });
   return post_launch(ctx, "arkmpc_fr_to_mont");
 }
@@ -413,10 +424,8 @@ int arkmpc_fr_from_mont(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* mo
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, plain && mont, "null pointer");
   ARK_REQUIRE(ctx, aligned32(plain) && aligned32(mont), "planes must be 32-byte aligned");
-  fe8 one;
-  for (int j = 0; j < 8; j++) one.v[j] = 0;
-  one.v[0] = 1;
-  ARK_FIELD_SWITCH(ctx, field, (fr_scale_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(mont), one, mvec(plain))));
+  const uint64_t one[4] = {1, 0, 0, 0};
+  ARK_FIELD_SWITCH(ctx, field, (fr_scale_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(mont), host_ctab<F>(one), mvec(plain))));
   return post_launch(ctx, "arkmpc_fr_from_mont");
 }
 
@@ -451,10 +460,10 @@ static int share_add_public_impl(arkmpc_ctx* ctx, int field, int party_id, const
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, key_host && a_share && a_mac && v && out_share && out_mac, "null pointer");
   ARK_REQUIRE(ctx, aligned32(a_share) && aligned32(a_mac) && aligned32(v) && aligned32(out_share) && aligned32(out_mac), "planes must be 32-byte aligned");
-  const fe8 key = load_host_fe(key_host);
   const unsigned grid = grid_stream(ctx, n, 8);
   cudaStream_t s = ctx->stream;
   ARK_FIELD_SWITCH(ctx, field, {
+    const CTab key = host_ctab<F>(key_host);
     if (party_id == 0) {
       if (sub) fr_share_add_public_kernel<F, 0, true><<<grid, kBlock, 0, s>>>(n, vec(a_share), vec(a_mac), vec(v), key, mvec(out_share), mvec(out_mac));
       else fr_share_add_public_kernel<F, 0, false><<<grid, kBlock, 0, s>>>(n, vec(a_share), vec(a_mac), vec(v), key, mvec(out_share), mvec(out_mac));
@@ -491,8 +500,7 @@ int arkmpc_fr_mac_check(arkmpc_ctx* ctx, int field, const uint64_t* key_host, si
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, key_host && opened && mac && check, "null pointer");
   ARK_REQUIRE(ctx, aligned32(opened) && aligned32(mac) && aligned32(check), "planes must be 32-byte aligned");
-  const fe8 key = load_host_fe(key_host);
-  ARK_FIELD_SWITCH(ctx, field, (fr_mac_check_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(opened), vec(mac), key, mvec(check))));
+  ARK_FIELD_SWITCH(ctx, field, (fr_mac_check_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(opened), vec(mac), host_ctab<F>(key_host), mvec(check))));
   return post_launch(ctx, "arkmpc_fr_mac_check");
 }
 
@@ -514,12 +522,30 @@ int arkmpc_fr_sum_is_zero(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* 
   return ARKMPC_OK;
 }
 
+int arkmpc_fr_validate(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, int* all_canonical_host) {
+  ARK_CHECK_CTX(ctx);
+  ARK_REQUIRE(ctx, all_canonical_host, "null pointer");
+  *all_canonical_host = 1;
+  if (n == 0) return ARKMPC_OK;
+  ARK_REQUIRE(ctx, a && aligned32(a), "null or misaligned plane");
+  *ctx->flag_host = 1;
+  ARK_CUDA(ctx, cudaMemcpyAsync(ctx->flag_dev, ctx->flag_host, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  ARK_FIELD_SWITCH(ctx, field, (fr_validate_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), ctx->flag_dev)));
+  int rc = post_launch(ctx, "arkmpc_fr_validate");
+  if (rc != ARKMPC_OK) return rc;
+  ARK_CUDA(ctx, cudaMemcpyAsync(ctx->flag_host, ctx->flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ARK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *all_canonical_host = *ctx->flag_host;
+  return ARKMPC_OK;
+}
+
 int arkmpc_fr_to_bytes_be(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, uint8_t* out_dev) {
   ARK_CHECK_CTX(ctx);
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, a && out_dev, "null pointer");
   ARK_REQUIRE(ctx, aligned32(a) && aligned32(out_dev), "planes must be 32-byte aligned");
-  ARK_FIELD_SWITCH(ctx, field, (fr_to_bytes_be_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), mvec(out_dev))));
+  const uint64_t one[4] = {1, 0, 0, 0};
+  ARK_FIELD_SWITCH(ctx, field, (fr_to_bytes_be_kernel<F><<<grid_stream(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(a), host_ctab<F>(one), mvec(out_dev))));
   return post_launch(ctx, "arkmpc_fr_to_bytes_be");
 }
 
@@ -562,7 +588,6 @@ int arkmpc_fr_beaver_recombine_sum(arkmpc_ctx* ctx, int field, int party_id, con
   g.d_mine = vec(d_mine); g.e_mine = vec(e_mine); g.d_peer = vec(d_peer); g.e_peer = vec(e_peer);
   g.a_s = vec(a_share); g.a_m = vec(a_mac); g.b_s = vec(b_share); g.b_m = vec(b_mac); g.c_s = vec(c_share); g.c_m = vec(c_mac);
   g.out_s = mvec(nullptr); g.out_m = mvec(nullptr); g.d_open = mvec(nullptr); g.e_open = mvec(nullptr);
-  g.key = load_host_fe(key_host);
   const size_t per_block = (size_t)kBlock * kSumGatesPerThread;
   const size_t need = (n + per_block - 1) / per_block;
   const unsigned grid = (unsigned)(need < (1u << 30) ? need : (1u << 30));
@@ -572,6 +597,7 @@ int arkmpc_fr_beaver_recombine_sum(arkmpc_ctx* ctx, int field, int party_id, con
   ARK_CUDA(ctx, cudaMallocAsync(&part, warps * 64, s));
   char* part_m = part + warps * 32;
   ARK_FIELD_SWITCH(ctx, field, {
+    g.key = host_ctab<F>(key_host);
     if (party_id == 0) launch_pdl(ctx, beaver_recombine_sum_kernel<F, 0>, grid, s, n, g, mvec(part), mvec(part_m));
     else launch_pdl(ctx, beaver_recombine_sum_kernel<F, 1>, grid, s, n, g, mvec(part), mvec(part_m));
   });
@@ -611,14 +637,23 @@ struct arkmpc_batch_mul {
   char* de = nullptr;     // d_mine | e_mine planes, n*32 B each
   char* stage = nullptr;  // kSlots * chunk staging
   size_t chunk = 0;
+  bool xy_zero_copy = false;
 };
 
 namespace {
 size_t stage_bytes_per_slot(size_t chunk) { return chunk * 64 * 2 + chunk * 32 * 2; }  // begin: x,y AoS ; finish: d_peer,e_peer + out AoS + d/e open
 
+// device-visible address of a pinned + mapped host buffer, or nullptr for pageable memory
+const char* mapped_device_pointer(const void* host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return static_cast<const char*>(at.devicePointer);
+}
+
+// the caller holds the context guard; drains the slot streams before the buffers go back to the pool
 int session_free(arkmpc_batch_mul* s) {
   arkmpc_ctx* ctx = s->ctx;
-  cudaSetDevice(ctx->device);
   for (int i = 0; i < kSlots; i++) cudaStreamSynchronize(ctx->slot_stream[i]);
   if (s->abc) cudaFreeAsync(s->abc, ctx->stream);
   if (s->de) cudaFreeAsync(s->de, ctx->stream);
@@ -669,27 +704,58 @@ int arkmpc_fr_batch_mul_begin_host(arkmpc_ctx* ctx, int field, int party_id, con
   char* c_dev = s->abc + n * 128;
   char* d_dev = s->de;
   char* e_dev = s->de + n * 32;
-  int slot = 0;
-  for (size_t off = 0; off < n; off += s->chunk, slot = (slot + 1) % kSlots) {
-    const size_t m = (n - off < s->chunk) ? n - off : s->chunk;
-    cudaStream_t st = ctx->slot_stream[slot];
-    char* xs = s->stage + (size_t)slot * stage_bytes_per_slot(s->chunk);
-    char* ys = xs + s->chunk * 64;
-    ARK_CUDA(ctx, cudaMemcpyAsync(xs, xh + off * 64, m * 64, cudaMemcpyHostToDevice, st));
-    ARK_CUDA(ctx, cudaMemcpyAsync(ys, yh + off * 64, m * 64, cudaMemcpyHostToDevice, st));
-    ARK_CUDA(ctx, cudaMemcpyAsync(a_dev + off * 64, ah + off * 64, m * 64, cudaMemcpyHostToDevice, st));
-    ARK_CUDA(ctx, cudaMemcpyAsync(b_dev + off * 64, bh + off * 64, m * 64, cudaMemcpyHostToDevice, st));
-    int rc = ARKMPC_OK;
-    ARK_FIELD_SWITCH(ctx, field, rc = launch_mask<F>(ctx, st, m, vec(xs, 64), vec(ys, 64), vec(a_dev + off * 64, 64), vec(b_dev + off * 64, 64),
-                                                     mvec(d_dev + off * 32), mvec(e_dev + off * 32)));
-    if (rc != ARKMPC_OK) return rc;
-    ARK_CUDA(ctx, cudaMemcpyAsync(dh + off * 32, d_dev + off * 32, m * 32, cudaMemcpyDeviceToHost, st));
-    ARK_CUDA(ctx, cudaMemcpyAsync(eh + off * 32, e_dev + off * 32, m * 32, cudaMemcpyDeviceToHost, st));
-    // c is only needed by phase 2: queue it behind the latency-critical d/e download
-    ARK_CUDA(ctx, cudaMemcpyAsync(c_dev + off * 64, ch + off * 64, m * 64, cudaMemcpyHostToDevice, st));
+  // zero-copy needs both buffers pinned and mapped (cudaHostAlloc / cudaHostRegister / arkmpc_host_alloc); pageable memory
+  // falls back to the flat copy
+  const char* x_map = ctx->xy_mode == 2 ? mapped_device_pointer(xh) : nullptr;
+  const char* y_map = ctx->xy_mode == 2 ? mapped_device_pointer(yh) : nullptr;
+  const bool xy_zero_copy = x_map && y_map;
+  s->xy_zero_copy = xy_zero_copy;
+  auto run = [&]() -> int {
+    int slot = 0;
+    for (size_t off = 0; off < n; off += s->chunk, slot = (slot + 1) % kSlots) {
+      const size_t m = (n - off < s->chunk) ? n - off : s->chunk;
+      cudaStream_t st = ctx->slot_stream[slot];
+      char* xs = s->stage + (size_t)slot * stage_bytes_per_slot(s->chunk);
+      char* ys = xs + s->chunk * 64;
+      // Only the share halves of x and y are read by the mask kernel (open_batch sends share.share() only,
+      // authenticated_scalar.rs:141-145).  xy_mode (ARKMPC_XY): "zc" = the kernel reads them straight from the caller's
+      // pinned buffers over PCIe with 256-bit loads at stride 64, the MAC halves never cross the link; "2d" = a strided
+      // DMA copy; "flat" = copy the whole AoS image.
+      Vec xv, yv;
+      if (xy_zero_copy) {
+        xv = vec(x_map + off * 64, 64);
+        yv = vec(y_map + off * 64, 64);
+      } else if (ctx->xy_mode == 1) {
+        ARK_CUDA(ctx, cudaMemcpy2DAsync(xs, 32, xh + off * 64, 64, 32, m, cudaMemcpyHostToDevice, st));
+        ARK_CUDA(ctx, cudaMemcpy2DAsync(ys, 32, yh + off * 64, 64, 32, m, cudaMemcpyHostToDevice, st));
+        xv = vec(xs);
+        yv = vec(ys);
+      } else {
+        ARK_CUDA(ctx, cudaMemcpyAsync(xs, xh + off * 64, m * 64, cudaMemcpyHostToDevice, st));
+        ARK_CUDA(ctx, cudaMemcpyAsync(ys, yh + off * 64, m * 64, cudaMemcpyHostToDevice, st));
+        xv = vec(xs, 64);
+        yv = vec(ys, 64);
+      }
+      ARK_CUDA(ctx, cudaMemcpyAsync(a_dev + off * 64, ah + off * 64, m * 64, cudaMemcpyHostToDevice, st));
+      ARK_CUDA(ctx, cudaMemcpyAsync(b_dev + off * 64, bh + off * 64, m * 64, cudaMemcpyHostToDevice, st));
+      int rc = ARKMPC_OK;
+      ARK_FIELD_SWITCH(ctx, field, rc = launch_mask<F>(ctx, st, m, xv, yv, vec(a_dev + off * 64, 64), vec(b_dev + off * 64, 64),
+                                                       mvec(d_dev + off * 32), mvec(e_dev + off * 32)));
+      if (rc != ARKMPC_OK) return rc;
+      ARK_CUDA(ctx, cudaMemcpyAsync(dh + off * 32, d_dev + off * 32, m * 32, cudaMemcpyDeviceToHost, st));
+      ARK_CUDA(ctx, cudaMemcpyAsync(eh + off * 32, e_dev + off * 32, m * 32, cudaMemcpyDeviceToHost, st));
+      // c is only needed by phase 2: queue it behind the latency-critical d/e download
+      ARK_CUDA(ctx, cudaMemcpyAsync(c_dev + off * 64, ch + off * 64, m * 64, cudaMemcpyHostToDevice, st));
+    }
+    for (int i = 0; i < kSlots; i++) ARK_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[i]));
+    return ARKMPC_OK;
+  };
+  const int rc = run();
+  if (rc != ARKMPC_OK) {  // drain what was queued and give the resident triples back: no session survives a failed begin
+    session_free(s);
+    *session = nullptr;
   }
-  for (int i = 0; i < kSlots; i++) ARK_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[i]));
-  return ARKMPC_OK;
+  return rc;
 }
 
 int arkmpc_fr_batch_mul_finish_host(arkmpc_batch_mul* s, const uint64_t* de_peer_host, uint64_t* out_host, uint64_t* de_open_host) {
@@ -698,7 +764,10 @@ int arkmpc_fr_batch_mul_finish_host(arkmpc_batch_mul* s, const uint64_t* de_peer
   ARK_CHECK_CTX(ctx);
   const size_t n = s->n;
   if (n == 0) return session_free(s);
-  if (!(de_peer_host && out_host)) return fail(ctx, ARKMPC_ERR_INVALID, "null pointer");
+  if (!(de_peer_host && out_host)) {
+    session_free(s);
+    return fail(ctx, ARKMPC_ERR_INVALID, "null pointer");
+  }
   const char* dph = reinterpret_cast<const char*>(de_peer_host);
   const char* eph = dph + n * 32;
   char* oh = reinterpret_cast<char*>(out_host);
@@ -707,42 +776,57 @@ int arkmpc_fr_batch_mul_finish_host(arkmpc_batch_mul* s, const uint64_t* de_peer
   char* a_dev = s->abc;
   char* b_dev = s->abc + n * 64;
   char* c_dev = s->abc + n * 128;
-  int slot = 0;
-  for (size_t off = 0; off < n; off += s->chunk, slot = (slot + 1) % kSlots) {
-    const size_t m = (n - off < s->chunk) ? n - off : s->chunk;
-    cudaStream_t st = ctx->slot_stream[slot];
-    char* base = s->stage + (size_t)slot * stage_bytes_per_slot(s->chunk);
-    char* dp = base;                      // chunk*32
-    char* ep = base + s->chunk * 32;      // chunk*32
-    char* out = base + s->chunk * 64;     // chunk*64 AoS
-    // the opened d/e overwrite the peer staging planes in place (element-for-element aliasing)
-    ARK_CUDA(ctx, cudaMemcpyAsync(dp, dph + off * 32, m * 32, cudaMemcpyHostToDevice, st));
-    ARK_CUDA(ctx, cudaMemcpyAsync(ep, eph + off * 32, m * 32, cudaMemcpyHostToDevice, st));
-    RecombineArgs g;
-    g.d_mine = vec(s->de + off * 32); g.e_mine = vec(s->de + n * 32 + off * 32);
-    g.d_peer = vec(dp); g.e_peer = vec(ep);
-    g.a_s = vec(a_dev + off * 64, 64); g.a_m = vec(a_dev + off * 64 + 32, 64);
-    g.b_s = vec(b_dev + off * 64, 64); g.b_m = vec(b_dev + off * 64 + 32, 64);
-    g.c_s = vec(c_dev + off * 64, 64); g.c_m = vec(c_dev + off * 64 + 32, 64);
-    g.out_s = mvec(out, 64); g.out_m = mvec(out + 32, 64);
-    g.d_open = mvec(dp); g.e_open = mvec(ep);
-    g.key = load_host_fe(s->key);
-    int rc = ARKMPC_OK;
-    ARK_FIELD_SWITCH(ctx, s->field, rc = launch_recombine<F>(ctx, st, s->party, m, g, doh != nullptr));
-    if (rc != ARKMPC_OK) return rc;
-    ARK_CUDA(ctx, cudaMemcpyAsync(oh + off * 64, out, m * 64, cudaMemcpyDeviceToHost, st));
-    if (doh) {
-      ARK_CUDA(ctx, cudaMemcpyAsync(doh + off * 32, dp, m * 32, cudaMemcpyDeviceToHost, st));
-      ARK_CUDA(ctx, cudaMemcpyAsync(eoh + off * 32, ep, m * 32, cudaMemcpyDeviceToHost, st));
+  auto run = [&]() -> int {
+    int slot = 0;
+    for (size_t off = 0; off < n; off += s->chunk, slot = (slot + 1) % kSlots) {
+      const size_t m = (n - off < s->chunk) ? n - off : s->chunk;
+      cudaStream_t st = ctx->slot_stream[slot];
+      char* base = s->stage + (size_t)slot * stage_bytes_per_slot(s->chunk);
+      char* dp = base;                      // chunk*32
+      char* ep = base + s->chunk * 32;      // chunk*32
+      char* out = base + s->chunk * 64;     // chunk*64 AoS
+      // the opened d/e overwrite the peer staging planes in place (element-for-element aliasing)
+      ARK_CUDA(ctx, cudaMemcpyAsync(dp, dph + off * 32, m * 32, cudaMemcpyHostToDevice, st));
+      ARK_CUDA(ctx, cudaMemcpyAsync(ep, eph + off * 32, m * 32, cudaMemcpyHostToDevice, st));
+      RecombineArgs g;
+      g.d_mine = vec(s->de + off * 32); g.e_mine = vec(s->de + n * 32 + off * 32);
+      g.d_peer = vec(dp); g.e_peer = vec(ep);
+      g.a_s = vec(a_dev + off * 64, 64); g.a_m = vec(a_dev + off * 64 + 32, 64);
+      g.b_s = vec(b_dev + off * 64, 64); g.b_m = vec(b_dev + off * 64 + 32, 64);
+      g.c_s = vec(c_dev + off * 64, 64); g.c_m = vec(c_dev + off * 64 + 32, 64);
+      g.out_s = mvec(out, 64); g.out_m = mvec(out + 32, 64);
+      g.d_open = mvec(dp); g.e_open = mvec(ep);
+      int rc = ARKMPC_OK;
+      ARK_FIELD_SWITCH(ctx, s->field, { g.key = host_ctab<F>(s->key); rc = launch_recombine<F>(ctx, st, s->party, m, g, doh != nullptr); });
+      if (rc != ARKMPC_OK) return rc;
+      ARK_CUDA(ctx, cudaMemcpyAsync(oh + off * 64, out, m * 64, cudaMemcpyDeviceToHost, st));
+      if (doh) {
+        ARK_CUDA(ctx, cudaMemcpyAsync(doh + off * 32, dp, m * 32, cudaMemcpyDeviceToHost, st));
+        ARK_CUDA(ctx, cudaMemcpyAsync(eoh + off * 32, ep, m * 32, cudaMemcpyDeviceToHost, st));
+      }
     }
-  }
-  for (int i = 0; i < kSlots; i++) ARK_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[i]));
-  return session_free(s);
+    for (int i = 0; i < kSlots; i++) ARK_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[i]));
+    return ARKMPC_OK;
+  };
+  const int rc = run();
+  session_free(s);  // finish consumes the session whether it succeeded or not (slot streams drained first)
+  return rc;
 }
 
 int arkmpc_fr_batch_mul_abort(arkmpc_batch_mul* s) {
   if (!s) return ARKMPC_OK;
+  arkmpc_ctx* ctx = s->ctx;
+  ARK_CHECK_CTX(ctx);
   return session_free(s);
+}
+
+/* bytes the host path moves per party for a batch of n gates (bench.py's h2d/d2h accounting comes from here) */
+int arkmpc_fr_batch_mul_host_bytes(arkmpc_ctx* ctx, size_t n, int with_open, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+  if (!ctx || !h2d_bytes || !d2h_bytes) return ARKMPC_ERR_INVALID;
+  const uint64_t xy = ctx->xy_mode == 0 ? 128 : 64;       // whole AoS x, y images, or their share halves only
+  *h2d_bytes = (uint64_t)n * (xy + 3 * 64 + 64);           // x, y, triple a, b, c, peer d || e
+  *d2h_bytes = (uint64_t)n * (64 + 64 + (with_open ? 64 : 0));  // own d || e, result shares, opened d || e on request
+  return ARKMPC_OK;
 }
 
 }  // extern "C"

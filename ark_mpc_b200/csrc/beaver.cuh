@@ -21,12 +21,13 @@ ARK_D void beaver_mask_elem(fe8& d_mine, fe8& e_mine, const fe8& x_s, const fe8&
 }
 
 // Fused recombination.  6 modular multiplications in the reference (d*e, d*b.share, d*b.mac, e*a.share,
-// e*a.mac, key*de) become 5 products and 3 Montgomery reductions:
+// e*a.mac, key*de) become 5 products and 2 + 3/8 Montgomery reductions:
 //   share = REDC(d*(b.share [+ e on party 0]) + e*a.share) + c.share
-//   mac   = REDC(d*(b.mac + REDC(key*e))      + e*a.mac)   + c.mac
-// Operand sums stay unreduced (< 3p < 2^256); F::kLazy2 makes one conditional subtraction enough.
+//   mac   = REDC(d*(b.mac + key*e)            + e*a.mac)   + c.mac
+// key*e uses the MAC key's constant-multiplier table (fp256.cuh CTab: three reduction steps instead of eight).
+// Operand sums stay unreduced (< 3p + 5p/2^32 < 2^256); F::kLazy2 makes one conditional subtraction enough.
 template <class F>
-ARK_D void beaver_recombine_elem(fe8& out_s, fe8& out_m, fe8& d, fe8& e, int party, const fe8& key,
+ARK_D void beaver_recombine_elem(fe8& out_s, fe8& out_m, fe8& d, fe8& e, int party, const CTab& key,
                                  const fe8& d_mine, const fe8& e_mine, const fe8& d_peer, const fe8& e_peer,
                                  const fe8& a_s, const fe8& a_m, const fe8& b_s, const fe8& b_m,
                                  const fe8& c_s, const fe8& c_m) {
@@ -42,34 +43,34 @@ ARK_D void beaver_recombine_elem(fe8& out_s, fe8& out_m, fe8& d, fe8& e, int par
   Fp<F>::add(out_s, s, c_s);
 
   fe8 ke;
-  Fp<F>::mul_lazy(ke, key, e);                                // < p^2/R + p < 2p
+  Fp<F>::mul_ctab_lazy(ke, key, e);                           // < p + 5p/2^32
   fe8 y;
-  Fp<F>::add_raw(y, b_m, ke);                                 // < 3p
+  Fp<F>::add_raw(y, b_m, ke);                                 // < 2p + 5p/2^32
   fe8 m;
-  Fp<F>::mul2_lazy(m, d, y, e, a_m);                          // < (3p^2 + p^2)/R + p < 2p
+  Fp<F>::mul2_lazy(m, d, y, e, a_m);                          // < (2.01p^2 + p^2)/R + p < 2p
   Fp<F>::csub_p(m);
   Fp<F>::add(out_m, m, c_m);
 }
 
 // ---- linear gates on ScalarShare (share.rs:74-131) ----
 template <class F>
-ARK_D void share_add_public_elem(fe8& out_s, fe8& out_m, int party, const fe8& key, const fe8& s, const fe8& m, const fe8& v) {
+ARK_D void share_add_public_elem(fe8& out_s, fe8& out_m, int party, const CTab& key, const fe8& s, const fe8& m, const fe8& v) {
   if (party == 0) Fp<F>::add(out_s, s, v); else out_s = s;   // share.rs:75
   fe8 kv;
-  Fp<F>::mul(kv, key, v);
+  Fp<F>::mul_ctab(kv, key, v);
   Fp<F>::add(out_m, m, kv);                                   // share.rs:76
 }
 template <class F>
-ARK_D void share_sub_public_elem(fe8& out_s, fe8& out_m, int party, const fe8& key, const fe8& s, const fe8& m, const fe8& v) {
+ARK_D void share_sub_public_elem(fe8& out_s, fe8& out_m, int party, const CTab& key, const fe8& s, const fe8& m, const fe8& v) {
   fe8 nv;
   Fp<F>::neg(nv, v);                                          // share.rs:80-82: add_public(-rhs)
   share_add_public_elem<F>(out_s, out_m, party, key, s, m, nv);
 }
 // mac_key * value - share.mac   (authenticated_scalar.rs:299-311)
 template <class F>
-ARK_D void mac_check_elem(fe8& out, const fe8& key, const fe8& opened, const fe8& mac) {
+ARK_D void mac_check_elem(fe8& out, const CTab& key, const fe8& opened, const fe8& mac) {
   fe8 kv;
-  Fp<F>::mul(kv, key, opened);
+  Fp<F>::mul_ctab(kv, key, opened);
   Fp<F>::sub(out, kv, mac);
 }
 

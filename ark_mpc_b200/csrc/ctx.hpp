@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,6 +14,7 @@
 #include <new>
 #include <string>
 
+#include "ctab.hpp"
 #include "fr_kernels.cuh"
 
 namespace arkctx {
@@ -22,34 +24,65 @@ constexpr int kMaxPartialBlocks = 1024;
 constexpr int kNumCurves = 2;
 }  // namespace arkctx
 
+// Threading (gate closures run on the executor thread or on arbitrary rayon workers concurrently,
+// /root/reference/online-phase/src/fabric/executor/multi_threaded/executor.rs:208-217, and handles are cloned across tokio
+// tasks, fabric/result.rs:262-266): a context may be called from any number of threads at once.  Every entry point holds the
+// context's (recursive) lock for the duration of the call — calls only enqueue work, so the lock is short except for the few
+// that synchronise (sum_is_zero, the host-buffer path) — and all work goes to the ONE context stream, so the order in which
+// calls return is the order in which the GPU runs them: a gate whose inputs were produced by calls that have RETURNED on
+// other threads sees their results without any event.  The last error string is per thread.
 struct arkmpc_ctx {
+  std::recursive_mutex mu;
   int device = 0;
   int sm_count = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;  // current (own or caller's)
   cudaStream_t slot_stream[arkctx::kSlots] = {nullptr, nullptr, nullptr};
   cudaEvent_t slot_event[arkctx::kSlots] = {nullptr, nullptr, nullptr};
-  uint64_t launches = 0;
+  std::atomic<uint64_t> launches{0};
   char* partials = nullptr;  // 2 * kMaxPartialBlocks field elements (also reused for point partial sums)
   int* flag_dev = nullptr;
   int* flag_host = nullptr;  // pinned
   bool use_tma = false;      // ARKMPC_RECOMBINE=tma
   bool pdl = true;           // Beaver K1/K2 launched with programmatic stream serialization (ARKMPC_PDL=0 disables)
   bool full_grids = true;    // element-wise kernels: one element per thread instead of a persistent wave (ARKMPC_GRID=persistent reverts)
+  int xy_mode = 2;           // host-buffer path, how x.share / y.share reach the mask kernel: 0 flat AoS copy, 1 strided DMA copy, 2 zero-copy reads of pinned memory (ARKMPC_XY=flat|2d|zc)
   size_t chunk_elems = arkctx::kChunkElems;  // host-buffer path staging granularity (ARKMPC_CHUNK_LOG2 overrides)
   void* gtab[arkctx::kNumCurves] = {nullptr, nullptr};  // fixed-base tables, built on first use (arkmpc_curve.cu)
   std::mutex gtab_mutex;
   void* ntt_tw = nullptr;    // twiddle table + constants of the last (field, log2n, direction) transform (arkmpc_ntt.cu)
   long ntt_key = -1;
-  std::string last_error;
+  void* nccl = nullptr;      // ncclComm_t of arkmpc_nccl_init (arkmpc_comm.cu)
+  int nccl_world = 0, nccl_rank = -1;
 };
 
 namespace arkctx {
 
-inline int fail(arkmpc_ctx* ctx, int code, const std::string& msg) {
-  if (ctx) ctx->last_error = msg;
+inline std::string& thread_error() {
+  static thread_local std::string e;
+  return e;
+}
+inline int fail(arkmpc_ctx*, int code, const std::string& msg) {
+  thread_error() = msg;
   return code;
 }
+
+// Held for the duration of one ABI call: the context lock, and the calling thread's current device switched to the
+// context's device and RESTORED on return (a multi-GPU host thread keeps its own current device).
+struct CallGuard {
+  std::unique_lock<std::recursive_mutex> lk;
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit CallGuard(arkmpc_ctx* ctx) : lk(ctx->mu) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != ctx->device) err = cudaSetDevice(ctx->device); else prev = -1;
+  }
+  ~CallGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  CallGuard(const CallGuard&) = delete;
+  CallGuard& operator=(const CallGuard&) = delete;
+};
 
 #define ARK_CUDA(ctx, expr)                                                                               \
   do {                                                                                                    \
@@ -77,6 +110,14 @@ inline ark::fe8 load_host_fe(const uint64_t* h) {
     r.v[2 * j + 1] = (uint32_t)(h[j] >> 32);
   }
   return r;
+}
+
+// constant-multiplier table of a batch-constant scalar given as the reference's 4 x u64 Montgomery image
+template <class F>
+inline ark::CTab host_ctab(const uint64_t* h) {
+  ark::CTab t;
+  ark::ctab_build<F>(t, h);
+  return t;
 }
 
 // persistent grid: enough blocks of `block` threads to cover n, capped at blocks_per_sm resident blocks per SM
@@ -108,11 +149,11 @@ inline int post_launch(arkmpc_ctx* ctx, const char* what) {
     default: return arkctx::fail(ctx, ARKMPC_ERR_INVALID, "unknown field id");   \
   }
 
+// First statement of every entry point (function scope: the guard lives until the call returns).
 #define ARK_CHECK_CTX(ctx)                                                                                                      \
-  do {                                                                                                                          \
-    if (!(ctx)) return ARKMPC_ERR_INVALID;                                                                                      \
-    cudaError_t _e = cudaSetDevice((ctx)->device);                                                                              \
-    if (_e != cudaSuccess) return arkctx::fail(ctx, ARKMPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_e));  \
-  } while (0)
+  if (!(ctx)) return ARKMPC_ERR_INVALID;                                                                                        \
+  arkctx::CallGuard _ark_guard(ctx);                                                                                            \
+  if (_ark_guard.err != cudaSuccess)                                                                                            \
+    return arkctx::fail(ctx, ARKMPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_ark_guard.err))
 
 }  // namespace arkctx

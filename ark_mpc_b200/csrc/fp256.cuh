@@ -210,6 +210,44 @@ ARK_D void acc_collapse(fe8& r, const MontAcc& t) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Multiplication by a batch-constant s (MAC key share, R^2, 1, ...): instead of a*s followed by a full 8-step
+// Montgomery reduction (64 + 64 wide multiply-adds), the host precomputes the eight residues
+//   k[i] = s * 2^(32 i + 96 - 256) mod p (i < 4),   k[i] = s * 2^(32 i + 64 - 256) mod p (i >= 4)
+// (ctab.hpp) and the kernel evaluates sum_i a_i * k[i] with only THREE reduction steps: rows 0..3, shift, rows 4..7,
+// shift, shift (64 + 24 wide multiply-adds).  Bounds (p < 2^254): after rows 0..3 the value is < 4 * 2^32 p < 2^288;
+// each shift maps V to (V + m p)/2^32, so the result is < p + 5p/2^32: one conditional subtraction canonicalises it,
+// and as a lazy operand it counts as "< 2p".  The table sits in the kernel's constant bank (a __grid_constant__
+// parameter), so the k[i][j] operands cost no registers.
+// ----------------------------------------------------------------------------------------------
+struct CTab { uint32_t k[8][8]; };
+
+// One Montgomery step on an accumulator whose folded word is still pending (no multiplication row in between): the
+// carry of E[0] + fold enters the O chain, exactly as in acc_row_first.
+template <class F>
+ARK_D void acc_reduce_shift_pending(MontAcc& t) {
+  t.E[0] = add_cc(t.E[0], t.fold);
+  const uint32_t m = mul_lo(t.E[0], F::INV);
+  mad_plimb<F::P1>(t.O[0], t.O[1], m, false);
+  mad_plimb<F::P3>(t.O[2], t.O[3], m, false);
+  mad_plimb<F::P5>(t.O[4], t.O[5], m, false);
+  mad_plimb<F::P7>(t.O[6], t.O[7], m, false);
+  ARK_EMU_EXPECT_NO_CARRY();
+  mad_plimb<F::P0>(t.E[0], t.E[1], m, true);
+  mad_plimb<F::P2>(t.E[2], t.E[3], m, false);
+  mad_plimb<F::P4>(t.E[4], t.E[5], m, false);
+  mad_plimb<F::P6>(t.E[6], t.E[7], m, false);
+  t.E[8] = addc(t.E[8], 0u);
+  const uint32_t fold = t.E[1];
+  uint32_t nO[8];
+  ARK_UNROLL for (int j = 0; j < 7; j++) nO[j] = t.E[j + 2];
+  nO[7] = 0;
+  ARK_UNROLL for (int j = 0; j < 8; j++) t.E[j] = t.O[j];
+  t.E[8] = 0;
+  ARK_UNROLL for (int j = 0; j < 8; j++) t.O[j] = nO[j];
+  t.fold = fold;
+}
+
+// ----------------------------------------------------------------------------------------------
 // 512-bit square of an 8-limb value: r[0..15] = a^2.
 // a^2 = D + 2S with D = sum a_i^2 2^(64 i) and S = sum_{i<j} a_i a_j 2^(32(i+j)).  S is a product with the multiplicand limbs
 // j <= i of row i skipped (28 wide multiply-adds instead of 64, same even/odd carry chains and word-per-row emission as
@@ -379,6 +417,31 @@ struct Fp {
       acc_reduce_shift<F>(t);
     }
     acc_collapse(r, t);
+  }
+
+  // Lazy product with a batch-constant multiplier given as its table (CTab above): r = a*s/R mod p, r < p + 5p/2^32.
+  // a: any 256-bit value.
+  ARK_DM static void mul_ctab_lazy(fe8& r, const CTab& T, const fe8& a) {
+    static_assert(F::kBits <= 254, "four unreduced rows need 4 * 2^32 p < 2^288");
+    MontAcc t;
+    acc_zero(t);
+    acc_row(t, T.k[0], a.v[0]);
+    acc_row(t, T.k[1], a.v[1]);
+    acc_row(t, T.k[2], a.v[2]);
+    acc_row(t, T.k[3], a.v[3]);
+    acc_reduce_shift<F>(t);
+    acc_row_first(t, T.k[4], a.v[4]);
+    acc_row(t, T.k[5], a.v[5]);
+    acc_row(t, T.k[6], a.v[6]);
+    acc_row(t, T.k[7], a.v[7]);
+    acc_reduce_shift<F>(t);
+    acc_reduce_shift_pending<F>(t);
+    acc_collapse(r, t);
+  }
+  // canonical
+  ARK_DM static void mul_ctab(fe8& r, const CTab& T, const fe8& a) {
+    mul_ctab_lazy(r, T, a);
+    csub_p(r);
   }
 
   // canonical square of a canonical input: dedicated 512-bit square (36 wide multiply-adds), then a word-serial Montgomery

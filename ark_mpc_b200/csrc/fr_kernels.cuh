@@ -73,7 +73,7 @@ struct RecombineArgs {
   Vec d_mine, e_mine, d_peer, e_peer;
   Vec a_s, a_m, b_s, b_m, c_s, c_m;
   MVec out_s, out_m, d_open, e_open;
-  fe8 key;
+  CTab key;  // constant-multiplier table of this party's MAC key share (ctab.hpp)
 };
 
 // Launch shape (measured on B200, tools/_k2v.cu, profiles/r01d_k2_launch_shapes.txt): the kernel is bound by the IMAD.WIDE
@@ -149,6 +149,63 @@ __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_
         st_fe(MVec{q.e[k], 32}, i, e);
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same with NVSwitch MULTICAST stores: the gathered planes of all ranks are bound to one multicast object
+// (arkmpc_mc_*, arkmpc_comm.cu) and each opened element leaves the SM ONCE (multimem.st, 2 x 16 B per plane); the switch
+// replicates it into every rank's memory, this rank's own copy included.  Egress per rank drops from (world-1) x 64 B
+// to 64 B per gate, so the gather stops being bound by the rank's NVLink egress.
+// ---------------------------------------------------------------------------------------------
+struct McGatherArgs {
+  char* d;  // multicast address of the gathered d plane, already offset to this rank's row block
+  char* e;
+};
+
+__device__ __forceinline__ void st_fe_multicast(char* base, size_t i, const fe8& r) {
+  char* a = base + i * 32;
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a), "f"(__uint_as_float(r.v[0])), "f"(__uint_as_float(r.v[1])),
+               "f"(__uint_as_float(r.v[2])), "f"(__uint_as_float(r.v[3]))
+               : "memory");
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a + 16), "f"(__uint_as_float(r.v[4])), "f"(__uint_as_float(r.v[5])),
+               "f"(__uint_as_float(r.v[6])), "f"(__uint_as_float(r.v[7]))
+               : "memory");
+}
+
+template <class F, int PARTY>
+__global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_gather_mc_kernel(size_t n, const __grid_constant__ RecombineArgs g,
+                                                                                               const __grid_constant__ McGatherArgs q) {
+  pdl_prologue();
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 dm, em, dp, ep, as, am, bs, bm, cs, cm;
+    ld_fe(dm, g.d_mine, i);
+    ld_fe(dp, g.d_peer, i);
+    ld_fe(em, g.e_mine, i);
+    ld_fe(ep, g.e_peer, i);
+    ld_fe(bs, g.b_s, i);
+    ld_fe(as, g.a_s, i);
+    ld_fe(bm, g.b_m, i);
+    ld_fe(am, g.a_m, i);
+    ld_fe(cs, g.c_s, i);
+    ld_fe(cm, g.c_m, i);
+    fe8 os, om, d, e;
+    beaver_recombine_elem<F>(os, om, d, e, PARTY, g.key, dm, em, dp, ep, as, am, bs, bm, cs, cm);
+    st_fe(g.out_s, i, os);
+    st_fe(g.out_m, i, om);
+    st_fe_multicast(q.d, i, d);
+    st_fe_multicast(q.e, i, e);
+  }
+}
+
+// plain all-gather by multicast (no arithmetic): rows of this rank's local plane -> every rank's gathered plane
+static __global__ void __launch_bounds__(kBlock) multicast_rows_kernel(size_t n, Vec local, char* mc_rows) {
+  const size_t step = (size_t)gridDim.x * kBlock;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 v;
+    ld_fe(v, local, i);
+    st_fe_multicast(mc_rows, i, v);
   }
 }
 
@@ -320,14 +377,14 @@ __global__ void __launch_bounds__(kBlock) fr_neg_kernel(size_t n, Vec a, MVec ou
   }
 }
 
-// out = a * s for one broadcast scalar s (also to_mont with s = R^2, from_mont with s = 1)
+// out = a * s for one broadcast scalar s given as its constant-multiplier table (also to_mont with s = R^2, from_mont with s = 1)
 template <class F>
-__global__ void __launch_bounds__(kBlock) fr_scale_kernel(size_t n, Vec a, fe8 s, MVec out) {
+__global__ void __launch_bounds__(kBlock) fr_scale_kernel(size_t n, Vec a, const __grid_constant__ CTab s, MVec out) {
   const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
     fe8 x, r;
     ld_fe(x, a, i);
-    Fp<F>::mul(r, x, s);
+    Fp<F>::mul_ctab(r, s, x);
     st_fe(out, i, r);
   }
 }
@@ -349,7 +406,7 @@ __global__ void __launch_bounds__(kBlock) fr_share_mul_public_kernel(size_t n, V
 }
 
 template <class F, int PARTY, bool SUB>
-__global__ void __launch_bounds__(kBlock) fr_share_add_public_kernel(size_t n, Vec a_s, Vec a_m, Vec v, fe8 key, MVec out_s, MVec out_m) {
+__global__ void __launch_bounds__(kBlock) fr_share_add_public_kernel(size_t n, Vec a_s, Vec a_m, Vec v, const __grid_constant__ CTab key, MVec out_s, MVec out_m) {
   const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
     fe8 s, m, w, os, om;
@@ -363,7 +420,7 @@ __global__ void __launch_bounds__(kBlock) fr_share_add_public_kernel(size_t n, V
 }
 
 template <class F>
-__global__ void __launch_bounds__(kBlock) fr_mac_check_kernel(size_t n, Vec opened, Vec mac, fe8 key, MVec out) {
+__global__ void __launch_bounds__(kBlock) fr_mac_check_kernel(size_t n, Vec opened, Vec mac, const __grid_constant__ CTab key, MVec out) {
   const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
     fe8 o, m, r;
@@ -389,17 +446,27 @@ __global__ void __launch_bounds__(kBlock) fr_sum_is_zero_kernel(size_t n, Vec mi
   if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(flag, 0);
 }
 
-// canonical integer value as 32 big-endian bytes (scalar.rs:118-127)
+// flag (initialised to 1 by the host) is cleared if any a[i] >= p: what arkworks' deserialisation rejects (scalar.rs:187-202)
 template <class F>
-__global__ void __launch_bounds__(kBlock) fr_to_bytes_be_kernel(size_t n, Vec a, MVec out) {
+__global__ void __launch_bounds__(kBlock) fr_validate_kernel(size_t n, Vec a, int* flag) {
   const size_t step = (size_t)gridDim.x * kBlock;
-  fe8 one;
-  Fp<F>::set_zero(one);
-  one.v[0] = 1;
+  bool ok = true;
+  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+    fe8 x;
+    ld_fe(x, a, i);
+    ok = ok && Fp<F>::is_canonical(x);
+  }
+  if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(flag, 0);
+}
+
+// canonical integer value as 32 big-endian bytes (scalar.rs:118-127); `one` = table of the integer 1 (leaves Montgomery form)
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_to_bytes_be_kernel(size_t n, Vec a, const __grid_constant__ CTab one, MVec out) {
+  const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
     fe8 x, r, o;
     ld_fe(x, a, i);
-    Fp<F>::mul(r, x, one);  // out of Montgomery form
+    Fp<F>::mul_ctab(r, one, x);
     for (int j = 0; j < 8; j++) o.v[j] = __byte_perm(r.v[7 - j], 0, 0x0123);
     st_fe(out, i, o);
   }

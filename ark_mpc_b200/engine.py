@@ -25,7 +25,9 @@ def _limbs_of_int(v: int) -> np.ndarray:
 
 
 class Engine:
-    """Owns one native context bound to `device`; all ops are enqueued on torch's current stream."""
+    """Owns one native context bound to `device`.  Every op is enqueued on the stream that is torch's CURRENT stream for the
+    device at the time of the call (the native context is re-pointed when it changed), so torch-side allocations, events and
+    `record_stream` made around a call always refer to the stream the kernels run on."""
 
     def __init__(self, device: int = 0, field: str = "bn254_fr"):
         if not torch.cuda.is_available():
@@ -53,10 +55,13 @@ class Engine:
             pass
 
     def bind_current_stream(self) -> None:
-        s = torch.cuda.current_stream(self.tdev)
-        self.lib.arkmpc_ctx_set_stream(self.ctx, C.c_void_p(s.cuda_stream))
+        s = torch.cuda.current_stream(self.tdev).cuda_stream
+        if s != getattr(self, "_bound_stream", -1):
+            self.lib.arkmpc_ctx_set_stream(self.ctx, C.c_void_p(s))
+            self._bound_stream = s
 
     def sync(self) -> None:
+        self.bind_current_stream()
         nat.check(self.lib.arkmpc_ctx_sync(self.ctx), "arkmpc_ctx_sync", self.ctx)
 
     @property
@@ -94,6 +99,7 @@ class Engine:
         return C.c_void_p(t.data_ptr())
 
     def _call(self, name: str, *args) -> None:
+        self.bind_current_stream()
         nat.check(getattr(self.lib, name)(self.ctx, *args), name, self.ctx)
 
     # -- Beaver multiplication ------------------------------------------------------------------
@@ -189,6 +195,7 @@ class Engine:
 
     def to_bytes_be(self, a) -> torch.Tensor:
         out = torch.empty((a.shape[0], 32), dtype=torch.uint8, device=self.tdev)
+        self.bind_current_stream()
         nat.check(self.lib.arkmpc_fr_to_bytes_be(self.ctx, self.field, a.shape[0], self._p(a), C.c_void_p(out.data_ptr())),
                   "arkmpc_fr_to_bytes_be", self.ctx)
         return out
@@ -403,6 +410,18 @@ class Engine:
         hp = lambda arr: C.c_void_p(arr.ctypes.data) if arr is not None else None
         nat.check(self.lib.arkmpc_fr_batch_mul_finish_host(sess, hp(de_peer), hp(out), hp(de_open)),
                   "arkmpc_fr_batch_mul_finish_host", self.ctx)
+
+    def host_path_bytes(self, n: int, with_open: bool = False) -> Tuple[int, int]:
+        """(host->device, device->host) bytes one party's begin + finish move for n gates."""
+        up, down = C.c_uint64(0), C.c_uint64(0)
+        self._call("arkmpc_fr_batch_mul_host_bytes", n, int(with_open), C.byref(up), C.byref(down))
+        return int(up.value), int(down.value)
+
+    def validate(self, a) -> bool:
+        """True iff every element of the plane is a canonical residue (< p)."""
+        flag = C.c_int(0)
+        self._call("arkmpc_fr_validate", self.field, a.shape[0], self._p(a), C.byref(flag))
+        return bool(flag.value)
 
     def pinned_empty(self, shape, dtype=np.uint64) -> np.ndarray:
         """Pinned host array (torch-owned pinned storage viewed as numpy)."""

@@ -72,16 +72,93 @@ class _DevArray:
 
 
 class OpenGather:
-    """Per-rank gathered planes for the opened d and e of a sharded batch_mul, plus the peer mappings of every other
-    rank's planes.  `planes()` are (world*n, 4) int64 CUDA tensors over memory owned by this object."""
+    """Per-rank gathered planes for the opened d and e of a sharded batch_mul.  `planes()` are (world*n, 4) int64 CUDA tensors
+    over memory owned by this object.  Two transports behind the same calls:
 
-    def __init__(self, engine, n_local: int, group=None):
+      * "multicast"  the planes of all ranks are bound to one NVSwitch multicast window (arkmpc_mc_*): the recombine kernel stores
+                     each opened element once and the switch replicates it into every rank's copy;
+      * "ipc"        CUDA IPC peer mappings of every other rank's planes: the kernel stores each element world times.
+
+    transport="auto" (or ARKMPC_GATHER=multicast|ipc) takes multicast when every rank supports it and the window can be built."""
+
+    def __init__(self, engine, n_local: int, group=None, transport: str = "auto"):
+        import os
+
         self.E, self.n, self.group = engine, n_local, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > 8:
             raise ValueError("OpenGather supports up to 8 ranks (one NVSwitch domain)")
-        lib, ctx = engine.lib, engine.ctx
-        self._own, self._peers = [], []
+        transport = os.environ.get("ARKMPC_GATHER", transport)
+        self._own, self._peers, self._mc = [], [], None
+        self.transport, self.fallback_reason = None, None
+        if transport in ("auto", "multicast") and self.world > 1:
+            try:
+                self._init_multicast()
+                self.transport = "multicast"
+            except _McUnavailable as e:
+                if transport == "multicast":
+                    raise
+                self.fallback_reason = str(e)
+        if self.transport is None:
+            self._init_ipc()
+            self.transport = "ipc"
+        dist.barrier(group=group)
+
+    # -- multicast window ------------------------------------------------------------------------------------------------
+    def _all_ok(self, ok: bool, why: str = "") -> None:
+        """Collective agreement: every rank proceeds, or every rank tears down and falls back."""
+        flags: List[object] = [None] * self.world
+        dist.all_gather_object(flags, (bool(ok), why), group=self.group)
+        bad = [w for o, w in flags if not o]
+        if bad:
+            self._close_mc()
+            raise _McUnavailable(bad[0] or "a rank could not build the multicast window")
+
+    def _init_multicast(self) -> None:
+        lib, ctx = self.E.lib, self.E.ctx
+        plane = self.world * self.n * 32
+        sup = C.c_int(0)
+        lib.arkmpc_mc_supported(ctx, C.byref(sup))
+        self._all_ok(bool(sup.value), "device / driver without multicast support")
+        h = C.c_void_p()
+        owner = [None]
+        ok, why = True, ""
+        if self.rank == 0:
+            rc = lib.arkmpc_mc_open(ctx, 2 * plane, self.world, 0, 0, -1, C.byref(h))
+            if rc == nat.OK:
+                pid, fd = C.c_int(0), C.c_int(0)
+                lib.arkmpc_mc_export(h, C.byref(pid), C.byref(fd))
+                owner = [(pid.value, fd.value)]
+                self._mc = h
+            else:
+                ok, why = False, (lib.arkmpc_last_error(ctx) or b"").decode()
+        dist.broadcast_object_list(owner, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        if self.rank != 0 and owner[0] is not None:
+            rc = lib.arkmpc_mc_open(ctx, 2 * plane, self.world, self.rank, owner[0][0], owner[0][1], C.byref(h))
+            if rc == nat.OK:
+                self._mc = h
+            else:
+                ok, why = False, (lib.arkmpc_last_error(ctx) or b"").decode()
+        elif self.rank != 0:
+            ok, why = False, "the owner rank could not create the multicast object"
+        self._all_ok(ok, why)  # doubles as the barrier "every device has been added"
+        loc, mc = C.c_void_p(), C.c_void_p()
+        rc = lib.arkmpc_mc_bind(self._mc, C.byref(loc), C.byref(mc))
+        self._all_ok(rc == nat.OK, (lib.arkmpc_last_error(ctx) or b"").decode() if rc != nat.OK else "")
+        self._mc_ptrs = (mc.value, mc.value + plane)
+        shape = (self.world * self.n, 4)
+        self.d_all = torch.as_tensor(_DevArray(loc.value, shape), device=self.E.tdev)
+        self.e_all = torch.as_tensor(_DevArray(loc.value + plane, shape), device=self.E.tdev)
+
+    def _close_mc(self) -> None:
+        if self._mc is not None:
+            self.E.lib.arkmpc_mc_close(self._mc)
+            self._mc = None
+
+    # -- CUDA IPC peer mappings ------------------------------------------------------------------------------------------
+    def _init_ipc(self) -> None:
+        lib, ctx = self.E.lib, self.E.ctx
+        n_local = self.n
         handles = []
         for _ in range(2):
             p = C.c_void_p()
@@ -91,7 +168,7 @@ class OpenGather:
             nat.check(lib.arkmpc_ipc_export(ctx, p, h), "arkmpc_ipc_export", ctx)
             handles.append(bytes(h))
         everyone: List[object] = [None] * self.world
-        dist.all_gather_object(everyone, handles, group=group)
+        dist.all_gather_object(everyone, handles, group=self.group)
         self._ptrs = [[None] * self.world, [None] * self.world]  # [d|e][rank]
         for r in range(self.world):
             for which in range(2):
@@ -105,9 +182,8 @@ class OpenGather:
                     self._ptrs[which][r] = q.value
         self._arr = [(C.c_void_p * self.world)(*self._ptrs[which]) for which in range(2)]
         shape = (self.world * n_local, 4)
-        self.d_all = torch.as_tensor(_DevArray(self._own[0].value, shape), device=engine.tdev)
-        self.e_all = torch.as_tensor(_DevArray(self._own[1].value, shape), device=engine.tdev)
-        dist.barrier(group=group)
+        self.d_all = torch.as_tensor(_DevArray(self._own[0].value, shape), device=self.E.tdev)
+        self.e_all = torch.as_tensor(_DevArray(self._own[1].value, shape), device=self.E.tdev)
 
     def planes(self):
         return self.d_all, self.e_all
@@ -120,9 +196,12 @@ class OpenGather:
         """Fused K2 + all-gather.  The caller synchronises (stream sync + barrier) before reading rows written by peers."""
         E = self.E
         k = E.key_limbs(key)
-        E._call("arkmpc_fr_beaver_recombine_gather", E.field, int(party), k.ctypes.data_as(C.c_void_p), self.n, E._p(d_mine), E._p(e_mine),
-                E._p(d_peer), E._p(e_peer), E._p(a[0]), E._p(a[1]), E._p(b[0]), E._p(b[1]), E._p(c[0]), E._p(c[1]), E._p(out[0]), E._p(out[1]),
-                self.world, self.rank, self._arr[0], self._arr[1])
+        common = (E.field, int(party), k.ctypes.data_as(C.c_void_p), self.n, E._p(d_mine), E._p(e_mine), E._p(d_peer), E._p(e_peer),
+                  E._p(a[0]), E._p(a[1]), E._p(b[0]), E._p(b[1]), E._p(c[0]), E._p(c[1]), E._p(out[0]), E._p(out[1]), self.world, self.rank)
+        if self.transport == "multicast":
+            E._call("arkmpc_fr_beaver_recombine_gather_mc", *common, C.c_void_p(self._mc_ptrs[0]), C.c_void_p(self._mc_ptrs[1]))
+        else:
+            E._call("arkmpc_fr_beaver_recombine_gather", *common, self._arr[0], self._arr[1])
 
     def recombine_then_nccl(self, party: int, key, d_mine, e_mine, d_peer, e_peer, a, b, c, out):
         """Baseline: K2 writes this rank's opened rows, then two NCCL all-gathers (in place on the gathered planes)."""
@@ -139,7 +218,36 @@ class OpenGather:
         self.d_all = self.e_all = None
         for q in self._peers:
             lib.arkmpc_ipc_release(ctx, q)
+        self._close_mc()
         dist.barrier(group=self.group)
         for p in self._own:
             lib.arkmpc_free(ctx, p)
         self._peers, self._own = [], []
+
+
+class _McUnavailable(RuntimeError):
+    pass
+
+
+class NativeAllGather:
+    """`arkmpc_allgather_open` — the plain NCCL all-gather behind the C ABI (what a Rust host binds): a communicator owned by the
+    native context, its id distributed here through torch.distributed (any host channel does)."""
+
+    def __init__(self, engine, group=None):
+        self.E, self.group = engine, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        ident = [None]
+        if self.rank == 0:
+            buf = (C.c_uint8 * 128)()
+            nat.check(engine.lib.arkmpc_nccl_unique_id(buf), "arkmpc_nccl_unique_id", engine.ctx)
+            ident = [bytes(buf)]
+        dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        buf = (C.c_uint8 * 128).from_buffer_copy(ident[0])
+        nat.check(engine.lib.arkmpc_nccl_init(engine.ctx, self.world, self.rank, buf), "arkmpc_nccl_init", engine.ctx)
+
+    def allgather_open(self, d_local: torch.Tensor, e_local: Optional[torch.Tensor], d_all: torch.Tensor, e_all: Optional[torch.Tensor]) -> None:
+        E = self.E
+        E._call("arkmpc_allgather_open", d_local.shape[0], E._p(d_local), E._p(e_local), E._p(d_all), E._p(e_all))
+
+    def close(self) -> None:
+        self.E.lib.arkmpc_nccl_destroy(self.E.ctx)

@@ -12,9 +12,17 @@ MockNetwork, benches/batch_ops.rs:20-40): mask(p0), mask(p1), fused recombine(p0
   roofline  the dominant kernel (fused recombine, 384 algorithmic B/gate) vs measured HBM peak
   cpu_baseline / --impl reference   the CPU restatement of the reference path (oracle/ark_oracle.c,
             kind "port": the Rust reference cannot be built here) on all host cores
+  configs   one object per BASELINE.json config, each with value / roofline / cpu_baseline:
+            [0] n = 1024 share + batch_mul + open_authenticated over Curve25519 Fr through the fabric mirror
+                (the reference bench's shape, benches/batch_ops.rs:20-40), [1] = the headline above,
+            [2] 2^20 AuthenticatedPoint scalar-muls (Curve25519), [3] inner product of length 2^22,
+            [4] 2^24 Beaver muls sharded over the N GPUs with the batch_open all-gather INSIDE the step (N > 1)
 
-N > 1: one process per GPU (torchrun), the batch is sharded by index range with NO data-path
-collective (every gate is element-wise); weak scaling, 2^log2_batch gates per GPU.
+N > 1: one process per GPU (torchrun), the batch is sharded by index range; `value` has NO data-path
+collective (every gate is element-wise; weak scaling, 2^log2_batch gates per GPU) and
+`value_with_open_gather` is the same step with party 0's opened d || e all-gathered onto every rank
+from inside the recombine kernel (NVSwitch multicast stores, or per-peer stores when multicast is
+unavailable), verified over the WHOLE gathered planes against rows recomputed from every rank's seed.
 """
 from __future__ import annotations
 
@@ -34,6 +42,7 @@ METRIC = "authenticated_beaver_mults_per_sec"
 UNIT = "mults/s"
 BYTES_RECOMBINE = 384  # K2 reads 4x32 + 3x64, writes 64
 BYTES_MASK = 192       # K1 reads 4x32, writes 2x32
+IMAD_WIDE_PER_GATE = 466  # SASS count of beaver_recombine_kernel<Bn254Fr> (tools/sass_hist.sh)
 
 
 def load_peaks():
@@ -191,28 +200,160 @@ def workload_config(args, world):
 
 def bind_to_gpu_numa_node(local_rank):
     """Multi-GPU e2e: run this rank's host threads on the CPUs of the NUMA node its GPU hangs off, so that the pinned
-    staging buffers (first touch) and the H2D/D2H traffic stay on the local socket.  Best effort; returns the node or None."""
+    staging buffers (first touch) and the H2D/D2H traffic stay on the local socket.  Best effort; returns a dict
+    describing what was found (node -1 = the platform reports no NUMA affinity for the device, e.g. a single-node VM)."""
+    info = {"node": None, "cpus_bound": None, "host_nodes": None}
     try:
         import torch
 
+        info["host_nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
         pr = torch.cuda.get_device_properties(local_rank)
         bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
         base = f"/sys/bus/pci/devices/{bus}"
-        node = int(open(f"{base}/numa_node").read().strip())
+        info["node"] = int(open(f"{base}/numa_node").read().strip())
         cpus = set()
         for part in open(f"{base}/local_cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus.update(range(int(lo), int(hi or lo) + 1))
-        if cpus:
+        if cpus and len(cpus) < (os.cpu_count() or 0):
             os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:
-        return None
+            info["cpus_bound"] = len(cpus)
+    except Exception as e:  # noqa: BLE001
+        info["error"] = repr(e)[:120]
+    return info
 
 
-def run_supplementary(args, rank, world, local_rank):
-    """configs[2] (2^20 AuthenticatedPoint scalar-muls) and configs[3] (inner product = batch_mul + Sum + open_authenticated pieces)
-    as bench lines of the same shape; one process per GPU, index-range sharding, no data-path collective."""
+class BeaverData:
+    """Synthetic two-party inputs of one shard, generated on the device: plaintext x, y, a, b uniform in
+    [0, p) from (seed, index), c = a*b, every value and its MAC split additively; one MAC key for the whole job."""
+
+    def __init__(self, E, n, seed, key_seed):
+        self.E, self.n, self.seed = E, n, seed
+        self.key0, self.key1 = (E.download(E.random(key_seed + p, 0, 1))[0].copy() for p in (0, 1))
+        self.key = E.download(E.add(E.upload(self.key0.reshape(1, 4)), E.upload(self.key1.reshape(1, 4))))[0].copy()
+        self.keys = (self.key0, self.key1)
+        key = self.key
+
+        def shared(s, val=None):
+            v = E.random(s, 0, n) if val is None else val
+            s0, m0 = E.random(s + 1, 0, n), E.random(s + 2, 0, n)
+            return v, (s0, m0), (E.sub(v, s0), E.sub(E.scale(v, key), m0))
+
+        self.xv, x0, x1 = shared(seed + 10)
+        self.yv, y0, y1 = shared(seed + 20)
+        self.av, a0, a1 = shared(seed + 30)
+        self.bv, b0, b1 = shared(seed + 40)
+        _, c0, c1 = shared(seed + 50, E.mul(self.av, self.bv))
+        self.X, self.Y, self.A, self.B, self.C = (x0, x1), (y0, y1), (a0, a1), (b0, b1), (c0, c1)
+        self.P = [dict(key=self.key0, x=x0, y=y0, a=a0, b=b0, c=c0), dict(key=self.key1, x=x1, y=y1, a=a1, b=b1, c=c1)]
+
+    @staticmethod
+    def opened_rows(E, n, seed):
+        """The opened d = x - a and e = y - b of the shard generated from `seed` (any rank can recompute any shard)."""
+        return E.sub(E.random(seed + 10, 0, n), E.random(seed + 30, 0, n)), E.sub(E.random(seed + 20, 0, n), E.random(seed + 40, 0, n))
+
+
+def shard_seed(base, rank):
+    return base + 7919 * rank
+
+
+def time_steps(step, steps, warmup, stream, world, dist, torch):
+    """`warmup` untimed + `steps` timed calls of step() on `stream`, barrier + synchronize on both sides, CUDA events,
+    max over ranks.  Returns ms per step."""
+    for _ in range(warmup):
+        step()
+    stream.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    stream.synchronize()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms
+
+
+def measure_open_gather(E, stream, D, n, rank, world, steps, warmup, base_seed, want_nccl=True):
+    """The step with north_star's one collective inside it: K1(p0) K1(p1) K2(p1) then party 0's K2 with the opened d || e
+    all-gathered onto every rank from inside the kernel (sharding.OpenGather: NVSwitch multicast stores when available, else
+    per-peer stores).  After the timed loop EVERY row of the gathered planes — the rows peers wrote included — is compared
+    with rows recomputed from the owning rank's seed."""
+    import torch
+    import torch.distributed as dist
+
+    from ark_mpc_b200 import sharding as sh
+
+    P = D.P
+    de = [(E.empty(n), E.empty(n)) for _ in range(2)]
+    out = [(E.empty(n), E.empty(n)) for _ in range(2)]
+    G = sh.OpenGather(E, n)
+    res = {"transport": G.transport, "rows_per_rank": n, "bytes_gathered_per_rank": 64 * n * world}
+
+    def masks():
+        for p in (0, 1):
+            E.beaver_mask(P[p]["x"][0], P[p]["y"][0], P[p]["a"][0], P[p]["b"][0], out=de[p])
+
+    def k2_p1():
+        E.beaver_recombine(1, P[1]["key"], de[1][0], de[1][1], de[0][0], de[0][1], P[1]["a"], P[1]["b"], P[1]["c"], out=out[1])
+
+    args0 = lambda: (0, P[0]["key"], de[0][0], de[0][1], de[1][0], de[1][1], P[0]["a"], P[0]["b"], P[0]["c"], out[0])
+
+    def step_fused():
+        masks()
+        k2_p1()
+        G.recombine_gather(*args0())
+
+    def step_nccl():
+        masks()
+        k2_p1()
+        G.recombine_then_nccl(*args0())
+
+    def verify(tag):
+        stream.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+        bad = 0
+        for r in range(world):
+            d_want, e_want = BeaverData.opened_rows(E, n, shard_seed(base_seed, r))
+            bad += int(not torch.equal(G.d_all[r * n:(r + 1) * n], d_want)) + int(not torch.equal(G.e_all[r * n:(r + 1) * n], e_want))
+        t = torch.tensor([bad], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        if int(t.item()):
+            raise SystemExit(f"open gather ({tag}): gathered planes differ from the rows recomputed from the owners' seeds")
+        G.d_all.zero_()
+        G.e_all.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    ms_f = time_steps(step_fused, steps, warmup, stream, world, dist, torch)
+    verify("fused")
+    res["ms_per_step"] = ms_f
+    res["verified"] = f"all {2 * world} gathered row blocks (2^{n.bit_length() - 1} rows each, peer-written included) equal the rows recomputed from each owner's seed, on every rank"
+    # the kernel alone: fused recombine + gather vs recombine followed by NCCL all-gather
+    ms_k = time_steps(lambda: G.recombine_gather(*args0()), max(5, min(steps, 50)), 3, stream, world, dist, torch)
+    res["fused_recombine_gather_ms"] = ms_k
+    res["recv_gbs_per_rank"] = 64 * n * (world - 1) / (ms_k * 1e-3) / 1e9
+    if want_nccl:
+        ms_n = time_steps(step_nccl, max(5, min(steps, 50)), 3, stream, world, dist, torch)
+        verify("nccl")
+        res["ms_per_step_nccl_allgather"] = ms_n
+        res["recombine_plus_nccl_allgather_ms"] = time_steps(lambda: G.recombine_then_nccl(*args0()), max(5, min(steps, 50)), 3, stream, world, dist, torch)
+    G.close()
+    return res
+
+
+def measure_supplementary(args, rank, world, local_rank, workload, log2_batch, field, steps, warmup, unfused_sum=False, cpu_baseline=True):
+    """configs[2] (AuthenticatedPoint scalar-muls) and configs[3] (inner product = batch_mul + Sum + open_authenticated pieces);
+    one process per GPU, index-range sharding.  Returns the bench object (rank 0) or None."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -220,41 +361,17 @@ def run_supplementary(args, rank, world, local_rank):
     from ark_mpc_b200 import sharding as sh
     from ark_mpc_b200.engine import Engine
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    points = args.workload == "point_mul"
-    field = args.field if not points or args.field != "bn254_fr" or "--field" in sys.argv else "curve25519_fr"
-    if points and "--log2-batch" not in sys.argv:
-        args.log2_batch = 20
-    if not points and "--log2-batch" not in sys.argv:
-        args.log2_batch = 22
-    n = 1 << args.log2_batch
-    steps = args.steps if "--steps" in sys.argv else (10 if points else 200)
-    warmup = max(3, args.warmup if "--warmup" in sys.argv else 3)
+    points = workload == "point_mul"
+    n = 1 << log2_batch
     fid = {"bn254_fr": 0, "curve25519_fr": 1}[field]
     sampler = ClockSampler(local_rank)
     sampler.start()
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         E = Engine(local_rank, field)
-        seed = 0xC0FFEE + 7919 * rank
         # one MAC key for the whole sharded batch (the same on every rank); everything else is generated per shard
-        key0, key1 = (E.download(E.random(0xC0FFEE + 900 + p, 0, 1))[0].copy() for p in (0, 1))
-        key = E.download(E.add(E.upload(key0.reshape(1, 4)), E.upload(key1.reshape(1, 4))))[0].copy()
-        keys = (key0, key1)
-
-        def shared(s, val=None):
-            v = E.random(s, 0, n) if val is None else val
-            s0, m0 = E.random(s + 1, 0, n), E.random(s + 2, 0, n)
-            return v, (s0, m0), (E.sub(v, s0), E.sub(E.scale(v, key), m0))
-
-        xv, x0, x1 = shared(seed + 10)
-        yv, y0, y1 = shared(seed + 20)
-        av, a0, a1 = shared(seed + 30)
-        bv, b0, b1 = shared(seed + 40)
-        _, c0, c1 = shared(seed + 50, E.mul(av, bv))
-        X, Y, A, B, Cc = (x0, x1), (y0, y1), (a0, a1), (b0, b1), (c0, c1)
+        D = BeaverData(E, n, shard_seed(0xC0FFEE, rank), 0xC0FFEE + 900)
+        keys, key, X, Y, A, B, Cc, xv, yv = D.keys, D.key, D.X, D.Y, D.A, D.B, D.C, D.xv, D.yv
         if points:
             # P = y*G shared in the exponent: PointShares (share*G, mac*G)
             Pt = [E.pt_mul_generator(Y[p]) for p in (0, 1)]
@@ -273,10 +390,11 @@ def run_supplementary(args, rank, world, local_rank):
             opened = E.pt_normalize(E.pt_add(outs[0], outs[1])).reshape(n, 2, 8)
             ok = torch.equal(opened[:, 0, :], E.pt_normalize(E.pt_mul_generator_public(xy))) and \
                 torch.equal(opened[:, 1, :], E.pt_normalize(E.pt_mul_generator_public(E.scale(xy, key))))
+            del xy, opened
             pw = E.point_words * 8
             alg_bytes = 2 * ((3 * 32 + 2 * pw + 32 + pw) + (2 * 32 + 2 * pw + 6 * 32 + 2 * pw))  # both parties, K1 + K2
             metric, unit = "authenticated_point_mults_per_sec", "point mults/s"
-            wl = f"2^{args.log2_batch} AuthenticatedPoint scalar-muls over {E.field_name.replace('_fr', '')} per GPU, both parties, mock net (BASELINE.json configs[2])"
+            wl = f"2^{log2_batch} AuthenticatedPoint scalar-muls over {E.field_name.replace('_fr', '')} per GPU, both parties, mock net (BASELINE.json configs[2])"
         else:
             de = [(E.empty(n), E.empty(n)) for _ in (0, 1)]
             outs = [(E.empty(n), E.empty(n)) for _ in (0, 1)]
@@ -286,7 +404,7 @@ def run_supplementary(args, rank, world, local_rank):
                 for p in (0, 1):
                     E.beaver_mask(X[p][0], Y[p][0], A[p][0], B[p][0], out=de[p])
                 for p in (0, 1):
-                    if args.unfused_sum:
+                    if unfused_sum:
                         E.beaver_recombine(p, keys[p], de[p][0], de[p][1], de[1 - p][0], de[1 - p][1], A[p], B[p], Cc[p], out=outs[p])
                         sums[p] = E.share_sum(outs[p])
                     else:  # second Beaver phase and the tree-sum in one kernel: the products are never written
@@ -303,85 +421,160 @@ def run_supplementary(args, rank, world, local_rank):
             if world > 1:
                 want = E.sum(sh.all_gather_rows(want))
             ok = torch.equal(opened, want) and E.sum_is_zero(chk[0], chk[1])
-            alg_bytes = 2 * (192 + 384 + 64) if args.unfused_sum else 2 * (192 + 320)
+            alg_bytes = 2 * (192 + 384 + 64) if unfused_sum else 2 * (192 + 320)
             metric, unit = "inner_product_elements_per_sec", "elements/s"
-            wl = f"secret-shared inner product of length-2^{args.log2_batch} vectors per GPU (batch_mul + tree-sum + open with MAC check), both parties (BASELINE.json configs[3])"
+            wl = f"secret-shared inner product of length-2^{log2_batch} vectors per GPU (batch_mul + tree-sum + open with MAC check), both parties (BASELINE.json configs[3])"
         if not ok:
-            raise SystemExit("correctness gate failed")
-        for _ in range(warmup):
-            step()
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            raise SystemExit(f"{workload}: correctness gate failed")
         sampler.wait_first()
         t_begin = time.perf_counter()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = E.launches
-        ev0.record(stream)
-        for _ in range(steps):
-            step()
-        ev1.record(stream)
-        stream.synchronize()
+        ms = time_steps(step, steps, warmup, stream, world, dist, torch)
         t_end = time.perf_counter()
-        launches = E.launches - l0
-        ms = ev0.elapsed_time(ev1) / steps
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        launches = (E.launches - l0) * steps // (steps + warmup)
         clocks = sampler.stop(t_begin, t_end)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    peak, peak_src = load_peaks()
-    achieved = alg_bytes * n / (ms * 1e-3) / 1e9
-    line = {"metric": metric, "value": n * world / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "dtype_note": "8 x u32 limbs; Montgomery for BN254, special-form 2^255-19 for Curve25519", "data": "synthetic",
-            "config": {"workload": wl, "field": field, "log2_batch_per_gpu": args.log2_batch, "parties": 2,
-                       "sharding": f"index-range x{world}, no data-path collective",
-                       "l2_hygiene": "inputs larger than L2" if n * 64 > (126 << 20) else "step touches more than L2 in total"},
-            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": ("compute-bound (INT32 multiply pipe): ~6.7k base-field multiplications per party-gate; the HBM fraction is "
-                                  "reported for completeness") if points else ("HBM-bound streaming: 640 algorithmic B per party-element" if args.unfused_sum else
-                                                                   "HBM-bound streaming: 512 algorithmic B per party-element (fused recombine + sum)")},
-            "clocks": clocks, "gpu_launches": int(launches) * world}
-    if not args.no_cpu_baseline and world == 1:
-        from oracle import coracle as co
-        from tests.util import aos
+        line = None
+        if rank == 0:
+            peak, peak_src = load_peaks()
+            achieved = alg_bytes * n / (ms * 1e-3) / 1e9
+            line = {"metric": metric, "value": n * world / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "u32", "dtype_note": "8 x u32 limbs; Montgomery for BN254, special-form 2^255-19 for Curve25519", "data": "synthetic",
+                    "config": {"workload": wl, "field": field, "log2_batch_per_gpu": log2_batch, "parties": 2,
+                               "sharding": f"index-range x{world}, no data-path collective" if points or world == 1 else
+                                           f"index-range x{world}; per step four 64-byte all-gathers of the partial ScalarShares (modular sums cannot use ncclSum)",
+                               "l2_hygiene": "inputs larger than L2" if n * 64 > (126 << 20) else "step touches more than L2 in total"},
+                    "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                 "traffic": None, "peak_source": peak_src,
+                                 "note": ("compute-bound (INT32 multiply pipe): ~6.7k base-field multiplications per party-gate; the HBM fraction is "
+                                          "reported for completeness") if points else ("HBM-bound streaming: 640 algorithmic B per party-element" if unfused_sum else
+                                                                           "HBM-bound streaming: 512 algorithmic B per party-element (fused recombine + sum)")},
+                    "clocks": clocks, "gpu_launches": int(launches) * world}
+            if cpu_baseline:
+                from oracle import coracle as co
+                from tests.util import aos
 
-        cores = os.cpu_count() or 1
-        m = min(n, 4096 if points else 1 << 18)
-        torch.cuda.synchronize()
-        cut = lambda pl: aos(E.download(pl[0][:m].contiguous()), E.download(pl[1][:m].contiguous()))
-        if points:
-            cv = fid
-            Ph = tuple(E.download(Pt[p][:m].contiguous()) for p in (0, 1))
-            ins = (keys, (cut(x0), cut(x1)), Ph, (cut(a0), cut(a1)), (cut(b0), cut(b1)), (cut(c0), cut(c1)))
-            co.two_party_point_mul(cv, cores, *ins, want_open=False)
-            t0 = time.perf_counter()
-            o0, _, _, _ = co.two_party_point_mul(cv, cores, *ins, want_open=False)
-            dt = time.perf_counter() - t0
-            with torch.cuda.stream(stream):  # the engine launches on the bench stream: download on the same one
-                got = E.download(E.pt_normalize(outs[0][:m].contiguous()))
-            same = np.array_equal(co.pt_normalize(cv, o0.reshape(2 * m, -1)), got)
-            if not same:
-                raise SystemExit("GPU result differs from the CPU oracle on the benchmark inputs")
-        else:
-            ins = (keys, (cut(x0), cut(x1)), (cut(y0), cut(y1)), (cut(a0), cut(a1)), (cut(b0), cut(b1)), (cut(c0), cut(c1)))
-            co.two_party_batch_mul(fid, cores, *ins, want_open=False)
-            t0 = time.perf_counter()
-            o0, o1, _, _ = co.two_party_batch_mul(fid, cores, *ins, want_open=False)
-            co.share_sum(fid, o0), co.share_sum(fid, o1)
-            dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": m / dt, "unit": unit, "cores": cores, "kind": "port",
-                                "sample": f"the first {m} elements of the same batch, unfused reference gate sequence (oracle/ark_oracle.c), all host threads"}
-    emit_json(line)
-    if world > 1:
-        dist.destroy_process_group()
+                cores = os.cpu_count() or 1
+                m = min(n, 4096 if points else 1 << 18)
+                torch.cuda.synchronize()
+                cut = lambda pl: aos(E.download(pl[0][:m].contiguous()), E.download(pl[1][:m].contiguous()))
+                x0, x1, y0, y1, a0, a1, b0, b1, c0, c1 = X[0], X[1], Y[0], Y[1], A[0], A[1], B[0], B[1], Cc[0], Cc[1]
+                if points:
+                    cv = fid
+                    Ph = tuple(E.download(Pt[p][:m].contiguous()) for p in (0, 1))
+                    ins = (keys, (cut(x0), cut(x1)), Ph, (cut(a0), cut(a1)), (cut(b0), cut(b1)), (cut(c0), cut(c1)))
+                    co.two_party_point_mul(cv, cores, *ins, want_open=False)
+                    t0 = time.perf_counter()
+                    o0, o1, _, _ = co.two_party_point_mul(cv, cores, *ins, want_open=False)
+                    dt = time.perf_counter() - t0
+                    # parity on the benchmark inputs: a prefix AND a strided sample over the whole batch, both parties, affine form
+                    got = [E.download(E.pt_normalize(outs[p][:m].contiguous())) for p in (0, 1)]
+                    same = all(np.array_equal(co.pt_normalize(cv, o.reshape(2 * m, -1)), g) for o, g in zip((o0, o1), got))
+                    stride = max(1, n // 512)
+                    pick = lambda pl: (pl[0][::stride].contiguous(), pl[1][::stride].contiguous())
+                    cuts = lambda pl: aos(E.download(pick(pl)[0]), E.download(pick(pl)[1]))
+                    Ps = tuple(E.download(Pt[p][::stride].contiguous()) for p in (0, 1))
+                    s0, s1, _, _ = co.two_party_point_mul(cv, cores, keys, (cuts(x0), cuts(x1)), Ps, (cuts(a0), cuts(a1)), (cuts(b0), cuts(b1)),
+                                                          (cuts(c0), cuts(c1)), want_open=False)
+                    gs = [E.download(E.pt_normalize(outs[p][::stride].contiguous())) for p in (0, 1)]
+                    same = same and all(np.array_equal(co.pt_normalize(cv, o.reshape(-1, o0.shape[-1] // 2 if o.ndim > 1 else 1).reshape(2 * gs[0].shape[0] // 2, -1)), g)
+                                        for o, g in zip((s0, s1), gs))
+                    line["parity"] = f"both parties' outputs equal the CPU oracle on the first {m} gates and on every {stride}th gate of the batch (affine form)"
+                    if not same:
+                        raise SystemExit("point_mul: GPU result differs from the CPU oracle on the benchmark inputs")
+                else:
+                    ins = (keys, (cut(x0), cut(x1)), (cut(y0), cut(y1)), (cut(a0), cut(a1)), (cut(b0), cut(b1)), (cut(c0), cut(c1)))
+                    co.two_party_batch_mul(fid, cores, *ins, want_open=False)
+                    t0 = time.perf_counter()
+                    o0, o1, _, _ = co.two_party_batch_mul(fid, cores, *ins, want_open=False)
+                    co.share_sum(fid, o0), co.share_sum(fid, o1)
+                    dt = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": m / dt, "unit": unit, "cores": cores, "kind": "port",
+                                        "sample": f"the first {m} elements of the same batch, unfused reference gate sequence (oracle/ark_oracle.c), all host threads"}
+        E.close()
+    return line
+
+
+def measure_config0(local_rank, iters=20):
+    """BASELINE.json configs[0] — the reference's own bench shape (benches/batch_ops.rs:20-40): n = 1024 random scalars over
+    Curve25519 Fr, both vectors shared by party 0, AuthenticatedScalarResult::batch_mul, open_authenticated_batch, results on the
+    host; PartyIDBeaverSource triples; in-memory mock network; the clock starts inside each party's closure and the slower
+    party counts.  GPU arm = ark_mpc_b200.fabric (launch-latency bound at this size); CPU arm = the C restatement of the same
+    gate sequence (arithmetic only)."""
+    import random
+
+    import numpy as np
+
+    from ark_mpc_b200 import fabric as fb
+    from ark_mpc_b200 import fields as fl
+
+    n, field = 1024, "curve25519_fr"
+    p = fl.MODULUS[field]
+    rng = random.Random(1024)
+    a = [rng.randrange(p) for _ in range(n)]
+    b = [rng.randrange(p) for _ in range(n)]
+    want = [x * y % p for x, y in zip(a, b)]
+    a_l, b_l = fl.mont_limbs_batch(field, a), fl.mont_limbs_batch(field, b)
+
+    def party(fabric):
+        t0 = time.perf_counter()
+        me = fabric.party_id()
+        sa = fabric.batch_share_scalar(a_l if me == 0 else n, 0)
+        sb = fabric.batch_share_scalar(b_l if me == 0 else n, 0)
+        res = fb.AuthenticatedScalarResult.batch_mul(sa, sb)
+        opened = fb.AuthenticatedScalarResult.open_authenticated_batch(res)
+        vals = opened.result().to_limbs()  # host copy = "await all"
+        return time.perf_counter() - t0, vals
+
+    times = []
+    for it in range(iters + 3):
+        (t0, v0), (t1, v1) = fb.execute_mock_mpc(party, field=field, device=local_rank)
+        if it == 0:
+            if fl.from_mont_batch(field, v0) != want:
+                raise SystemExit("configs[0]: opened products differ from a*b")
+            if not np.array_equal(v0, v1):
+                raise SystemExit("configs[0]: the parties opened different values")
+        if it >= 3:
+            times.append(max(t0, t1))
+    times.sort()
+    med = times[len(times) // 2]
+    out = {"metric": METRIC, "value": n / med, "unit": UNIT, "ms_per_iter": 1e3 * med, "iters": iters,
+           "config": {"workload": "1024-element share + AuthenticatedScalar batch_mul + open_authenticated over Curve25519 Fr, 2 parties in one process, "
+                                  "in-memory mock net, PartyIDBeaverSource (BASELINE.json configs[0]; benches/batch_ops.rs:20-40)",
+                      "field": field, "batch": n, "parties": 2},
+           "note": "host wall clock from inside each party's closure to the opened values on the host, slower party, median; at n = 1024 the "
+                   "GPU path is bound by ~25 kernel launches, 8 message hand-offs and two host SHA3 commitments per party, not by arithmetic",
+           "roofline": None}
+    # CPU arm: the same gate sequence restated in C, both parties, arithmetic only (no executor, no commitment hash)
+    from oracle import coracle as co
+    from tests.util import TwoPartyData, aos
+
+    fid = 1
+    D = TwoPartyData(fid, n, seed=1024)
+    g = lambda t: (aos(*t[0]), aos(*t[1]))
+    ins = (D.keys, g(D.x), g(D.y), g(D.a), g(D.b), g(D.c))
+    v = D.x[0][0]  # a public (n,4) plane for the input-sharing add_public
+
+    def cpu_iter():
+        for sh in (ins[1], ins[2]):  # batch_share_scalar: mask shares + add_public of the masked value, both parties
+            for pid in (0, 1):
+                co.batch_add_public(fid, pid, D.keys[pid], sh[pid], v)
+        o0, o1, _, _ = co.two_party_batch_mul(fid, 1, *ins, want_open=False)
+        opened = co.scalar_add(fid, np.ascontiguousarray(o0[:, :4]), np.ascontiguousarray(o1[:, :4]))
+        for pid, o in ((0, o0), (1, o1)):
+            co.mac_check(fid, D.keys[pid], opened, o)
+
+    cpu_iter()
+    t0 = time.perf_counter()
+    reps = 50
+    for _ in range(reps):
+        cpu_iter()
+    dt = (time.perf_counter() - t0) / reps
+    out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                           "sample": f"{reps} iterations of the same 1024-gate flow (input sharing add_public x2, unfused batch_mul, open, MAC-check vector), both "
+                                     "parties on one thread, arithmetic only: omits the reference executor, its per-element result bookkeeping and the "
+                                     "commitment hash, so it flatters the reference"}
+    return out
 
 
 _JSON_FD = None
@@ -413,14 +606,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-batch", type=int, default=20)
+    ap.add_argument("--log2-total", type=int, default=24, help="configs[4]: total gates sharded over the N GPUs (N > 1)")
     ap.add_argument("--field", default="bn254_fr", choices=["bn254_fr", "curve25519_fr"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused-sum", action="store_true", help="inner_product: separate recombine and share_sum launches (A/B)")
-    ap.add_argument("--workload", default="beaver_fr", choices=["beaver_fr", "point_mul", "inner_product"],
-                    help="beaver_fr = BASELINE.json's metric (configs[1]); point_mul = configs[2]; inner_product = configs[3] "
-                         "(supplementary lines, same JSON shape)")
+    ap.add_argument("--configs", default="all", help="'all' (default), 'none', or a comma list of 0,2,3,4: which BASELINE.json configs ride along "
+                                                     "under the `configs` key of the headline line")
+    ap.add_argument("--workload", default="beaver_fr", choices=["beaver_fr", "point_mul", "inner_product", "config0"],
+                    help="beaver_fr = BASELINE.json's metric (configs[1]) with the other configs under `configs`; point_mul = configs[2]; "
+                         "inner_product = configs[3]; config0 = configs[0] (single-config lines of the same JSON shape)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     claim_stdout()
@@ -432,8 +628,6 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if args.workload != "beaver_fr":
-        return run_supplementary(args, rank, world, local_rank)
 
     import numpy as np
     import torch
@@ -448,32 +642,41 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    def finish(line):
+        if rank == 0 and line is not None:
+            emit_json(line)
+        if world > 1:
+            dist.destroy_process_group()
+
+    given = lambda flag: flag in sys.argv
+    if args.workload in ("point_mul", "inner_product"):
+        points = args.workload == "point_mul"
+        field = args.field if not points or args.field != "bn254_fr" or given("--field") else "curve25519_fr"
+        log2 = args.log2_batch if given("--log2-batch") else (20 if points else 22)
+        steps = args.steps if given("--steps") else (10 if points else 200)
+        warmup = max(3, args.warmup if given("--warmup") else 3)
+        return finish(measure_supplementary(args, rank, world, local_rank, args.workload, log2, field, steps, warmup, args.unfused_sum,
+                                            cpu_baseline=not args.no_cpu_baseline and world == 1))
+    if args.workload == "config0":
+        return finish(measure_config0(local_rank) if rank == 0 else None)
+
+    which = {"all": {0, 2, 3, 4}, "none": set()}.get(args.configs)
+    if which is None:
+        which = {int(c) for c in args.configs.split(",") if c.strip()}
+
     fid = {"bn254_fr": 0, "curve25519_fr": 1}[args.field]
     n = 1 << args.log2_batch
     sampler = ClockSampler(local_rank)
     sampler.start()
     stream = torch.cuda.Stream()
+    open_gather = None
+    config4 = None
     with torch.cuda.stream(stream):
         E = Engine(local_rank, args.field)  # binds the current (bench) stream
-        seed = 0xA11CE + 7919 * rank
-
-        def rnd_key(s):
-            return E.download(E.random(s, 0, 1))[0].copy()
-
-        key0, key1 = rnd_key(seed + 900), rnd_key(seed + 901)
-        key = E.download(E.add(E.upload(key0.reshape(1, 4)), E.upload(key1.reshape(1, 4))))[0].copy()
-
-        def shared(s, val=None):
-            v = E.random(s, 0, n) if val is None else val
-            s0, m0 = E.random(s + 1, 0, n), E.random(s + 2, 0, n)
-            return v, (s0, m0), (E.sub(v, s0), E.sub(E.scale(v, key), m0))
-
-        xv, x0, x1 = shared(seed + 10)
-        yv, y0, y1 = shared(seed + 20)
-        av, a0, a1 = shared(seed + 30)
-        bv, b0, b1 = shared(seed + 40)
-        _, c0, c1 = shared(seed + 50, E.mul(av, bv))
-        P = [dict(key=key0, x=x0, y=y0, a=a0, b=b0, c=c0), dict(key=key1, x=x1, y=y1, a=a1, b=b1, c=c1)]
+        base_seed = 0xA11CE
+        D = BeaverData(E, n, shard_seed(base_seed, rank), shard_seed(base_seed, rank) + 900)
+        P, key, key0, key1, xv, yv = D.P, D.key, D.key0, D.key1, D.xv, D.yv
+        x0, x1, y0, y1, a0, a1, b0, b1, c0, c1 = D.X[0], D.X[1], D.Y[0], D.Y[1], D.A[0], D.A[1], D.B[0], D.B[1], D.C[0], D.C[1]
         de = [(E.empty(n), E.empty(n)) for _ in range(2)]
         out = [(E.empty(n), E.empty(n)) for _ in range(2)]
 
@@ -592,48 +795,102 @@ def main():
                 t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 e2e_ms = float(t.item())
+            h2d, d2h = E.host_path_bytes(n)
             e2e = {"value": n * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                   "h2d_bytes_per_step": 2 * (5 * 64 + 64) * n, "d2h_bytes_per_step": 2 * (64 + 64) * n,
+                   "h2d_bytes_per_step": 2 * h2d, "d2h_bytes_per_step": 2 * d2h,
+                   "h2d_gbs_aggregate": 2 * h2d * world / (e2e_ms * 1e-3) / 1e9, "d2h_gbs_aggregate": 2 * d2h * world / (e2e_ms * 1e-3) / 1e9,
                    "api": "arkmpc_fr_batch_mul_begin_host / arkmpc_fr_batch_mul_finish_host (pinned host AoS buffers, one host thread per party)",
-                   "host_numa_node": numa}
+                   "host_numa": numa}
             E1.close()
+            del host
 
-        # ---- N > 1: the batch_open all-gather (north_star's one collective), NCCL vs fused into the kernel's stores ----
-        open_allgather = None
+        # ---- N > 1: the step with the batch_open all-gather inside it (north_star's one collective) ----
         if world > 1:
-          try:
-              from ark_mpc_b200 import sharding as sh
+            try:
+                gsteps = max(20, min(args.steps, 200))
+                open_gather = measure_open_gather(E, stream, D, n, rank, world, gsteps, 5, base_seed)
+                open_gather["value_with_open_gather"] = n * world / (open_gather["ms_per_step"] * 1e-3)
+            except SystemExit:
+                raise
+            except Exception as ex:  # e.g. CUDA IPC unavailable in a restricted container: the headline numbers do not depend on it
+                open_gather = {"error": repr(ex)[:300]}
+        del de, out
 
-              G = sh.OpenGather(E, n)
-              modes = {}
-              for mode in ("nccl", "fused"):
-                  fn = G.recombine_then_nccl if mode == "nccl" else G.recombine_gather
-                  call = lambda: fn(0, P[0]["key"], de[0][0], de[0][1], de[1][0], de[1][1], P[0]["a"], P[0]["b"], P[0]["c"], out[0])
-                  for _ in range(3):
-                      call()
-                  torch.cuda.synchronize()
-                  dist.barrier()
-                  a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                  reps = max(5, min(args.steps, 50))
-                  a0.record(stream)
-                  for _ in range(reps):
-                      call()
-                  a1.record(stream)
-                  stream.synchronize()
-                  t = torch.tensor([a0.elapsed_time(a1) / reps], device="cuda", dtype=torch.float64)
-                  dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                  modes[mode] = float(t.item())
-                  dist.barrier()
-              if not (torch.equal(G.my_rows()[0], E.add(de[0][0], de[1][0]))):
-                  raise SystemExit("gathered rows differ from the local opened values")
-              gathered = 64 * n * world
-              open_allgather = {"what": "party 0's fused recombine + all-gather of the opened d||e (64 B x 2^%d rows per rank) onto every rank" % args.log2_batch,
-                                "recombine_plus_nccl_allgather_ms": modes["nccl"], "fused_recombine_gather_ms": modes["fused"],
-                                "bytes_gathered_per_rank": gathered,
-                                "fused_recv_gbs_per_rank": gathered * (world - 1) / world / (modes["fused"] * 1e-3) / 1e9}
-              G.close()
-          except Exception as ex:  # e.g. CUDA IPC unavailable in a restricted container: the headline numbers do not depend on it
-            open_allgather = {"error": repr(ex)[:300]}
+        # ---- configs[4]: 2^log2_total gates sharded over the N GPUs, gather inside the step ----
+        if world > 1 and 4 in which and args.field == "bn254_fr":
+            try:
+                n4 = (1 << args.log2_total) // world
+                if n4 == n:
+                    D4 = D
+                else:
+                    del D, P
+                    D4 = BeaverData(E, n4, shard_seed(base_seed, rank), shard_seed(base_seed, rank) + 900)
+                s4 = max(10, min(args.steps, 100))
+                g4 = measure_open_gather(E, stream, D4, n4, rank, world, s4, 3, base_seed)
+                peak, _ = load_peaks()
+                config4 = {"metric": METRIC, "value": n4 * world / (g4["ms_per_step"] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": s4, "warmup": 3,
+                           "ms_per_step": g4["ms_per_step"], "scaling": "strong",
+                           "config": {"workload": f"2^{args.log2_total} authenticated scalar Beaver muls over bn254_fr sharded over {world} GPUs "
+                                                  f"(2^{n4.bit_length() - 1} per GPU), both parties, mock net, party 0's opened d || e all-gathered onto every "
+                                                  "rank inside the step (BASELINE.json configs[4])",
+                                      "field": "bn254_fr", "log2_total": args.log2_total, "parties": 2,
+                                      "sharding": f"index-range x{world}; one all-gather per step, fused into the recombine kernel's stores"},
+                           "open_gather": g4,
+                           "roofline": {"bound": "nvlink", "kernel": "beaver_recombine_gather (party 0)", "achieved": g4["recv_gbs_per_rank"], "peak": 900.0,
+                                        "unit": "GB/s", "frac": g4["recv_gbs_per_rank"] / 900.0,
+                                        "note": "bytes received per rank (64 B x rows of the other ranks) over the fused kernel's duration vs NVLink 5's 900 GB/s per "
+                                                "direction (nominal, task statement); the compute phase of the same step is HBM-bound like configs[1]",
+                                        "step_hbm_gbs": (2 * (BYTES_MASK + BYTES_RECOMBINE) + 64) * n4 / (g4["ms_per_step"] * 1e-3) / 1e9, "hbm_peak": peak}}
+                del D4
+            except SystemExit:
+                raise
+            except Exception as ex:  # noqa: BLE001
+                config4 = {"error": repr(ex)[:300]}
+
+        cpu_line = None
+        if rank == 0 and not args.no_cpu_baseline and world == 1:
+            from oracle import coracle as co
+            from tests.util import aos
+
+            cores = os.cpu_count() or 1
+            ha = lambda pl: aos(E.download(pl[0]), E.download(pl[1]))
+            ins = ((key0, key1), (ha(x0), ha(x1)), (ha(y0), ha(y1)), (ha(a0), ha(a1)), (ha(b0), ha(b1)), (ha(c0), ha(c1)))
+            o0, _, _, _ = co.two_party_batch_mul(fid, cores, *ins, want_open=False)  # warm-up + parity check of the timed data
+            E.beaver_mask(x0[0], y0[0], a0[0], b0[0], out=(de0 := (E.empty(n), E.empty(n))))
+            E.beaver_mask(x1[0], y1[0], a1[0], b1[0], out=(de1 := (E.empty(n), E.empty(n))))
+            (gs, gm), _ = E.beaver_recombine(0, key0, de0[0], de0[1], de1[0], de1[1], a0, b0, c0)
+            if not np.array_equal(o0, aos(E.download(gs), E.download(gm))):
+                raise SystemExit("GPU result differs from the CPU oracle on the benchmark inputs")
+            t0 = time.perf_counter()
+            for _ in range(args.cpu_steps):
+                co.two_party_batch_mul(fid, cores, *ins, want_open=False)
+            dt = (time.perf_counter() - t0) / args.cpu_steps
+            t0 = time.perf_counter()
+            co.two_party_batch_mul(fid, 1, *ins, want_open=False)
+            dt1 = time.perf_counter() - t0
+            cpu_line = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"the same 2^{args.log2_batch} two-party batch, {args.cpu_steps} reps, all host threads",
+                        "single_thread_value": n / dt1}
+            del ins, o0
+        sm_count = E.sm_count
+        E.close()
+
+    # ---- the other BASELINE.json configs, each a bench object of its own under `configs` ----
+    cfgs = [None] * 5
+    cfgs[1] = {"see": "this line (headline): value, e2e, roofline, cpu_baseline"}
+    sup_cpu = not args.no_cpu_baseline and world == 1
+    if 0 in which:
+        cfgs[0] = (measure_config0(local_rank) if rank == 0 else None) if world == 1 else {"see": "the N = 1 line (a 1024-gate batch does not shard)"}
+        if world > 1:
+            dist.barrier()
+    if 2 in which:
+        cfgs[2] = measure_supplementary(args, rank, world, local_rank, "point_mul", 20, "curve25519_fr", 10, 3, cpu_baseline=sup_cpu)
+        if cfgs[2] is not None and world == 1:
+            bn = measure_supplementary(args, rank, world, local_rank, "point_mul", 20, "bn254_fr", 6, 3, cpu_baseline=False)
+            cfgs[2]["bn254_g1"] = {k: bn[k] for k in ("value", "unit", "ms_per_step", "steps")}
+    if 3 in which:
+        cfgs[3] = measure_supplementary(args, rank, world, local_rank, "inner_product", 22, "bn254_fr", 100, 3, cpu_baseline=sup_cpu)
+    cfgs[4] = config4 if config4 is not None else {"see": "needs N > 1 (SCALE lines carry it): 2^24 gates sharded over the GPUs with the open all-gather in the step"}
 
     if rank != 0:
         if world > 1:
@@ -658,36 +915,21 @@ def main():
                      "traffic_source": traffic[1] if traffic else None, "peak_source": peak_src, "kernel_us": 1e3 * k2_ms,
                      "algorithmic_bytes_per_launch": BYTES_RECOMBINE * n,
                      "modmul_equiv_per_sec": 6 * n / (k2_ms * 1e-3),
-                     # the second bound of this kernel: 501 IMAD.WIDE per gate at the measured issue rate of
+                     # the second bound of this kernel: wide multiply-adds per gate at the measured issue rate of
                      # 31.5 lanes/clk/SM (tools/pipe_bench.cu, profiles/r01a_pipe_bench.txt) at the sampled SM clock
-                     "int_pipe_floor_us": (501 * n / (31.5 * E.sm_count * (clocks.get("sm_mhz") or 1965.0) * 1e6)) * 1e6,
+                     "int_pipe_floor_us": (IMAD_WIDE_PER_GATE * n / (31.5 * sm_count * (clocks.get("sm_mhz") or 1965.0) * 1e6)) * 1e6,
                      "hbm_floor_us": BYTES_RECOMBINE * n / (peak * 1e9) * 1e6},
         "clocks": clocks, "gpu_launches": int(launches) * world,
     }
     if e2e:
         line["e2e"] = e2e
-    if open_allgather:
-        line["open_allgather"] = open_allgather
-    if not args.no_cpu_baseline and world == 1:
-        from oracle import coracle as co
-        from tests.util import aos
-
-        cores = os.cpu_count() or 1
-        ha = lambda pl: aos(E.download(pl[0]), E.download(pl[1]))
-        ins = ((key0, key1), (ha(x0), ha(x1)), (ha(y0), ha(y1)), (ha(a0), ha(a1)), (ha(b0), ha(b1)), (ha(c0), ha(c1)))
-        o0, _, _, _ = co.two_party_batch_mul(fid, cores, *ins, want_open=False)  # warm-up + parity check of the timed data
-        if not np.array_equal(o0, ha(out[0])):
-            raise SystemExit("GPU result differs from the CPU oracle on the benchmark inputs")
-        t0 = time.perf_counter()
-        for _ in range(args.cpu_steps):
-            co.two_party_batch_mul(fid, cores, *ins, want_open=False)
-        dt = (time.perf_counter() - t0) / args.cpu_steps
-        t0 = time.perf_counter()
-        co.two_party_batch_mul(fid, 1, *ins, want_open=False)
-        dt1 = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"the same 2^{args.log2_batch} two-party batch, {args.cpu_steps} reps, all host threads",
-                                "single_thread_value": n / dt1}
+    if open_gather:
+        if "value_with_open_gather" in open_gather:
+            line["value_with_open_gather"] = open_gather.pop("value_with_open_gather")
+        line["open_gather"] = open_gather
+    if cpu_line:
+        line["cpu_baseline"] = cpu_line
+    line["configs"] = cfgs
     emit_json(line)
     if world > 1:
         dist.destroy_process_group()

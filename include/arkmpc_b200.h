@@ -16,9 +16,20 @@
  *    Planes must be 32-byte aligned.  Output planes may alias input planes element-for-element.
  *  - Pointers named `*_dev`/planes are DEVICE pointers; `key` arguments are HOST pointers to 4 u64
  *    (Montgomery image of the party's MAC-key share, `MpcFabric::mac_key()`); `*_host` are host buffers.
- *  - All work is enqueued on the context's stream and is asynchronous unless stated; a context is
- *    bound to one device and may be used from any one thread at a time (two parties in one process
- *    use two contexts, mirroring execute_mock_mpc, online-phase/src/lib.rs:157-201).
+ *  - All work is enqueued on the context's stream and is asynchronous unless stated.  A context is bound to
+ *    one device and is THREAD-SAFE: any number of threads may call into the same context concurrently
+ *    (the reference runs gate closures on its executor thread or on arbitrary rayon workers,
+ *    fabric/executor/multi_threaded/executor.rs:208-217, and clones result handles across tokio tasks,
+ *    fabric/result.rs:262-266).  Each call holds the context's lock while it enqueues; everything goes to
+ *    the one context stream, so work runs on the GPU in the order the calls RETURN — a gate scheduled after
+ *    its inputs' calls have returned (on whatever threads) sees their results, with no event to manage.
+ *    The calling thread's current CUDA device is restored before a call returns.  arkmpc_last_error is
+ *    per thread.  Two parties in one process use two contexts, mirroring execute_mock_mpc
+ *    (online-phase/src/lib.rs:157-201).
+ *  - Values received from the PEER (d_peer / e_peer, peer MAC-check shares, E_peer points) must already be
+ *    valid: canonical field elements (< p) and on-curve, prime-order-subgroup points.  The reference gets
+ *    this from arkworks' validating deserialisation (scalar.rs:187-202, curve.rs:105-135); a shim passes
+ *    only deserialised values, or checks a buffer with arkmpc_fr_validate / arkmpc_pt_validate first.
  *  - n == 0 is a no-op returning ARKMPC_OK (the reference returns empty vectors,
  *    authenticated_scalar.rs:854-856).  Length mismatches cannot occur: one n per call.
  */
@@ -32,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ARKMPC_ABI_VERSION 1
+#define ARKMPC_ABI_VERSION 2
 
 typedef enum arkmpc_status {
   ARKMPC_OK = 0,
@@ -154,6 +165,9 @@ int arkmpc_fr_mac_check(arkmpc_ctx* ctx, int field, const uint64_t* key_host, si
                         const uint64_t* opened, const uint64_t* mac, uint64_t* check);
 /* *all_zero_host = 1 iff mine[i] + peer[i] == 0 for every i  (:217-219).  Synchronous. */
 int arkmpc_fr_sum_is_zero(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* mine, const uint64_t* peer, int* all_zero_host);
+/* *all_canonical_host = 1 iff a[i] < p for every i: the check arkworks' deserialisation applies to values that arrive from
+ * the peer (scalar.rs:187-202) before they may be used as d_peer / e_peer / peer check shares.  Synchronous. */
+int arkmpc_fr_validate(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, int* all_canonical_host);
 /* canonical big-endian 32-byte encoding of each element for the hash commitment (scalar.rs:118-127) */
 int arkmpc_fr_to_bytes_be(arkmpc_ctx* ctx, int field, size_t n, const uint64_t* a, uint8_t* out_dev);
 
@@ -204,6 +218,49 @@ int arkmpc_fr_beaver_recombine_gather(arkmpc_ctx* ctx, int field, int party_id, 
                                       int world, int rank,
                                       uint64_t* const* gather_d /* [world] base of rank k's (world*n)-scalar plane */,
                                       uint64_t* const* gather_e);
+
+/* The same gather with NVSwitch MULTICAST stores: the gathered planes of all ranks live in one multicast window, and each
+ * opened element leaves the GPU once (multimem.st); the switch replicates it into every rank's copy (this rank's included).
+ * Window life cycle (collective over the ranks of one NVSwitch domain; the host provides the barriers):
+ *   1. rank 0: arkmpc_mc_open(owner_pid = 0) creates the multicast object; arkmpc_mc_export gives (pid, fd);
+ *      the host hands both integers to the other ranks (any channel), which call arkmpc_mc_open(owner_pid, owner_fd) —
+ *      the descriptor is duplicated with pidfd_getfd; owner_pid < 0 means owner_fd is already a descriptor of this process.
+ *   2. barrier; every rank: arkmpc_mc_bind -> local_ptr (this rank's copy, ordinary device memory) and multicast_ptr
+ *      (stores through it land in EVERY rank's copy at the same offset).  barrier.
+ *   3. use: arkmpc_fr_beaver_recombine_gather_mc / arkmpc_mc_allgather_rows with pointers derived from multicast_ptr; read
+ *      the gathered rows through local_ptr after a stream sync + barrier.
+ *   4. stream sync + barrier; arkmpc_mc_close.
+ * ARKMPC_ERR_UNSUPPORTED (and *supported = 0) when the device or driver has no multicast support: fall back to
+ * arkmpc_fr_beaver_recombine_gather or arkmpc_allgather_open. */
+typedef struct arkmpc_mc arkmpc_mc;
+int arkmpc_mc_supported(arkmpc_ctx* ctx, int* supported);
+int arkmpc_mc_open(arkmpc_ctx* ctx, size_t bytes, int world, int rank, int owner_pid, int owner_fd, arkmpc_mc** out);
+int arkmpc_mc_export(arkmpc_mc* window, int* pid, int* fd);
+int arkmpc_mc_bind(arkmpc_mc* window, void** local_ptr, void** multicast_ptr);
+int arkmpc_mc_close(arkmpc_mc* window);
+int arkmpc_fr_beaver_recombine_gather_mc(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                                         const uint64_t* d_mine, const uint64_t* e_mine,
+                                         const uint64_t* d_peer, const uint64_t* e_peer,
+                                         const uint64_t* a_share, const uint64_t* a_mac,
+                                         const uint64_t* b_share, const uint64_t* b_mac,
+                                         const uint64_t* c_share, const uint64_t* c_mac,
+                                         uint64_t* out_share, uint64_t* out_mac, int world, int rank,
+                                         uint64_t* gather_d_multicast /* multicast address of the (world*n)-scalar d plane */,
+                                         uint64_t* gather_e_multicast);
+/* rows [rank*n, (rank+1)*n) of every rank's gathered plane <- local_rows (no arithmetic) */
+int arkmpc_mc_allgather_rows(arkmpc_ctx* ctx, size_t n, int rank, const uint64_t* local_rows, uint64_t* gathered_multicast);
+
+/* The plain collective (SURVEY §8b `arkmpc_allgather_open`): ncclAllGather of this rank's opened d and e rows into the
+ * gathered planes of every rank, on the context's stream.  NCCL (libnccl.so.2) is resolved at run time; rank 0 obtains an id
+ * with arkmpc_nccl_unique_id, the host distributes its ARKMPC_NCCL_ID_BYTES bytes, every rank calls arkmpc_nccl_init
+ * (collective).  e_local / e_all may both be NULL to gather one plane.  ARKMPC_ERR_UNSUPPORTED if NCCL cannot be loaded,
+ * ARKMPC_ERR_NCCL if a NCCL call fails. */
+#define ARKMPC_NCCL_ID_BYTES 128
+int arkmpc_nccl_unique_id(uint8_t* id_out /* ARKMPC_NCCL_ID_BYTES */);
+int arkmpc_nccl_init(arkmpc_ctx* ctx, int world, int rank, const uint8_t* id);
+int arkmpc_nccl_destroy(arkmpc_ctx* ctx);
+int arkmpc_allgather_open(arkmpc_ctx* ctx, size_t n_local, const uint64_t* d_local, const uint64_t* e_local,
+                          uint64_t* d_all, uint64_t* e_all);
 
 /* ---- point gates (algebra/curve/authenticated_curve.rs, curve/share.rs, curve/curve.rs) ----
  * Points are DEVICE arrays in the reference's AoS memory image: BN254 `G1Projective` {x,y,z} = 96 B (Jacobian,
@@ -284,6 +341,11 @@ int arkmpc_fr_batch_mul_begin_host(arkmpc_ctx* ctx, int field, int party_id, con
 int arkmpc_fr_batch_mul_finish_host(arkmpc_batch_mul* session, const uint64_t* de_peer_host, uint64_t* out_host,
                                     uint64_t* de_open_host);
 int arkmpc_fr_batch_mul_abort(arkmpc_batch_mul* session);
+/* Bytes one party's begin + finish move over PCIe for n gates (x.share, y.share, a, b, c, the peer's d || e up; own d || e,
+ * the result shares and, with_open, the opened d || e down).  begin reads the 32-byte share halves of x and y straight from
+ * the caller's buffers when they are pinned (arkmpc_host_alloc / cudaHostRegister): the MAC halves never cross the link.
+ * A failed begin leaves no session (*session = NULL); finish consumes the session whether it succeeds or not. */
+int arkmpc_fr_batch_mul_host_bytes(arkmpc_ctx* ctx, size_t n, int with_open, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
 #ifdef __cplusplus
 }

@@ -4,7 +4,17 @@
 // Test infrastructure; not part of the product library.
 #include <cstring>
 #include "../../ark_mpc_b200/csrc/beaver.cuh"
+#include "../../ark_mpc_b200/csrc/ctab.hpp"
 using namespace ark;
+
+// constant-multiplier table from an 8 x u32 value, through the product's own host builder (ctab.hpp)
+template <class F> static CTab tab_of(const fe8& s) {
+  uint64_t h[4];
+  for (int j = 0; j < 4; j++) h[j] = (uint64_t)s.v[2 * j] | ((uint64_t)s.v[2 * j + 1] << 32);
+  CTab t;
+  ctab_build<F>(t, h);
+  return t;
+}
 
 template <class F> static void run(int op, const uint32_t* in, uint32_t* out, int party) {
   const fe8* v = reinterpret_cast<const fe8*>(in);
@@ -19,14 +29,17 @@ template <class F> static void run(int op, const uint32_t* in, uint32_t* out, in
     case 6: beaver_mask_elem<F>(o[0], o[1], v[0], v[1], v[2], v[3]); break;
     case 7: if constexpr (F::kLazy2) {
       // in: key, d_mine, e_mine, d_peer, e_peer, a_s, a_m, b_s, b_m, c_s, c_m ; out: out_s, out_m, d, e
-      beaver_recombine_elem<F>(o[0], o[1], o[2], o[3], party, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10]);
+      beaver_recombine_elem<F>(o[0], o[1], o[2], o[3], party, tab_of<F>(v[0]), v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10]);
     } break;
-    case 8: share_add_public_elem<F>(o[0], o[1], party, v[0], v[1], v[2], v[3]); break;
-    case 9: share_sub_public_elem<F>(o[0], o[1], party, v[0], v[1], v[2], v[3]); break;
-    case 10: mac_check_elem<F>(o[0], v[0], v[1], v[2]); break;
+    case 8: if constexpr (F::kBits <= 254) { share_add_public_elem<F>(o[0], o[1], party, tab_of<F>(v[0]), v[1], v[2], v[3]); } break;
+    case 9: if constexpr (F::kBits <= 254) { share_sub_public_elem<F>(o[0], o[1], party, tab_of<F>(v[0]), v[1], v[2], v[3]); } break;
+    case 10: if constexpr (F::kBits <= 254) { mac_check_elem<F>(o[0], tab_of<F>(v[0]), v[1], v[2]); } break;
     case 11: o[0] = v[0]; Fp<F>::csub_p(o[0]); break;
     case 12: Fp<F>::set_one(o[0]); Fp<F>::set_r2(o[1]); break;
     case 13: Fp<F>::sqr(o[0], v[0]); break;
+    case 14: if constexpr (F::kBits <= 254) { Fp<F>::mul_ctab_lazy(o[0], tab_of<F>(v[0]), v[1]); } break;  // lazy: s * a / R, any 256-bit a
+    case 15: if constexpr (F::kBits <= 254) { Fp<F>::mul_ctab(o[0], tab_of<F>(v[0]), v[1]); } break;
+    case 16: if constexpr (F::kBits <= 254) { CTab t = tab_of<F>(v[0]); memcpy(o, &t, sizeof t); } break;       // the table itself (8 elements)
   }
 }
 

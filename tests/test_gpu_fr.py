@@ -34,7 +34,7 @@ def dn(E, t):
 def test_native_library_is_loaded(engines, fid):
     import ark_mpc_b200._native as nat
 
-    assert nat.load().arkmpc_abi_version() == 1
+    assert nat.load().arkmpc_abi_version() == 2
     with open("/proc/self/maps") as f:
         assert "libarkmpc_b200.so" in f.read()
     assert engines[fid].sm_count >= 100
@@ -283,3 +283,69 @@ def test_multi_gpu_open_gather():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("multi-GPU open gather OK") == min(n_dev, 8)
+
+
+import torch  # noqa: E402
+import ark_mpc_b200._native as nat  # noqa: E402
+from ark_mpc_b200.engine import Engine  # noqa: E402
+
+
+def test_native_allgather_single_rank():
+    """arkmpc_nccl_unique_id / arkmpc_nccl_init / arkmpc_allgather_open on a world of one: NCCL is resolved at run
+    time behind the C ABI and the gathered planes equal the local rows (the multi-rank form is covered by multi_gpu_check.py)."""
+    import ctypes as C
+
+    E = Engine(0, "bn254_fr")
+    n = 3001
+    d, e = E.random(1, 0, n), E.random(2, 0, n)
+    ident = (C.c_uint8 * 128)()
+    nat.check(E.lib.arkmpc_nccl_unique_id(ident), "arkmpc_nccl_unique_id", E.ctx)
+    nat.check(E.lib.arkmpc_nccl_init(E.ctx, 1, 0, ident), "arkmpc_nccl_init", E.ctx)
+    d_all, e_all = torch.zeros_like(d), torch.zeros_like(e)
+    E._call("arkmpc_allgather_open", n, E._p(d), E._p(e), E._p(d_all), E._p(e_all))
+    E.sync()
+    assert torch.equal(d_all, d) and torch.equal(e_all, e)
+    with pytest.raises(nat.ArkMpcError):  # a second communicator on the same context is refused
+        nat.check(E.lib.arkmpc_nccl_init(E.ctx, 1, 0, ident), "arkmpc_nccl_init", E.ctx)
+    nat.check(E.lib.arkmpc_nccl_destroy(E.ctx), "arkmpc_nccl_destroy", E.ctx)
+    with pytest.raises(nat.ArkMpcError):  # no communicator any more
+        E._call("arkmpc_allgather_open", n, E._p(d), E._p(e), E._p(d_all), E._p(e_all))
+    E.close()
+
+
+@pytest.mark.parametrize("field", ["bn254_fr", "curve25519_fr"])
+def test_validate_rejects_non_canonical_peer_values(field):
+    """arkmpc_fr_validate: what arkworks' deserialisation enforces on values from the peer (scalar.rs:187-202)."""
+    from ark_mpc_b200 import fields as fl
+
+    E = Engine(0, field)
+    n = 5000
+    a = E.random(9, 0, n)
+    assert E.validate(a)
+    p = fl.MODULUS[field]
+    for bad in (p, p + 1, (1 << 256) - 1):
+        b = a.clone()
+        b[n - 7] = torch.from_numpy(fl.int_to_limbs(bad).view(np.int64))
+        assert not E.validate(b)
+    b = a.clone()
+    b[0] = torch.from_numpy(fl.int_to_limbs(p - 1).view(np.int64))
+    assert E.validate(b)
+    assert E.validate(E.empty(0))
+    E.close()
+
+
+def test_engine_follows_torch_current_stream():
+    """an Engine built outside a `with torch.cuda.stream(...)` block and used inside one must run on that stream."""
+    E = Engine(0, "bn254_fr")
+    s = torch.cuda.Stream()
+    n = 1 << 16
+    with torch.cuda.stream(s):
+        a, b = E.random(1, 0, n), E.random(2, 0, n)
+        assert int(E.lib.arkmpc_ctx_get_stream(E.ctx) or 0) == s.cuda_stream
+        c = E.mul(a, b)
+    s.synchronize()
+    c2 = E.mul(a, b)  # back on the default stream
+    assert int(E.lib.arkmpc_ctx_get_stream(E.ctx) or 0) == torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    assert torch.equal(c, c2)
+    E.close()

@@ -25,6 +25,40 @@ def build():
     return EXE
 
 
+TSRC = os.path.join(ROOT, "tests", "host_cpp", "test_threads.cpp")
+TEXE = os.path.join(ROOT, "tests", "host_cpp", "test_threads")
+
+
+def build_threads():
+    from ark_mpc_b200.build import build_native
+    from oracle import coracle
+
+    build_native()
+    coracle.build()
+    deps = [TSRC, os.path.join(ROOT, "include", "arkmpc_b200.h")]
+    if not os.path.exists(TEXE) or any(os.path.getmtime(d) > os.path.getmtime(TEXE) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), TSRC, "-o", TEXE,
+                               "-L", os.path.join(ROOT, "ark_mpc_b200", "lib"), "-larkmpc_b200", "-L", os.path.join(ROOT, "oracle"),
+                               "-lark_oracle", "-lpthread", "-Wl,-rpath," + os.path.join(ROOT, "ark_mpc_b200", "lib"),
+                               "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return TEXE
+
+
+def test_thread_test_builds_and_refuses_to_run_without_a_gpu(has_gpu):
+    exe = build_threads()
+    if not has_gpu:
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 2 and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_one_context_driven_from_four_threads():
+    """per-context thread safety (executor workers call gate closures concurrently)."""
+    r = subprocess.run([build_threads(), "4", "6"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "thread-safety test OK" in r.stdout
+
+
 def test_host_mirror_compiles_against_the_c_abi_only():
     exe = build()
     # no CUDA or torch headers are needed by the host mirror: only include/arkmpc_b200.h

@@ -163,3 +163,26 @@ def test_dedicated_square(emu, name, fid):
             int("ffffffff" * 7 + "00000000", 16) % F.p, int("80000000" * 8, 16) % F.p]
     for a in samples(F, rng, 300) + hard:
         assert emu(fid, 13, [a], 1)[0] == a * a * F.rinv % F.p
+
+
+@pytest.mark.parametrize("name,fid", LAZY)
+def test_constant_multiplier_table(emu, name, fid):
+    """ctab.hpp builds k[i] = s*2^(32i-160) (i<4) / s*2^(32i-192) (i>=4) mod p; Fp::mul_ctab_lazy(T, a) == s*a/R mod p with
+    the result < p + 5p/2^32 for ANY 256-bit a (three reduction steps instead of eight); mul_ctab is canonical."""
+    F = po.FIELDS[name]
+    rng = random.Random(50 + fid)
+    inv2 = pow(2, -1, F.p)
+    keys = [0, 1, F.p - 1, F.p - 2, F.r, F.r2, (F.p - 1) // 2] + [rng.randrange(F.p) for _ in range(40)]
+    for s in keys:
+        tab = emu(fid, 16, [s], 8)
+        for i in range(8):
+            e = 32 * i - 160 if i < 4 else 32 * i - 192
+            want = s * (pow(2, e, F.p) if e >= 0 else pow(inv2, -e, F.p)) % F.p
+            assert tab[i] == want
+        xs = [0, 1, F.p - 1, (1 << 256) - 1, int("ffffffff00000000" * 4, 16), int("00000000ffffffff" * 4, 16), 3 * F.p % (1 << 256)]
+        xs += [rng.randrange(1 << 256) for _ in range(6)] + [rng.randrange(F.p) for _ in range(6)]
+        for a in xs:
+            r = emu(fid, 14, [s, a], 1)[0]
+            assert r % F.p == s * a * F.rinv % F.p
+            assert r < F.p + (5 * F.p >> 32) + 1
+            assert emu(fid, 15, [s, a], 1)[0] == s * a * F.rinv % F.p

@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I include -o tools/_k2v tools/_k2v.cu
 #include <cstdio>
 #include <vector>
+#include "../ark_mpc_b200/csrc/ctab.hpp"
 #include "../ark_mpc_b200/csrc/fr_kernels.cuh"
 using namespace ark;
 template <class F, int PARTY, int BLK, int MINB>
@@ -46,8 +47,8 @@ int main() {
   g.d_mine = Vec{buf[0], 32}; g.e_mine = Vec{buf[1], 32}; g.d_peer = Vec{buf[2], 32}; g.e_peer = Vec{buf[3], 32};
   g.a_s = Vec{buf[4], 32}; g.a_m = Vec{buf[5], 32}; g.b_s = Vec{buf[6], 32}; g.b_m = Vec{buf[7], 32}; g.c_s = Vec{buf[8], 32}; g.c_m = Vec{buf[9], 32};
   g.out_s = MVec{buf[10], 32}; g.out_m = MVec{buf[11], 32}; g.d_open = MVec{nullptr, 32}; g.e_open = MVec{nullptr, 32};
-  for (int j = 0; j < 8; j++) g.key.v[j] = 0x1234567u * (j + 1);
-  g.key.v[7] &= 0x0fffffffu;
+  const uint64_t key[4] = {0x123456789abcdef1ull, 0x0fedcba987654321ull, 0x1122334455667788ull, 0x0123456789abcdefull};
+  ctab_build<Bn254Fr>(g.key, key);
   uint64_t s;
   for (int rep = 0; rep < 2; rep++) {
     run<Bn254Fr, 256, 3>("occ3 full grid (current)", n, g, sms, 1 << 20, &s);
