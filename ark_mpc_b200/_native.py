@@ -39,6 +39,7 @@ _PROTOS = {
     "arkmpc_ctx_destroy": [_vp],
     "arkmpc_ctx_set_stream": [_vp, _vp],
     "arkmpc_ctx_reset_stream": [_vp],
+    "arkmpc_ctx_hint_independent": [_vp],
     "arkmpc_ctx_get_stream": [_vp],
     "arkmpc_ctx_device": [_vp],
     "arkmpc_ctx_sync": [_vp],

@@ -31,7 +31,7 @@ void launch_pdl(const arkmpc_ctx* ctx, void (*kern)(KArgs...), unsigned grid, cu
 // ---- launch helpers shared by the device-pointer ABI and the host-buffer path ----
 template <class F>
 int launch_mask(arkmpc_ctx* ctx, cudaStream_t s, size_t n, Vec x, Vec y, Vec a, Vec b, MVec d, MVec e) {
-  launch_pdl(ctx, beaver_mask_kernel<F>, grid_stream(ctx, n, 8), s, n, x, y, a, b, d, e);
+  launch_pdl(ctx, beaver_mask_kernel<F>, grid_stream(ctx, n, 8), s, n, x, y, a, b, d, e, take_hint(ctx));
   return post_launch(ctx, "beaver_mask_kernel");
 }
 
@@ -64,7 +64,8 @@ inline bool recombine_is_planar(const RecombineArgs& g, bool open) {
 // (536 IMAD.WIDE at ~4 issue cycles + ~320 other instructions per gate), not by memory latency, so TMA staging buys
 // nothing (88.4 us vs 84.5 us per 2^20 gates); ARKMPC_RECOMBINE=tma selects the staged kernel for planar operands.
 template <class F>
-int launch_recombine(arkmpc_ctx* ctx, cudaStream_t s, int party, size_t n, const RecombineArgs& g, bool open) {
+int launch_recombine(arkmpc_ctx* ctx, cudaStream_t s, int party, size_t n, RecombineArgs g, bool open) {
+  g.independent = take_hint(ctx);
   if (ctx->use_tma && recombine_is_planar(g, open)) {
     if (party == 0) return open ? launch_recombine_tma<F, 0, true>(ctx, s, n, g) : launch_recombine_tma<F, 0, false>(ctx, s, n, g);
     return open ? launch_recombine_tma<F, 1, true>(ctx, s, n, g) : launch_recombine_tma<F, 1, false>(ctx, s, n, g);
@@ -153,6 +154,10 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
     if (pd && strcmp(pd, "0") == 0) ctx->pdl = false;
     const char* gm = getenv("ARKMPC_GRID");
     if (gm && strcmp(gm, "persistent") == 0) ctx->full_grids = false;
+    // Default: copy the whole AoS images.  Measured on B200 / PCIe 5 (tools/_zc.cu, profiles/r02b_zero_copy.txt): device reads of
+    // pinned host memory move whole 64-byte blocks, so fetching only the 32-byte share halves at stride 64 takes exactly as long
+    // as reading everything (25.5 GB/s useful = 51 GB/s on the wire), and a strided DMA copy is slower still (22 GB/s useful).
+    ctx->xy_mode = 0;
     const char* xy = getenv("ARKMPC_XY");
     if (xy && strcmp(xy, "flat") == 0) ctx->xy_mode = 0;
     if (xy && strcmp(xy, "2d") == 0) ctx->xy_mode = 1;
@@ -189,6 +194,12 @@ int arkmpc_ctx_set_stream(arkmpc_ctx* ctx, void* cuda_stream) {
   if (!ctx) return ARKMPC_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  return ARKMPC_OK;
+}
+int arkmpc_ctx_hint_independent(arkmpc_ctx* ctx) {
+  if (!ctx) return ARKMPC_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  ctx->hint_independent = true;
   return ARKMPC_OK;
 }
 int arkmpc_ctx_reset_stream(arkmpc_ctx* ctx) {
@@ -365,6 +376,7 @@ int arkmpc_fr_beaver_recombine_gather(arkmpc_ctx* ctx, int field, int party_id, 
   const unsigned grid = full_grid(n);
   ARK_FIELD_SWITCH(ctx, field, {
     g.key = host_ctab<F>(key_host);
+    g.independent = take_hint(ctx);
     if (party_id == 0) launch_pdl(ctx, beaver_recombine_gather_kernel<F, 0>, grid, ctx->stream, n, g, q);
     else launch_pdl(ctx, beaver_recombine_gather_kernel<F, 1>, grid, ctx->stream, n, g, q);
   });
@@ -598,6 +610,7 @@ int arkmpc_fr_beaver_recombine_sum(arkmpc_ctx* ctx, int field, int party_id, con
   char* part_m = part + warps * 32;
   ARK_FIELD_SWITCH(ctx, field, {
     g.key = host_ctab<F>(key_host);
+    g.independent = take_hint(ctx);
     if (party_id == 0) launch_pdl(ctx, beaver_recombine_sum_kernel<F, 0>, grid, s, n, g, mvec(part), mvec(part_m));
     else launch_pdl(ctx, beaver_recombine_sum_kernel<F, 1>, grid, s, n, g, mvec(part), mvec(part_m));
   });

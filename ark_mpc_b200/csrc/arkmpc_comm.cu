@@ -292,6 +292,7 @@ int arkmpc_fr_beaver_recombine_gather_mc(arkmpc_ctx* ctx, int field, int party_i
   cfg.numAttrs = ctx->pdl ? 1 : 0;
   ARK_FIELD_SWITCH(ctx, field, {
     g.key = host_ctab<F>(key_host);
+    g.independent = take_hint(ctx);
     if (party_id == 0) cudaLaunchKernelEx(&cfg, beaver_recombine_gather_mc_kernel<F, 0>, n, g, q);
     else cudaLaunchKernelEx(&cfg, beaver_recombine_gather_mc_kernel<F, 1>, n, g, q);
   });

@@ -44,6 +44,7 @@ struct arkmpc_ctx {
   int* flag_dev = nullptr;
   int* flag_host = nullptr;  // pinned
   bool use_tma = false;      // ARKMPC_RECOMBINE=tma
+  bool hint_independent = false;  // arkmpc_ctx_hint_independent: consumed by the next Beaver kernel launch
   bool pdl = true;           // Beaver K1/K2 launched with programmatic stream serialization (ARKMPC_PDL=0 disables)
   bool full_grids = true;    // element-wise kernels: one element per thread instead of a persistent wave (ARKMPC_GRID=persistent reverts)
   int xy_mode = 2;           // host-buffer path, how x.share / y.share reach the mask kernel: 0 flat AoS copy, 1 strided DMA copy, 2 zero-copy reads of pinned memory (ARKMPC_XY=flat|2d|zc)
@@ -133,6 +134,13 @@ inline unsigned grid_stream(const arkmpc_ctx* ctx, size_t n, int blocks_per_sm, 
   if (!ctx->full_grids) return grid_for(ctx, n, blocks_per_sm, block);
   size_t need = (n + block - 1) / block;
   return (unsigned)(need < (1u << 30) ? (need ? need : 1) : (1u << 30));
+}
+
+// consume the independence hint (one launch)
+inline int take_hint(arkmpc_ctx* ctx) {
+  const bool h = ctx->hint_independent && ctx->pdl;
+  ctx->hint_independent = false;
+  return h ? 1 : 0;
 }
 
 inline int post_launch(arkmpc_ctx* ctx, const char* what) {

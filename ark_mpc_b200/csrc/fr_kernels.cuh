@@ -39,20 +39,31 @@ __device__ __forceinline__ void st_fe(const MVec& v, size_t i, const fe8& r) {
 constexpr int kBlock = 256;
 
 // Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
-// scheduled while its predecessor in the stream drains.  `pdl_prologue()` first lets OUR successor do the same, then waits until
-// every predecessor grid has completed and its writes are visible; nothing before it touches global memory.  Launched normally
+// scheduled while its predecessor in the stream drains.  `pdl_prologue()` waits until every predecessor grid has completed and
+// its writes are visible (nothing before it touches global memory), then lets OUR successor be scheduled.  Launched normally
 // (<<<>>>), both instructions are no-ops.  Measured on the 4-kernel Beaver step: 213-221 -> 207-210 us (tools/_pdl.cu).
-__device__ __forceinline__ void pdl_prologue() {
+//
+// `independent` (arkmpc_ctx_hint_independent): the host states that this launch is independent of the launches before it back
+// to the most recent un-hinted one (it neither reads nor overwrites what they write or read — e.g. the other party's
+// recombine in a mock run, or a gate on other operands).  The wait moves from the first instruction to the LAST: the grid's
+// loads and arithmetic overlap the predecessor's drain — drain plus ramp-up cost ~8 us of a 70 us recombine launch otherwise
+// (tools/_k2t.cu, profiles/r02b_k2_timeline.txt) — and the wait before exit keeps completion transitive: a later launch that
+// waits on this grid also waits on everything before it.  An un-hinted launch triggers its successors only after its own
+// wait has returned, so a hinted successor never runs ahead of work that is older than its group.
+__device__ __forceinline__ void pdl_prologue(bool independent = false) {
+  if (!independent) asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_epilogue(bool independent) {
+  if (independent) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
 // Beaver phase 1: d_mine = x - a, e_mine = y - b on the share components.   192 B / gate.
 // ---------------------------------------------------------------------------------------------
 template <class F>
-__global__ void __launch_bounds__(kBlock) beaver_mask_kernel(size_t n, Vec x, Vec y, Vec a, Vec b, MVec d, MVec e) {
-  pdl_prologue();
+__global__ void __launch_bounds__(kBlock) beaver_mask_kernel(size_t n, Vec x, Vec y, Vec a, Vec b, MVec d, MVec e, int independent) {
+  pdl_prologue(independent != 0);
   const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
     fe8 xs, ys, as, bs, dm, em;
@@ -64,6 +75,7 @@ __global__ void __launch_bounds__(kBlock) beaver_mask_kernel(size_t n, Vec x, Ve
     st_fe(d, i, dm);
     st_fe(e, i, em);
   }
+  pdl_epilogue(independent != 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -74,6 +86,7 @@ struct RecombineArgs {
   Vec a_s, a_m, b_s, b_m, c_s, c_m;
   MVec out_s, out_m, d_open, e_open;
   CTab key;  // constant-multiplier table of this party's MAC key share (ctab.hpp)
+  int independent;  // see pdl_prologue
 };
 
 // Launch shape (measured on B200, tools/_k2v.cu, profiles/r01d_k2_launch_shapes.txt): the kernel is bound by the IMAD.WIDE
@@ -81,11 +94,13 @@ struct RecombineArgs {
 // wave) with 3 resident blocks of 256 (78 registers) is 10 % faster than 2 persistent blocks per SM: 74.9 vs 82.7 us.
 constexpr int kRecombineMinBlocks = 3;
 
+// One gate per thread, no grid-stride loop: the launch covers n (gridDim.x < 2^31), and the straight-line body is 2.5 % faster
+// than the same body inside a loop (tools/_k2t.cu vs tools/_k2v.cu).
 template <class F, int PARTY, bool OPEN>
 __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_kernel(size_t n, const __grid_constant__ RecombineArgs g) {
-  pdl_prologue();
-  const size_t step = (size_t)gridDim.x * kBlock;
-  for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
+  pdl_prologue(g.independent != 0);
+  const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) {
     fe8 dm, em, dp, ep, as, am, bs, bm, cs, cm;
     ld_fe(dm, g.d_mine, i);
     ld_fe(dp, g.d_peer, i);
@@ -106,6 +121,7 @@ __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_
       st_fe(g.e_open, i, e);
     }
   }
+  pdl_epilogue(g.independent != 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -124,7 +140,7 @@ struct GatherArgs {
 template <class F, int PARTY>
 __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_gather_kernel(size_t n, const __grid_constant__ RecombineArgs g,
                                                                             const __grid_constant__ GatherArgs q) {
-  pdl_prologue();
+  pdl_prologue(g.independent != 0);
   const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
     fe8 dm, em, dp, ep, as, am, bs, bm, cs, cm;
@@ -150,6 +166,7 @@ __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_
       }
     }
   }
+  pdl_epilogue(g.independent != 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -176,7 +193,7 @@ __device__ __forceinline__ void st_fe_multicast(char* base, size_t i, const fe8&
 template <class F, int PARTY>
 __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_gather_mc_kernel(size_t n, const __grid_constant__ RecombineArgs g,
                                                                                                const __grid_constant__ McGatherArgs q) {
-  pdl_prologue();
+  pdl_prologue(g.independent != 0);
   const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
     fe8 dm, em, dp, ep, as, am, bs, bm, cs, cm;
@@ -197,6 +214,7 @@ __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_
     st_fe_multicast(q.d, i, d);
     st_fe_multicast(q.e, i, e);
   }
+  pdl_epilogue(g.independent != 0);
 }
 
 // plain all-gather by multicast (no arithmetic): rows of this rank's local plane -> every rank's gathered plane
@@ -539,7 +557,7 @@ constexpr int kSumGatesPerThread = 8;
 template <class F, int PARTY>
 __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_sum_kernel(size_t n, const __grid_constant__ RecombineArgs g,
                                                                                          MVec part_s, MVec part_m) {
-  pdl_prologue();
+  pdl_prologue(g.independent != 0);
   const size_t step = (size_t)gridDim.x * kBlock;
   fe8 acc_s, acc_m;
   Fp<F>::set_zero(acc_s);
@@ -571,6 +589,7 @@ __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_
     st_fe(part_s, w, acc_s);
     st_fe(part_m, w, acc_m);
   }
+  pdl_epilogue(g.independent != 0);
 }
 
 // ---------------------------------------------------------------------------------------------

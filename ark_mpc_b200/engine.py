@@ -60,6 +60,11 @@ class Engine:
             self.lib.arkmpc_ctx_set_stream(self.ctx, C.c_void_p(s))
             self._bound_stream = s
 
+    def hint_independent(self) -> None:
+        """The next Beaver kernel launched through this engine does not depend on the kernel launched just before it
+        (arkmpc_ctx_hint_independent): its ramp-up overlaps the predecessor's drain."""
+        self.lib.arkmpc_ctx_hint_independent(self.ctx)
+
     def sync(self) -> None:
         self.bind_current_stream()
         nat.check(self.lib.arkmpc_ctx_sync(self.ctx), "arkmpc_ctx_sync", self.ctx)

@@ -195,7 +195,9 @@ def workload_config(args, world):
                         f"(BASELINE.json configs[1])",
             "field": args.field, "log2_batch_per_gpu": args.log2_batch, "parties": 2,
             "sharding": f"index-range x{world}, no data-path collective",
-            "l2_hygiene": "inputs larger than L2: ~0.9 GB touched per step vs 126 MB L2"}
+            "l2_hygiene": "inputs larger than L2: ~0.9 GB touched per step vs 126 MB L2",
+            "launch_order": "mask(p0) mask(p1) recombine(p0) recombine(p1); " + ("every launch ordered after its predecessor" if args.no_hint else
+                            "the second launch of each phase carries the independence hint (overlaps the first's drain)")}
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -299,8 +301,9 @@ def measure_open_gather(E, stream, D, n, rank, world, steps, warmup, base_seed, 
     res = {"transport": G.transport, "rows_per_rank": n, "bytes_gathered_per_rank": 64 * n * world}
 
     def masks():
-        for p in (0, 1):
-            E.beaver_mask(P[p]["x"][0], P[p]["y"][0], P[p]["a"][0], P[p]["b"][0], out=de[p])
+        E.beaver_mask(P[0]["x"][0], P[0]["y"][0], P[0]["a"][0], P[0]["b"][0], out=de[0])
+        E.hint_independent()
+        E.beaver_mask(P[1]["x"][0], P[1]["y"][0], P[1]["a"][0], P[1]["b"][0], out=de[1])
 
     def k2_p1():
         E.beaver_recombine(1, P[1]["key"], de[1][0], de[1][1], de[0][0], de[0][1], P[1]["a"], P[1]["b"], P[1]["c"], out=out[1])
@@ -310,6 +313,7 @@ def measure_open_gather(E, stream, D, n, rank, world, steps, warmup, base_seed, 
     def step_fused():
         masks()
         k2_p1()
+        E.hint_independent()  # party 0's recombine + gather does not depend on party 1's recombine
         G.recombine_gather(*args0())
 
     def step_nccl():
@@ -611,6 +615,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hint", action="store_true", help="A/B: launch every kernel ordered after its predecessor (no independence hints)")
     ap.add_argument("--unfused-sum", action="store_true", help="inner_product: separate recombine and share_sum launches (A/B)")
     ap.add_argument("--configs", default="all", help="'all' (default), 'none', or a comma list of 0,2,3,4: which BASELINE.json configs ride along "
                                                      "under the `configs` key of the headline line")
@@ -680,13 +685,19 @@ def main():
         de = [(E.empty(n), E.empty(n)) for _ in range(2)]
         out = [(E.empty(n), E.empty(n)) for _ in range(2)]
 
+        # The two parties' launches of one phase are independent of each other (different operands, different outputs): the
+        # second carries the executor's independence hint (arkmpc_ctx_hint_independent), so its ramp-up overlaps the first's drain.
+        hint = (lambda: None) if args.no_hint else E.hint_independent
+
         def mask_both():
-            for p in (0, 1):
-                E.beaver_mask(P[p]["x"][0], P[p]["y"][0], P[p]["a"][0], P[p]["b"][0], out=de[p])
+            E.beaver_mask(P[0]["x"][0], P[0]["y"][0], P[0]["a"][0], P[0]["b"][0], out=de[0])
+            hint()
+            E.beaver_mask(P[1]["x"][0], P[1]["y"][0], P[1]["a"][0], P[1]["b"][0], out=de[1])
 
         def recombine_both():
-            for p in (0, 1):
-                E.beaver_recombine(p, P[p]["key"], de[p][0], de[p][1], de[1 - p][0], de[1 - p][1], P[p]["a"], P[p]["b"], P[p]["c"], out=out[p])
+            E.beaver_recombine(0, P[0]["key"], de[0][0], de[0][1], de[1][0], de[1][1], P[0]["a"], P[0]["b"], P[0]["c"], out=out[0])
+            hint()
+            E.beaver_recombine(1, P[1]["key"], de[1][0], de[1][1], de[0][0], de[0][1], P[1]["a"], P[1]["b"], P[1]["c"], out=out[1])
 
         def step():
             mask_both()

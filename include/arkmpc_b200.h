@@ -73,6 +73,15 @@ int arkmpc_ctx_destroy(arkmpc_ctx* ctx);
  * non-blocking stream; arkmpc_ctx_reset_stream returns to it. */
 int arkmpc_ctx_set_stream(arkmpc_ctx* ctx, void* cuda_stream);
 int arkmpc_ctx_reset_stream(arkmpc_ctx* ctx);
+/* Scheduling hint for the executor thread (the fabric knows its gate DAG).  Beaver kernels (arkmpc_fr_beaver_mask /
+ * _recombine / _recombine_sum / _recombine_gather*) launched WITH the hint form a group with the un-hinted launch that
+ * precedes them; the members of a group must be mutually independent — none reads or overwrites what another writes or
+ * reads (e.g. the same gate of the two parties in a mock run, or batch_muls on unrelated operands).  A hinted launch starts
+ * its loads and arithmetic while the earlier members of its group are still draining instead of waiting for them (its
+ * programmatic-dependency wait moves to its last instruction); dependencies on everything launched before the group, and of
+ * everything launched after it, are honoured as usual.  The hint is consumed by one launch.  It is meant for ONE scheduling
+ * thread per context: with concurrent callers the predecessor is unknown, so do not use it there. */
+int arkmpc_ctx_hint_independent(arkmpc_ctx* ctx);
 void* arkmpc_ctx_get_stream(arkmpc_ctx* ctx);
 int arkmpc_ctx_device(arkmpc_ctx* ctx);
 int arkmpc_ctx_sync(arkmpc_ctx* ctx);

@@ -49,9 +49,9 @@ def main():
     want_e = torch.cat([shard_data(E, n, 7919 * r)[2] for r in range(world)], dim=0)
     de = [E.beaver_mask(P[p]["x"][0], P[p]["y"][0], P[p]["a"][0], P[p]["b"][0]) for p in (0, 1)]
     used = []
-    for transport in ("ipc", "auto"):
+    for transport in ("ipc", "multicast_or_ipc"):
         G = sh.OpenGather(E, n, transport=transport)
-        if transport == "auto" and G.transport == "ipc":
+        if transport != "ipc" and G.transport == "ipc":
             print(f"rank {rank}: multicast unavailable ({G.fallback_reason}); ipc already covered", flush=True)
             G.close()
             continue

@@ -349,3 +349,36 @@ def test_engine_follows_torch_current_stream():
     torch.cuda.synchronize()
     assert torch.equal(c, c2)
     E.close()
+
+
+@pytest.mark.parametrize("fid", FIDS)
+@pytest.mark.parametrize("n", [1000, 1 << 18, (1 << 20) + 77])
+def test_independence_hint_keeps_results_and_ordering(engines, fid, n):
+    """arkmpc_ctx_hint_independent: the four launches of a two-party step with the second launch of each phase hinted, repeated
+    back to back with the SAME buffers (so each phase truly depends on the one before it: recombine reads what the masks wrote,
+    the next step's masks overwrite what this step's recombines read).  Every step's outputs must equal the oracle's."""
+    E = engines[fid]
+    D = TwoPartyData(fid, n, seed=4242 + n)
+    o0, o1, _, _ = D.oracle_batch_mul()
+    P = [D.party(p) for p in (0, 1)]
+    dev = [{k: ((up(E, v[0]), up(E, v[1])) if isinstance(v, tuple) else v) for k, v in P[p].items()} for p in (0, 1)]
+    de = [(E.empty(n), E.empty(n)) for _ in (0, 1)]
+    out = [(E.empty(n), E.empty(n)) for _ in (0, 1)]
+    zero = [t for pair in de + out for t in pair]
+    for rep in range(6):
+        for t in zero:
+            t.zero_()  # torch kernels between the steps: plain launches, ordered as usual
+        for p in (0, 1):
+            if p == 1:
+                E.hint_independent()
+            E.beaver_mask(dev[p]["x"][0], dev[p]["y"][0], dev[p]["a"][0], dev[p]["b"][0], out=de[p])
+        for p in (0, 1):
+            if p == 1:
+                E.hint_independent()
+            E.beaver_recombine(p, P[p]["key"], de[p][0], de[p][1], de[1 - p][0], de[1 - p][1], dev[p]["a"], dev[p]["b"], dev[p]["c"], out=out[p])
+        if rep % 2 == 1:  # un-synchronised back-to-back steps on odd reps, checked ones on even reps
+            continue
+        for p, want in ((0, o0), (1, o1)):
+            assert np.array_equal(dn(E, out[p][0]), want[:, :4]) and np.array_equal(dn(E, out[p][1]), want[:, 4:]), f"rep {rep} party {p}"
+    for p, want in ((0, o0), (1, o1)):
+        assert np.array_equal(dn(E, out[p][0]), want[:, :4]) and np.array_equal(dn(E, out[p][1]), want[:, 4:])

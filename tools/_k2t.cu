@@ -101,7 +101,7 @@ int main() {
   RecombineArgs g;
   g.d_mine = Vec{buf[0], 32}; g.e_mine = Vec{buf[1], 32}; g.d_peer = Vec{buf[2], 32}; g.e_peer = Vec{buf[3], 32};
   g.a_s = Vec{buf[4], 32}; g.a_m = Vec{buf[5], 32}; g.b_s = Vec{buf[6], 32}; g.b_m = Vec{buf[7], 32}; g.c_s = Vec{buf[8], 32}; g.c_m = Vec{buf[9], 32};
-  g.out_s = MVec{buf[10], 32}; g.out_m = MVec{buf[11], 32}; g.d_open = MVec{nullptr, 32}; g.e_open = MVec{nullptr, 32};
+  g.out_s = MVec{buf[10], 32}; g.out_m = MVec{buf[11], 32}; g.d_open = MVec{nullptr, 32}; g.e_open = MVec{nullptr, 32}; g.independent = 0;
   const uint64_t key[4] = {0x123456789abcdef1ull, 0x0fedcba987654321ull, 0x1122334455667788ull, 0x0123456789abcdefull};
   ctab_build<Bn254Fr>(g.key, key);
   unsigned long long* stamps; cudaMalloc(&stamps, (size_t)(n / 64 + 1) * 24);
