@@ -185,6 +185,8 @@ int arkmpc_ctx_destroy(arkmpc_ctx* ctx) {
   for (int c = 0; c < kNumCurves; c++)
     if (ctx->gtab[c]) cudaFree(ctx->gtab[c]);
   if (ctx->ntt_tw) cudaFree(ctx->ntt_tw);
+  if (ctx->tab_scratch) cudaFree(ctx->tab_scratch);
+  if (ctx->tab_masks) cudaFree(ctx->tab_masks);
   }  // the guard (and the lock it holds) must be gone before the context is
   delete ctx;
   return ARKMPC_OK;

@@ -51,6 +51,8 @@ struct arkmpc_ctx {
   size_t chunk_elems = arkctx::kChunkElems;  // host-buffer path staging granularity (ARKMPC_CHUNK_LOG2 overrides)
   void* gtab[arkctx::kNumCurves] = {nullptr, nullptr};  // fixed-base tables, built on first use (arkmpc_curve.cu)
   std::mutex gtab_mutex;
+  void* tab_scratch = nullptr;  // window-table records of the variable-base multiplications (curve_kernels.cuh), L2-resident
+  void* tab_masks = nullptr;    // per-SM slot claim masks
   void* ntt_tw = nullptr;    // twiddle table + constants of the last (field, log2n, direction) transform (arkmpc_ntt.cu)
   long ntt_key = -1;
   void* nccl = nullptr;      // ncclComm_t of arkmpc_nccl_init (arkmpc_comm.cu)

@@ -104,6 +104,7 @@ struct Bn254G1 {
   }
   ARK_DM static void neg(Pt& p) { K::neg(p.Y, p.Y); }
   ARK_DM static void cache(Cached& c, const Pt& p) { c = p; }
+  ARK_DM static void cached_neg(Cached& c) { K::neg(c.Y, c.Y); }
 
   // dbl-2009-l (2M + 5S); Z = 0 stays Z = 0
   ARK_DM static void dbl(Pt& p, bool = true) {
@@ -268,6 +269,12 @@ struct Ed25519 {
     K::sub(c.YmX, p.Y, p.X);
     K::dbl(c.Z2, p.Z);
     K::mul(c.T2d, p.T, k);
+  }
+  ARK_DM static void cached_neg(Cached& c) {  // -(X, Y, T, Z) = (-X, Y, -T, Z): swap Y+X and Y-X, negate 2dT
+    const fe8 t = c.YpX;
+    c.YpX = c.YmX;
+    c.YmX = t;
+    K::neg(c.T2d, c.T2d);
   }
 
   // dbl-2008-hwcd with a = -1 (4M + 4S).  T is consumed only by additions, so inside a run of doublings it is computed
@@ -440,45 +447,93 @@ ARK_D void glv_decompose_bn254(const uint32_t* k, uint32_t* k1, bool& neg1, uint
 // ----------------------------------------------------------------------------------------------
 // Scalar multiplication building blocks
 // ----------------------------------------------------------------------------------------------
+// Variable base: SIGNED 4-bit windows.  With k' = k + 0x88...8 the digit of window i is nibble_i(k') - 8 in [-8, 7], so the
+// table holds only 1P..8P (8 entries instead of 15; negation of a table entry is free) and a 256-bit scalar still costs 252
+// doublings and at most 64 additions.  The table lives behind a small store interface (`put` / `get`) so that the same code
+// runs on a per-thread array (host emulation, small kernels) and on the kernels' L2-resident scratch records (curve_kernels.cuh:
+// a per-thread array indexed by a divergent window would be local memory, whose word-interleaved layout turns every entry
+// read into 32 sectors per warp instruction — 8.7 GB of DRAM traffic per 2^17-element launch in round 1).
 constexpr int kWindows = 64;      // 4-bit windows of a 256-bit scalar
-constexpr int kTabEntries = 16;   // index 0 unused
+constexpr int kTabEntries = 8;    // 1P .. 8P (entry w-1 holds w*P)
 
-// tab[w] = w*P for w = 1..15
 template <class C>
-ARK_D void build_table(typename C::Cached* tab, const typename C::Pt& P) {
+struct LocalTab {
+  typename C::Cached t[kTabEntries];
+  ARK_DM void put(int idx, const typename C::Cached& c) { t[idx] = c; }
+  ARK_DM void get(typename C::Cached& c, int idx) const { c = t[idx]; }
+  ARK_DM void prefetch(int) const {}
+};
+
+// store w*P for w = 1..8
+template <class C, class Tab>
+ARK_D void build_table(Tab& tab, const typename C::Pt& P) {
   typename C::Pt t = P;
-  C::cache(tab[1], t);
+  typename C::Cached c1, c;
+  C::cache(c1, t);
+  tab.put(0, c1);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-  for (int w = 2; w < kTabEntries; w++) {
-    C::add_cached(t, tab[1]);
-    C::cache(tab[w], t);
+  for (int w = 2; w <= kTabEntries; w++) {
+    C::add_cached(t, c1);
+    C::cache(c, t);
+    tab.put(w - 1, c);
   }
 }
 
-// acc = k * P from the table (acc must be the identity on entry)
-template <class C> ARK_D void var_mul_glv(typename C::Pt& acc, const typename C::Cached* tab, const uint32_t* k);
-template <class C>
-ARK_D void var_mul2_glv(typename C::Pt& acc0, typename C::Pt& acc1, const typename C::Cached* tab, const uint32_t* ka, const uint32_t* kb);
+// k' = k + 0x8888...8 over `limbs` words; returns the carry out of the top word (an extra, non-negative top digit)
+ARK_D uint32_t signed_recode(uint32_t* kk, const uint32_t* k, int limbs) {
+  uint64_t c = 0;
+  for (int j = 0; j < limbs; j++) {
+    c += (uint64_t)k[j] + 0x88888888u;
+    kk[j] = (uint32_t)c;
+    c >>= 32;
+  }
+  return (uint32_t)c;
+}
 
-template <class C>
-ARK_D void var_mul(typename C::Pt& acc, const typename C::Cached* tab, const uint32_t* k) {
+// request the table entry a signed digit will need (no-op for digit 0 and for array-backed tables)
+template <class Tab>
+ARK_D void prefetch_signed(const Tab& tab, int digit) {
+  if (digit != 0) tab.prefetch((digit < 0 ? -digit : digit) - 1);
+}
+
+// acc += digit * P for a signed digit in [-8, 8]
+template <class C, class Tab>
+ARK_D void add_signed(typename C::Pt& acc, const Tab& tab, int digit) {
+  if (digit == 0) return;
+  typename C::Cached c;
+  tab.get(c, (digit < 0 ? -digit : digit) - 1);
+  if (digit < 0) C::cached_neg(c);
+  C::add_cached(acc, c);
+}
+
+// acc = k * P from the table (acc must be the identity on entry)
+template <class C, class Tab> ARK_D void var_mul_glv(typename C::Pt& acc, const Tab& tab, const uint32_t* k);
+template <class C, class Tab>
+ARK_D void var_mul2_glv(typename C::Pt& acc0, typename C::Pt& acc1, const Tab& tab, const uint32_t* ka, const uint32_t* kb);
+
+template <class C, class Tab>
+ARK_D void var_mul(typename C::Pt& acc, const Tab& tab, const uint32_t* k) {
   if constexpr (C::kGlv) {
     var_mul_glv<C>(acc, tab, k);
   } else {
+    uint32_t kk[8];
+    const uint32_t top = signed_recode(kk, k, 8);  // k < r < 2^254: the top nibble is <= 3, never carries out
+    (void)top;
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
     for (int i = kWindows - 1; i >= 0; i--) {
+      const int digit = (int)window4(kk, i) - 8;
+      prefetch_signed(tab, digit);
       if (i != kWindows - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
         for (int j = 0; j < 4; j++) C::dbl(acc, j == 3);  // every window ends in (possibly) an addition; the final T is part of the result
       }
-      const uint32_t w = window4(k, i);
-      if (w) C::add_cached(acc, tab[w]);
+      add_signed<C>(acc, tab, digit);
     }
   }
 }
@@ -486,15 +541,21 @@ ARK_D void var_mul(typename C::Pt& acc, const typename C::Cached* tab, const uin
 // (acc0, acc1) = (k0 * P, k1 * P): two accumulators advanced in lock-step over one table.  The two chains are independent, so the
 // instruction scheduler can interleave them: the kernels are bound by the latency of dependent carry chains at 8-16 warps per
 // SM, and a second chain per thread fills the bubbles (C::kDualChain selects it per curve, profiles/r01g_dual_chain_ab.txt).
-template <class C>
-ARK_D void var_mul2(typename C::Pt& acc0, typename C::Pt& acc1, const typename C::Cached* tab, const uint32_t* k0, const uint32_t* k1) {
+template <class C, class Tab>
+ARK_D void var_mul2(typename C::Pt& acc0, typename C::Pt& acc1, const Tab& tab, const uint32_t* k0, const uint32_t* k1) {
   if constexpr (C::kGlv) {
     var_mul2_glv<C>(acc0, acc1, tab, k0, k1);
   } else {
+    uint32_t kk0[8], kk1[8];
+    signed_recode(kk0, k0, 8);
+    signed_recode(kk1, k1, 8);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
     for (int i = kWindows - 1; i >= 0; i--) {
+      const int d0 = (int)window4(kk0, i) - 8, d1 = (int)window4(kk1, i) - 8;
+      prefetch_signed(tab, d0);
+      prefetch_signed(tab, d1);
       if (i != kWindows - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
@@ -504,61 +565,89 @@ ARK_D void var_mul2(typename C::Pt& acc0, typename C::Pt& acc1, const typename C
           C::dbl(acc1, j == 3);
         }
       }
-      const uint32_t w0 = window4(k0, i), w1 = window4(k1, i);
-      if (w0) C::add_cached(acc0, tab[w0]);
-      if (w1) C::add_cached(acc1, tab[w1]);
+      add_signed<C>(acc0, tab, d0);
+      add_signed<C>(acc1, tab, d1);
     }
   }
 }
 
-// GLV variants (C::kGlv): acc = k1 P + k2 phi(P) with |k1|, |k2| < 2^132: 33 windows, 128 doublings.  phi and the signs are
-// applied to the looked-up table entry (one multiplication by beta, one negation), so both halves share the table of P.
+// GLV variants (C::kGlv): acc = k1 P + k2 phi(P) with |k1|, |k2| < 2^128: 33 signed windows, 128 doublings.  phi and the signs
+// are applied to the looked-up table entry (one multiplication by beta, one negation), so both halves share the table of P.
 constexpr int kGlvWindows = 33;
 
-template <class C>
-ARK_D void glv_add(typename C::Pt& acc, const typename C::Cached& e, bool endo, bool neg) {
-  typename C::Cached t = e;
+template <class C, class Tab>
+ARK_D void glv_add(typename C::Pt& acc, const Tab& tab, int digit, bool endo, bool neg) {
+  if (digit == 0) return;
+  typename C::Cached t;
+  tab.get(t, (digit < 0 ? -digit : digit) - 1);
   if (endo) {
     fe8 beta;
     beta.v[0] = 0xd782e155u; beta.v[1] = 0x71930c11u; beta.v[2] = 0xffbe3323u; beta.v[3] = 0xa6bb947cu;
     beta.v[4] = 0xd4741444u; beta.v[5] = 0xaa303344u; beta.v[6] = 0x26594943u; beta.v[7] = 0x2c3b3f0du;
     C::K::mul(t.X, t.X, beta);
   }
-  if (neg) C::K::neg(t.Y, t.Y);
+  if (neg != (digit < 0)) C::cached_neg(t);
   C::add_cached(acc, t);
 }
 
-template <class C>
-ARK_D void var_mul_glv(typename C::Pt& acc, const typename C::Cached* tab, const uint32_t* k) {
-  uint32_t k1[5], k2[5];
+// digit of window i (0..32) of a recoded half-scalar
+ARK_D int glv_digit(const uint32_t* kk, int i) { return (int)window4(kk, i) - 8; }
+// k' = k + (0x8 in each of the 33 low nibbles).  |k| < 2^128 (glv_decompose_bn254), so k' < 2^128 + 0.54 * 2^132 < 2^132: the
+// 33 nibbles hold all of k' and there is no carry digit.
+ARK_D void glv_recode(uint32_t* kk, const uint32_t* k) {
+  uint64_t c = 0;
+  for (int j = 0; j < 4; j++) {
+    c += (uint64_t)k[j] + 0x88888888u;
+    kk[j] = (uint32_t)c;
+    c >>= 32;
+  }
+  kk[4] = (uint32_t)(c + k[4] + 0x8u);
+}
+
+template <class C, class Tab>
+ARK_D void var_mul_glv(typename C::Pt& acc, const Tab& tab, const uint32_t* k) {
+  uint32_t k1[5], k2[5], r1[5], r2[5];
   bool n1, n2;
   glv_decompose_bn254(k, k1, n1, k2, n2);
+  glv_recode(r1, k1);
+  glv_recode(r2, k2);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
   for (int i = kGlvWindows - 1; i >= 0; i--) {
+    const int d1 = glv_digit(r1, i), d2 = glv_digit(r2, i);
+    prefetch_signed(tab, d1);
+    prefetch_signed(tab, d2);
     if (i != kGlvWindows - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
       for (int j = 0; j < 4; j++) C::dbl(acc, j == 3);
     }
-    const uint32_t w1 = window4(k1, i), w2 = window4(k2, i);
-    if (w1) glv_add<C>(acc, tab[w1], false, n1);
-    if (w2) glv_add<C>(acc, tab[w2], true, n2);
+    glv_add<C>(acc, tab, d1, false, n1);
+    glv_add<C>(acc, tab, d2, true, n2);
   }
 }
 
-template <class C>
-ARK_D void var_mul2_glv(typename C::Pt& acc0, typename C::Pt& acc1, const typename C::Cached* tab, const uint32_t* ka, const uint32_t* kb) {
-  uint32_t a1[5], a2[5], b1[5], b2[5];
+template <class C, class Tab>
+ARK_D void var_mul2_glv(typename C::Pt& acc0, typename C::Pt& acc1, const Tab& tab, const uint32_t* ka, const uint32_t* kb) {
+  uint32_t a1[5], a2[5], b1[5], b2[5], t[5];
   bool na1, na2, nb1, nb2;
   glv_decompose_bn254(ka, a1, na1, a2, na2);
   glv_decompose_bn254(kb, b1, nb1, b2, nb2);
+  glv_recode(t, a1); ARK_UNROLL for (int j = 0; j < 5; j++) a1[j] = t[j];
+  glv_recode(t, a2); ARK_UNROLL for (int j = 0; j < 5; j++) a2[j] = t[j];
+  glv_recode(t, b1); ARK_UNROLL for (int j = 0; j < 5; j++) b1[j] = t[j];
+  glv_recode(t, b2); ARK_UNROLL for (int j = 0; j < 5; j++) b2[j] = t[j];
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
   for (int i = kGlvWindows - 1; i >= 0; i--) {
+    const int da1 = glv_digit(a1, i), db1 = glv_digit(b1, i), da2 = glv_digit(a2, i), db2 = glv_digit(b2, i);
+    prefetch_signed(tab, da1);
+    prefetch_signed(tab, db1);
+    prefetch_signed(tab, da2);
+    prefetch_signed(tab, db2);
     if (i != kGlvWindows - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
@@ -568,14 +657,152 @@ ARK_D void var_mul2_glv(typename C::Pt& acc0, typename C::Pt& acc1, const typena
         C::dbl(acc1, j == 3);
       }
     }
-    uint32_t w = window4(a1, i);
-    if (w) glv_add<C>(acc0, tab[w], false, na1);
-    w = window4(b1, i);
-    if (w) glv_add<C>(acc1, tab[w], false, nb1);
-    w = window4(a2, i);
-    if (w) glv_add<C>(acc0, tab[w], true, na2);
-    w = window4(b2, i);
-    if (w) glv_add<C>(acc1, tab[w], true, nb2);
+    glv_add<C>(acc0, tab, da1, false, na1);
+    glv_add<C>(acc1, tab, db1, false, nb1);
+    glv_add<C>(acc0, tab, da2, true, na2);
+    glv_add<C>(acc1, tab, db2, true, nb2);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Two multiplications of the SAME point (share and MAC passes of a gate): split every scalar at the middle window,
+// k = k_lo + 2^s k_hi, and give the high half its own table of P' = 2^s P.  The s doublings that produce P' are paid once,
+// and each pass then runs over half the windows with two additions per window: for 256-bit scalars 128 + 2 x 124 doublings
+// instead of 2 x 252 (Edwards), for the 33-window GLV halves 68 + 2 x 64 instead of 2 x 128 (BN254).  Additions are unchanged.
+// ----------------------------------------------------------------------------------------------
+constexpr int kSplitWindows = kWindows / 2;            // 32 windows = 128 bits
+constexpr int kGlvSplitWindows = (kGlvWindows + 1) / 2;  // 17 windows = 68 bits
+
+// P' = 2^(4 * windows) P
+template <class C>
+ARK_D void shift_windows(typename C::Pt& p, int windows) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int j = 4 * windows - 1; j >= 0; j--) C::dbl(p, j == 0);
+}
+template <class C>
+ARK_D int split_shift_windows() { return C::kGlv ? kGlvSplitWindows : kSplitWindows; }
+
+// acc = k * P given the tables of P (lo) and of P' (hi); acc must be the identity on entry
+template <class C, class Tab>
+ARK_D void var_mul_split(typename C::Pt& acc, const Tab& lo, const Tab& hi, const uint32_t* k) {
+  if constexpr (C::kGlv) {
+    uint32_t k1[5], k2[5], r1[5], r2[5];
+    bool n1, n2;
+    glv_decompose_bn254(k, k1, n1, k2, n2);
+    glv_recode(r1, k1);
+    glv_recode(r2, k2);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int i = kGlvSplitWindows - 1; i >= 0; i--) {
+      const bool has_hi = i + kGlvSplitWindows < kGlvWindows;
+      const int l1 = glv_digit(r1, i), l2 = glv_digit(r2, i);
+      const int h1 = has_hi ? glv_digit(r1, i + kGlvSplitWindows) : 0, h2 = has_hi ? glv_digit(r2, i + kGlvSplitWindows) : 0;
+      prefetch_signed(lo, l1);
+      prefetch_signed(lo, l2);
+      prefetch_signed(hi, h1);
+      prefetch_signed(hi, h2);
+      if (i != kGlvSplitWindows - 1) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < 4; j++) C::dbl(acc, j == 3);
+      }
+      glv_add<C>(acc, lo, l1, false, n1);
+      glv_add<C>(acc, lo, l2, true, n2);
+      glv_add<C>(acc, hi, h1, false, n1);
+      glv_add<C>(acc, hi, h2, true, n2);
+    }
+  } else {
+    uint32_t kk[8];
+    signed_recode(kk, k, 8);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int i = kSplitWindows - 1; i >= 0; i--) {
+      const int dl = (int)window4(kk, i) - 8, dh = (int)window4(kk, i + kSplitWindows) - 8;
+      prefetch_signed(lo, dl);
+      prefetch_signed(hi, dh);
+      if (i != kSplitWindows - 1) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < 4; j++) C::dbl(acc, j == 3);
+      }
+      add_signed<C>(acc, lo, dl);
+      add_signed<C>(acc, hi, dh);
+    }
+  }
+}
+
+// (acc0, acc1) = (ka * P, kb * P) in lock-step (C::kDualChain), same tables
+template <class C, class Tab>
+ARK_D void var_mul2_split(typename C::Pt& acc0, typename C::Pt& acc1, const Tab& lo, const Tab& hi, const uint32_t* ka, const uint32_t* kb) {
+  if constexpr (C::kGlv) {
+    uint32_t a1[5], a2[5], b1[5], b2[5], t[5];
+    bool na1, na2, nb1, nb2;
+    glv_decompose_bn254(ka, a1, na1, a2, na2);
+    glv_decompose_bn254(kb, b1, nb1, b2, nb2);
+    glv_recode(t, a1); ARK_UNROLL for (int j = 0; j < 5; j++) a1[j] = t[j];
+    glv_recode(t, a2); ARK_UNROLL for (int j = 0; j < 5; j++) a2[j] = t[j];
+    glv_recode(t, b1); ARK_UNROLL for (int j = 0; j < 5; j++) b1[j] = t[j];
+    glv_recode(t, b2); ARK_UNROLL for (int j = 0; j < 5; j++) b2[j] = t[j];
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int i = kGlvSplitWindows - 1; i >= 0; i--) {
+      const bool has_hi = i + kGlvSplitWindows < kGlvWindows;
+      const int ih = i + kGlvSplitWindows;
+      const int la1 = glv_digit(a1, i), la2 = glv_digit(a2, i), lb1 = glv_digit(b1, i), lb2 = glv_digit(b2, i);
+      const int ha1 = has_hi ? glv_digit(a1, ih) : 0, ha2 = has_hi ? glv_digit(a2, ih) : 0;
+      const int hb1 = has_hi ? glv_digit(b1, ih) : 0, hb2 = has_hi ? glv_digit(b2, ih) : 0;
+      prefetch_signed(lo, la1); prefetch_signed(lo, lb1); prefetch_signed(lo, la2); prefetch_signed(lo, lb2);
+      prefetch_signed(hi, ha1); prefetch_signed(hi, hb1); prefetch_signed(hi, ha2); prefetch_signed(hi, hb2);
+      if (i != kGlvSplitWindows - 1) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < 4; j++) {
+          C::dbl(acc0, j == 3);
+          C::dbl(acc1, j == 3);
+        }
+      }
+      glv_add<C>(acc0, lo, la1, false, na1);
+      glv_add<C>(acc1, lo, lb1, false, nb1);
+      glv_add<C>(acc0, lo, la2, true, na2);
+      glv_add<C>(acc1, lo, lb2, true, nb2);
+      glv_add<C>(acc0, hi, ha1, false, na1);
+      glv_add<C>(acc1, hi, hb1, false, nb1);
+      glv_add<C>(acc0, hi, ha2, true, na2);
+      glv_add<C>(acc1, hi, hb2, true, nb2);
+    }
+  } else {
+    uint32_t kk0[8], kk1[8];
+    signed_recode(kk0, ka, 8);
+    signed_recode(kk1, kb, 8);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int i = kSplitWindows - 1; i >= 0; i--) {
+      const int l0 = (int)window4(kk0, i) - 8, l1 = (int)window4(kk1, i) - 8;
+      const int h0 = (int)window4(kk0, i + kSplitWindows) - 8, h1 = (int)window4(kk1, i + kSplitWindows) - 8;
+      prefetch_signed(lo, l0); prefetch_signed(lo, l1); prefetch_signed(hi, h0); prefetch_signed(hi, h1);
+      if (i != kSplitWindows - 1) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < 4; j++) {
+          C::dbl(acc0, j == 3);
+          C::dbl(acc1, j == 3);
+        }
+      }
+      add_signed<C>(acc0, lo, l0);
+      add_signed<C>(acc1, lo, l1);
+      add_signed<C>(acc0, hi, h0);
+      add_signed<C>(acc1, hi, h1);
+    }
   }
 }
 

@@ -19,29 +19,49 @@
 
 namespace ark {
 
+// Every gate that multiplies a variable point takes the window-table store as a workspace (`Tab`, curve.cuh): the kernels
+// pass their scratch record, the overloads without it use a per-thread array (host emulation, tests).
+
 // out = s * P
-template <class C>
-ARK_D void pt_mul_elem(typename C::Pt& out, const fe8& s, const typename C::Pt& P) {
-  typename C::Cached tab[kTabEntries];
+template <class C, class Tab>
+ARK_D void pt_mul_elem(Tab& tab, typename C::Pt& out, const fe8& s, const typename C::Pt& P) {
   uint32_t k[8];
   build_table<C>(tab, P);
   scalar_to_plain<typename C::R>(k, s);
   C::set_identity(out);
   var_mul<C>(out, tab, k);
 }
-
-// (out0, out1) = (s0 * P, s1 * P): one table, two passes
 template <class C>
-ARK_D void pt_mul2_elem(typename C::Pt& out0, typename C::Pt& out1, const fe8& s0, const fe8& s1, const typename C::Pt& P) {
-  typename C::Cached tab[kTabEntries];
+ARK_D void pt_mul_elem(typename C::Pt& out, const fe8& s, const typename C::Pt& P) {
+  LocalTab<C> tab;
+  pt_mul_elem<C>(tab, out, s, P);
+}
+
+// tables of P and of P' = 2^s P for the split two-pass multiplications (curve.cuh)
+template <class C, class Tab>
+ARK_D void build_split_tables(Tab& lo, Tab& hi, const typename C::Pt& P) {
+  build_table<C>(lo, P);
+  typename C::Pt P2 = P;
+  shift_windows<C>(P2, split_shift_windows<C>());
+  build_table<C>(hi, P2);
+}
+
+// (out0, out1) = (s0 * P, s1 * P): the two passes share the tables of P and 2^s P
+template <class C, class Tab>
+ARK_D void pt_mul2_elem(Tab& lo, Tab& hi, typename C::Pt& out0, typename C::Pt& out1, const fe8& s0, const fe8& s1, const typename C::Pt& P) {
   uint32_t k[8];
-  build_table<C>(tab, P);
+  build_split_tables<C>(lo, hi, P);
   scalar_to_plain<typename C::R>(k, s0);
   C::set_identity(out0);
-  var_mul<C>(out0, tab, k);
+  var_mul_split<C>(out0, lo, hi, k);
   scalar_to_plain<typename C::R>(k, s1);
   C::set_identity(out1);
-  var_mul<C>(out1, tab, k);
+  var_mul_split<C>(out1, lo, hi, k);
+}
+template <class C>
+ARK_D void pt_mul2_elem(typename C::Pt& out0, typename C::Pt& out1, const fe8& s0, const fe8& s1, const typename C::Pt& P) {
+  LocalTab<C> lo, hi;
+  pt_mul2_elem<C>(lo, hi, out0, out1, s0, s1, P);
 }
 
 // out = s * G
@@ -54,26 +74,37 @@ ARK_D void pt_mul_gen_elem(typename C::Pt& out, const fe8& s, const typename C::
 }
 
 // PointShare::add_public / sub_public
-template <class C>
-ARK_D void pt_share_add_public_elem(typename C::Pt& out_s, typename C::Pt& out_m, int party, bool sub, const fe8& key,
+template <class C, class Tab>
+ARK_D void pt_share_add_public_elem(Tab& tab, typename C::Pt& out_s, typename C::Pt& out_m, int party, bool sub, const fe8& key,
                                     const typename C::Pt& a_s, const typename C::Pt& a_m, const typename C::Pt& pub) {
   typename C::Pt P = pub;
   if (sub) C::neg(P);                                   // curve/share.rs:63-65: add_public(-rhs)
   out_s = a_s;
   if (party == 0) C::add(out_s, P);
   typename C::Pt kp;
-  pt_mul_elem<C>(kp, key, P);
+  pt_mul_elem<C>(tab, kp, key, P);
   out_m = a_m;
   C::add(out_m, kp);
 }
+template <class C>
+ARK_D void pt_share_add_public_elem(typename C::Pt& out_s, typename C::Pt& out_m, int party, bool sub, const fe8& key,
+                                    const typename C::Pt& a_s, const typename C::Pt& a_m, const typename C::Pt& pub) {
+  LocalTab<C> tab;
+  pt_share_add_public_elem<C>(tab, out_s, out_m, party, sub, key, a_s, a_m, pub);
+}
 
 // mac_key * opened - mac  (authenticated_curve.rs:160-175 `mac_check_value`)
-template <class C>
-ARK_D void pt_mac_check_elem(typename C::Pt& out, const fe8& key, const typename C::Pt& opened, const typename C::Pt& mac) {
-  pt_mul_elem<C>(out, key, opened);
+template <class C, class Tab>
+ARK_D void pt_mac_check_elem(Tab& tab, typename C::Pt& out, const fe8& key, const typename C::Pt& opened, const typename C::Pt& mac) {
+  pt_mul_elem<C>(tab, out, key, opened);
   typename C::Pt m = mac;
   C::neg(m);
   C::add(out, m);
+}
+template <class C>
+ARK_D void pt_mac_check_elem(typename C::Pt& out, const fe8& key, const typename C::Pt& opened, const typename C::Pt& mac) {
+  LocalTab<C> tab;
+  pt_mac_check_elem<C>(tab, out, key, opened, mac);
 }
 
 template <class C>
@@ -89,8 +120,8 @@ ARK_D void pt_beaver_mask_elem(fe8& d_mine, typename C::Pt& E_mine, const fe8& x
 
 // Writes the opened d and E, and the two result points through `emit(which, point)` (which = 0 share, 1 mac)
 // so that a kernel can store each as soon as its pass finishes.
-template <class C, bool DUAL, class Emit>
-ARK_D void pt_beaver_recombine_elem(fe8& d, typename C::Pt& E, int party, const fe8& key, const fe8& d_mine, const fe8& d_peer,
+template <class C, bool DUAL, class Tab, class Emit>
+ARK_D void pt_beaver_recombine_elem(Tab& tab, Tab& tab_hi, fe8& d, typename C::Pt& E, int party, const fe8& key, const fe8& d_mine, const fe8& d_peer,
                                     const typename C::Pt& E_mine, const typename C::Pt& E_peer, const fe8& a_s, const fe8& a_m,
                                     const fe8& b_s, const fe8& b_m, const fe8& c_s, const fe8& c_m,
                                     const typename C::Aff* gtab, Emit emit) {
@@ -98,8 +129,7 @@ ARK_D void pt_beaver_recombine_elem(fe8& d, typename C::Pt& E, int party, const 
   FR::add(d, d_mine, d_peer);
   E = E_mine;
   C::add(E, E_peer);
-  typename C::Cached tab[kTabEntries];
-  build_table<C>(tab, E);
+  build_split_tables<C>(tab, tab_hi, E);
   fe8 sv[2], tv[2], t;
   if (party == 0) FR::add(sv[0], a_s, d); else sv[0] = a_s;
   FR::mul(t, d, b_s);
@@ -115,7 +145,7 @@ ARK_D void pt_beaver_recombine_elem(fe8& d, typename C::Pt& E, int party, const 
     C::set_identity(acc1);
     scalar_to_plain<typename C::R>(k0, sv[0]);
     scalar_to_plain<typename C::R>(k1, sv[1]);
-    var_mul2<C>(acc0, acc1, tab, k0, k1);
+    var_mul2_split<C>(acc0, acc1, tab, tab_hi, k0, k1);
     scalar_to_plain<typename C::R>(k0, tv[0]);
     fix_mul_acc<C>(acc0, gtab, k0);
     emit(0, acc0);
@@ -131,12 +161,21 @@ ARK_D void pt_beaver_recombine_elem(fe8& d, typename C::Pt& E, int party, const 
       typename C::Pt acc;
       C::set_identity(acc);
       scalar_to_plain<typename C::R>(k, sv[which]);
-      var_mul<C>(acc, tab, k);
+      var_mul_split<C>(acc, tab, tab_hi, k);
       scalar_to_plain<typename C::R>(k, tv[which]);
       fix_mul_acc<C>(acc, gtab, k);
       emit(which, acc);
     }
   }
+}
+
+template <class C, bool DUAL, class Emit>
+ARK_D void pt_beaver_recombine_elem(fe8& d, typename C::Pt& E, int party, const fe8& key, const fe8& d_mine, const fe8& d_peer,
+                                    const typename C::Pt& E_mine, const typename C::Pt& E_peer, const fe8& a_s, const fe8& a_m,
+                                    const fe8& b_s, const fe8& b_m, const fe8& c_s, const fe8& c_m,
+                                    const typename C::Aff* gtab, Emit emit) {
+  LocalTab<C> tab, tab_hi;
+  pt_beaver_recombine_elem<C, DUAL>(tab, tab_hi, d, E, party, key, d_mine, d_peer, E_mine, E_peer, a_s, a_m, b_s, b_m, c_s, c_m, gtab, emit);
 }
 
 }  // namespace ark

@@ -39,6 +39,82 @@ __device__ __forceinline__ void st_pt(const PMVec& v, size_t i, const typename C
   for (int k = 0; k < C::kCoords; k++) st_fe(c, k, f[k]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Window tables of the variable-base multiplications: L2-resident scratch records instead of per-thread local arrays.
+// Every resident 128-thread block claims one of kTabSlotsPerSm slots of its SM (an atomic bit mask per SM id), and each of its
+// threads owns one contiguous kTabRecordBytes record in that slot: entries are written and read with 256-bit accesses, one
+// 32-byte sector per lane per instruction, no over-fetch.  The scratch is (SM ids) x 6 x 128 x 2 KiB, is reused by every
+// block that ever runs on the SM, and therefore stays in (or near) L2.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTabSlotsPerSm = 6;
+constexpr int kTabHalfBytes = kTabEntries * 128;     // one table: 8 entries of up to 128 B (Edwards cached form); BN254 uses 96 B of each
+constexpr int kTabRecordBytes = 2 * kTabHalfBytes;   // the table of P and, for the two-pass gates, of 2^s P behind it
+
+struct TabScratch {
+  char* base;
+  unsigned int* masks;  // one claim mask per SM id
+};
+
+// Table reads go through L1 (default caching): at 2 resident blocks per SM (BN254, 230 registers) nothing else hides an L2
+// round trip in the middle of a dependent chain of point additions, and `prefetch` lets the variable-base loops request the
+// entry of the NEXT window before the four doublings that precede its use.  A thread only ever reads records it wrote itself,
+// so L1 residency needs no coherence beyond program order.
+template <class C>
+struct GlobalTab {
+  char* rec;
+  __device__ __forceinline__ void put(int idx, const typename C::Cached& c) const {
+    const fe8* f = reinterpret_cast<const fe8*>(&c);
+    char* a = rec + idx * 128;
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(typename C::Cached) / 32); k++)
+      asm volatile("st.global.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(f[k].v[0]), "r"(f[k].v[1]), "r"(f[k].v[2]), "r"(f[k].v[3]),
+                   "r"(f[k].v[4]), "r"(f[k].v[5]), "r"(f[k].v[6]), "r"(f[k].v[7]), "l"(a + 32 * k)
+                   : "memory");
+  }
+  __device__ __forceinline__ void get(typename C::Cached& c, int idx) const {
+    fe8* f = reinterpret_cast<fe8*>(&c);
+    const char* a = rec + idx * 128;
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(typename C::Cached) / 32); k++)
+      asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(f[k].v[0]), "=r"(f[k].v[1]), "=r"(f[k].v[2]), "=r"(f[k].v[3]), "=r"(f[k].v[4]), "=r"(f[k].v[5]), "=r"(f[k].v[6]),
+                     "=r"(f[k].v[7])
+                   : "l"(a + 32 * k)
+                   : "memory");
+  }
+  __device__ __forceinline__ void prefetch(int idx) const { asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + idx * 128)); }
+};
+
+// all threads of the block call both; `token` identifies the slot between claim and release
+template <class C>
+__device__ __forceinline__ GlobalTab<C> tab_claim(const TabScratch& ts, unsigned int& token) {
+  __shared__ unsigned int s_token;
+  if (threadIdx.x == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned int b = 0;
+    for (;;) {  // more resident blocks than slots simply wait for one to be released
+      const unsigned int bit = 1u << b;
+      if (!(atomicOr(ts.masks + smid, bit) & bit)) break;
+      b = (b + 1) % kTabSlotsPerSm;
+    }
+    s_token = smid * kTabSlotsPerSm + b;
+  }
+  __syncthreads();
+  token = s_token;
+  return GlobalTab<C>{ts.base + ((size_t)token * kPtBlock + threadIdx.x) * kTabRecordBytes};
+}
+__device__ __forceinline__ void tab_release(const TabScratch& ts, unsigned int token) {
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAnd(ts.masks + token / kTabSlotsPerSm, ~(1u << (token % kTabSlotsPerSm)));
+}
+
+static __global__ void nsmid_kernel(unsigned int* out) {
+  unsigned int n;
+  asm volatile("mov.u32 %0, %%nsmid;" : "=r"(n));
+  *out = n;
+}
+
 // fixed-base table: 32 windows x 256 entries, one thread per entry (entry 0 of each window is unused)
 template <class C>
 __global__ void __launch_bounds__(kFixEntries) pt_gtab_kernel(typename C::Aff* gtab) {
@@ -93,21 +169,26 @@ __global__ void __launch_bounds__(kPtBlock) pt_neg_kernel(size_t n, PVec a, PMVe
 // out[i] = s[i >> sshift] * P[i]   (CurvePointResult::batch_mul curve.rs:459-479; batch_mul_public :718-751 with
 // sshift = 1 over the 2n points of n PointShares)
 template <class C>
-__global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_mul_kernel(size_t n, Vec s, int sshift, PVec P, PMVec out) {
+__global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_mul_kernel(size_t n, Vec s, int sshift, PVec P, PMVec out, TabScratch ts) {
+  unsigned int token;
+  GlobalTab<C> tab = tab_claim<C>(ts, token);
   const size_t step = (size_t)gridDim.x * kPtBlock;
   for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
     typename C::Pt x, r;
     fe8 k;
     ld_pt<C>(x, P, i);
     ld_fe(k, s, i >> sshift);
-    pt_mul_elem<C>(r, k, x);
+    pt_mul_elem<C>(tab, r, k, x);
     st_pt<C>(out, i, r);
   }
+  tab_release(ts, token);
 }
 
 // out[i] = (s_share[i] * P[i], s_mac[i] * P[i])   (batch_mul_authenticated curve.rs:483-517)
 template <class C>
-__global__ void __launch_bounds__(kPtBlock) pt_mul_auth_kernel(size_t n, Vec s_share, Vec s_mac, PVec P, PMVec out_s, PMVec out_m) {
+__global__ void __launch_bounds__(kPtBlock) pt_mul_auth_kernel(size_t n, Vec s_share, Vec s_mac, PVec P, PMVec out_s, PMVec out_m, TabScratch ts) {
+  unsigned int token;
+  GlobalTab<C> tab = tab_claim<C>(ts, token);
   const size_t step = (size_t)gridDim.x * kPtBlock;
   for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
     typename C::Pt x, r0, r1;
@@ -115,10 +196,12 @@ __global__ void __launch_bounds__(kPtBlock) pt_mul_auth_kernel(size_t n, Vec s_s
     ld_pt<C>(x, P, i);
     ld_fe(k0, s_share, i);
     ld_fe(k1, s_mac, i);
-    pt_mul2_elem<C>(r0, r1, k0, k1, x);
+    GlobalTab<C> tab_hi{tab.rec + kTabHalfBytes};
+    pt_mul2_elem<C>(tab, tab_hi, r0, r1, k0, k1, x);
     st_pt<C>(out_s, i, r0);
     st_pt<C>(out_m, i, r1);
   }
+  tab_release(ts, token);
 }
 
 // out[i] = s[i] * G   (batch_mul_generator :754-780, one launch per plane)
@@ -136,29 +219,35 @@ __global__ void __launch_bounds__(kPtBlock) pt_mul_gen_kernel(size_t n, Vec s, c
 
 template <class C>
 __global__ void __launch_bounds__(kPtBlock) pt_share_add_public_kernel(size_t n, int party, int sub, fe8 key, PVec a_s, PVec a_m, PVec pub,
-                                                                     PMVec out_s, PMVec out_m) {
+                                                                     PMVec out_s, PMVec out_m, TabScratch ts) {
+  unsigned int token;
+  GlobalTab<C> tab = tab_claim<C>(ts, token);
   const size_t step = (size_t)gridDim.x * kPtBlock;
   for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
     typename C::Pt s, m, P, os, om;
     ld_pt<C>(s, a_s, i);
     ld_pt<C>(m, a_m, i);
     ld_pt<C>(P, pub, i);
-    pt_share_add_public_elem<C>(os, om, party, sub != 0, key, s, m, P);
+    pt_share_add_public_elem<C>(tab, os, om, party, sub != 0, key, s, m, P);
     st_pt<C>(out_s, i, os);
     st_pt<C>(out_m, i, om);
   }
+  tab_release(ts, token);
 }
 
 template <class C>
-__global__ void __launch_bounds__(kPtBlock) pt_mac_check_kernel(size_t n, fe8 key, PVec opened, PVec mac, PMVec out) {
+__global__ void __launch_bounds__(kPtBlock) pt_mac_check_kernel(size_t n, fe8 key, PVec opened, PVec mac, PMVec out, TabScratch ts) {
+  unsigned int token;
+  GlobalTab<C> tab = tab_claim<C>(ts, token);
   const size_t step = (size_t)gridDim.x * kPtBlock;
   for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
     typename C::Pt o, m, r;
     ld_pt<C>(o, opened, i);
     ld_pt<C>(m, mac, i);
-    pt_mac_check_elem<C>(r, key, o, m);
+    pt_mac_check_elem<C>(tab, r, key, o, m);
     st_pt<C>(out, i, r);
   }
+  tab_release(ts, token);
 }
 
 // flag (initialised to 1) is cleared if any mine[i] + peer[i] is not the identity (:128-131)
@@ -223,7 +312,9 @@ struct PtRecombineArgs {
 
 template <class C>
 __global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_beaver_recombine_kernel(size_t n, const __grid_constant__ PtRecombineArgs g,
-                                                                      const typename C::Aff* __restrict__ gtab) {
+                                                                      const typename C::Aff* __restrict__ gtab, TabScratch ts) {
+  unsigned int token;
+  GlobalTab<C> tab = tab_claim<C>(ts, token);
   const size_t step = (size_t)gridDim.x * kPtBlock;
   for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
     fe8 dm, dp, as, am, bs, bm, cs, cm, d;
@@ -238,13 +329,15 @@ __global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_beaver_recombine_k
     ld_fe(bm, g.b_m, i);
     ld_fe(cs, g.c_s, i);
     ld_fe(cm, g.c_m, i);
-    pt_beaver_recombine_elem<C, C::kDualChain>(d, E, g.party, g.key, dm, dp, Em, Ep, as, am, bs, bm, cs, cm, gtab,
+    GlobalTab<C> tab_hi{tab.rec + kTabHalfBytes};
+    pt_beaver_recombine_elem<C, C::kDualChain>(tab, tab_hi, d, E, g.party, g.key, dm, dp, Em, Ep, as, am, bs, bm, cs, cm, gtab,
                                 [&](int which, const typename C::Pt& r) { st_pt<C>(which ? g.out_m : g.out_s, i, r); });
     if (g.open) {
       st_fe(g.d_open, i, d);
       st_pt<C>(g.E_open, i, E);
     }
   }
+  tab_release(ts, token);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -87,6 +87,37 @@ struct CurveLaunch {
     return ARKMPC_OK;
   }
 
+  // Scratch records of the variable-base window tables (curve_kernels.cuh), shared by both curves, created on first use.
+  static int tab_scratch(arkmpc_ctx* ctx, TabScratch* out) {
+    std::lock_guard<std::mutex> lock(ctx->gtab_mutex);
+    if (!ctx->tab_scratch) {
+      unsigned int* probe = nullptr;
+      ARK_CUDA(ctx, cudaMalloc(&probe, sizeof(unsigned int)));
+      nsmid_kernel<<<1, 1, 0, ctx->stream>>>(probe);
+      unsigned int nsmid = 0;
+      cudaError_t e = cudaMemcpyAsync(&nsmid, probe, sizeof nsmid, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      cudaFree(probe);
+      if (e != cudaSuccess || nsmid == 0 || nsmid > 4096) return fail(ctx, ARKMPC_ERR_CUDA, "could not read the SM id range");
+      const size_t bytes = (size_t)nsmid * kTabSlotsPerSm * kPtBlock * kTabRecordBytes;
+      void *mem = nullptr, *masks = nullptr;
+      ARK_CUDA(ctx, cudaMalloc(&mem, bytes));
+      e = cudaMalloc(&masks, nsmid * sizeof(unsigned int));
+      if (e == cudaSuccess) e = cudaMemsetAsync(masks, 0, nsmid * sizeof(unsigned int), ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) {
+        cudaFree(mem);
+        if (masks) cudaFree(masks);
+        return fail(ctx, ARKMPC_ERR_CUDA, std::string("window-table scratch: ") + cudaGetErrorString(e));
+      }
+      ctx->tab_scratch = mem;
+      ctx->tab_masks = masks;
+    }
+    out->base = static_cast<char*>(ctx->tab_scratch);
+    out->masks = static_cast<unsigned int*>(ctx->tab_masks);
+    return ARKMPC_OK;
+  }
+
   static int binary(arkmpc_ctx* ctx, size_t n, const void* a, const void* b, void* out, int sub)
 #if ARK_IN_PART(0)
   {
@@ -111,8 +142,11 @@ struct CurveLaunch {
   {
     const char* a = static_cast<const char*>(a_ps);
     char* o = static_cast<char*>(out_ps);
+    TabScratch ts;
+    int trc = tab_scratch(ctx, &ts);
+    if (trc != ARKMPC_OK) return trc;
     pt_share_add_public_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, party, sub, key, pvec(a, 2 * PB), pvec(a + PB, 2 * PB), pvec(pub, PB),
-                                                                                  pmvec(o, 2 * PB), pmvec(o + PB, 2 * PB));
+                                                                                  pmvec(o, 2 * PB), pmvec(o + PB, 2 * PB), ts);
     return post_launch(ctx, "pt_share_add_public_kernel");
   }
 #else
@@ -121,7 +155,10 @@ struct CurveLaunch {
   static int mul(arkmpc_ctx* ctx, size_t n_points, const void* scalars, int sshift, const void* pts, void* out)
 #if ARK_IN_PART(0)
   {
-    pt_mul_kernel<C><<<pt_grid(ctx, n_points, 2), kPtBlock, 0, ctx->stream>>>(n_points, vec(scalars), sshift, pvec(pts, PB), pmvec(out, PB));
+    TabScratch ts;
+    int trc = tab_scratch(ctx, &ts);
+    if (trc != ARKMPC_OK) return trc;
+    pt_mul_kernel<C><<<pt_grid(ctx, n_points, 2), kPtBlock, 0, ctx->stream>>>(n_points, vec(scalars), sshift, pvec(pts, PB), pmvec(out, PB), ts);
     return post_launch(ctx, "pt_mul_kernel");
   }
 #else
@@ -131,7 +168,10 @@ struct CurveLaunch {
 #if ARK_IN_PART(3)
   {
     char* o = static_cast<char*>(out_ps);
-    pt_mul_auth_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, vec(s_share), vec(s_mac), pvec(pts, PB), pmvec(o, 2 * PB), pmvec(o + PB, 2 * PB));
+    TabScratch ts;
+    int trc = tab_scratch(ctx, &ts);
+    if (trc != ARKMPC_OK) return trc;
+    pt_mul_auth_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, vec(s_share), vec(s_mac), pvec(pts, PB), pmvec(o, 2 * PB), pmvec(o + PB, 2 * PB), ts);
     return post_launch(ctx, "pt_mul_auth_kernel");
   }
 #else
@@ -181,7 +221,10 @@ struct CurveLaunch {
     g.key = key;
     g.party = party;
     g.open = d_open != nullptr;
-    pt_beaver_recombine_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, g, gt);
+    TabScratch ts;
+    int trc = tab_scratch(ctx, &ts);
+    if (trc != ARKMPC_OK) return trc;
+    pt_beaver_recombine_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, g, gt, ts);
     return post_launch(ctx, "pt_beaver_recombine_kernel");
   }
 #else
@@ -191,7 +234,10 @@ struct CurveLaunch {
 #if ARK_IN_PART(3)
   {
     const char* a = static_cast<const char*>(a_ps);
-    pt_mac_check_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, key, pvec(opened, PB), pvec(a + PB, 2 * PB), pmvec(check, PB));
+    TabScratch ts;
+    int trc = tab_scratch(ctx, &ts);
+    if (trc != ARKMPC_OK) return trc;
+    pt_mac_check_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, key, pvec(opened, PB), pvec(a + PB, 2 * PB), pmvec(check, PB), ts);
     return post_launch(ctx, "pt_mac_check_kernel");
   }
 #else

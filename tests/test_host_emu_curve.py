@@ -116,9 +116,16 @@ def test_scalar_mul(emu, Cv, cid):
     # identity base
     got = from_proj(Cv, fq_out(Cv, emu(Cv, cid, 3, [12345], [to_proj(Cv, Cv.identity, rng)], K)))
     assert got == Cv.identity
-    s0, s1 = rng.randrange(r), rng.randrange(r)
-    out = fq_out(Cv, emu(Cv, cid, 10, [s0, s1], [to_proj(Cv, P, rng)], 2 * K))
-    assert from_proj(Cv, out[:K]) == Cv.mul(P, s0) and from_proj(Cv, out[K:]) == Cv.mul(P, s1)
+    # the two-pass form (tables of P and of 2^128 P / 2^68 P, signed windows): scalars around the split point and at both ends
+    pairs = [(rng.randrange(r), rng.randrange(r)), (0, 1), (r - 1, r - 2), ((1 << 128) - 1, 1 << 128), ((1 << 127), (1 << 128) + 1),
+             (8, 9), (0x8888888888888888, 0x7777777777777777), ((1 << 252) - 1, glv_lambda), (r - glv_lambda, glv_lambda + 1),
+             ((1 << 68) - 1, 1 << 68), (int("8" * 63, 16) % r, int("7" * 63, 16) % r)]
+    for s0, s1 in pairs:
+        s0, s1 = s0 % r, s1 % r
+        out = fq_out(Cv, emu(Cv, cid, 10, [s0, s1], [to_proj(Cv, P, rng)], 2 * K))
+        assert from_proj(Cv, out[:K]) == Cv.mul(P, s0) and from_proj(Cv, out[K:]) == Cv.mul(P, s1), f"two-pass s0={s0:x} s1={s1:x}"
+    out = fq_out(Cv, emu(Cv, cid, 10, [5, r - 5], [to_proj(Cv, Cv.identity, rng)], 2 * K))
+    assert from_proj(Cv, out[:K]) == Cv.identity and from_proj(Cv, out[K:]) == Cv.identity
 
 
 @pytest.mark.parametrize("Cv,cid", CURVES)
