@@ -111,6 +111,7 @@ _PROTOS = {
     "arkmpc_pt_beaver_recombine": [_vp, _i, _i, _vp, _sz] + [_vp] * 13,
     "arkmpc_pt_mac_check": [_vp, _i, _vp, _sz, _vp, _vp, _vp],
     "arkmpc_pt_sum_is_identity": [_vp, _i, _sz, _vp, _vp, C.POINTER(_i)],
+    "arkmpc_pt_validate": [_vp, _i, _sz, _vp, C.POINTER(_i)],
     "arkmpc_pt_sum": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_pt_share_sum": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_pt_msm": [_vp, _i, _sz, _vp, _vp, _vp],

@@ -134,6 +134,20 @@ int arkmpc_pt_sum_is_identity(arkmpc_ctx* ctx, int curve, size_t n, const uint64
   return ARKMPC_OK;
 }
 
+int arkmpc_pt_validate(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, int* all_valid_host) {
+  if (!ctx || !all_valid_host) return ARKMPC_ERR_INVALID;
+  *all_valid_host = 1;
+  ARK_PT_PROLOGUE(pts);
+  *ctx->flag_host = 1;
+  ARK_CUDA(ctx, cudaMemcpyAsync(ctx->flag_dev, ctx->flag_host, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = ops->validate(ctx, n, pts, ctx->flag_dev);
+  if (rc != ARKMPC_OK) return rc;
+  ARK_CUDA(ctx, cudaMemcpyAsync(ctx->flag_host, ctx->flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ARK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *all_valid_host = *ctx->flag_host;
+  return ARKMPC_OK;
+}
+
 int arkmpc_pt_share_split(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_ps, uint64_t* share_pts, uint64_t* mac_pts) {
   ARK_PT_PROLOGUE(a_ps);
   ARK_REQUIRE(ctx, aligned32(share_pts) && aligned32(mac_pts), "arrays must be 32-byte aligned");

@@ -89,8 +89,13 @@ struct Bn254G1 {
   // registers, capping them spills and measured slower (profiles/r01f_pt_minblocks_ab.txt)
   static constexpr int kMinBlocks = 1;
   static constexpr bool kGlv = true;         // variable-base multiplications use the endomorphism (x, y) -> (beta x, y), see var_mul_glv
-  static constexpr bool kDualChain = true;   // the recombination's two variable-base passes in lock-step: +5 % (3.94 -> 4.14 M mults/s)
+  // The recombination's two variable-base passes in lock-step were +5 % in round 1 (3.94 -> 4.14 M mults/s), but a lock-step
+  // loop holds twice the inlined additions; with the single-copy loops of round 2 the sequential passes win (profiles/r02f_*).
+  static constexpr bool kDualChain = false;
   static constexpr int kAffWords = 16;  // u32 words per fixed-table entry
+  // threads per block of the two-pass kernels (recombine, mul_authenticated): ONE block per SM whose warps move through the
+  // loop body together (ARK_PHASE_SYNC); 230 registers per thread allow 256 threads
+  static constexpr int kTwoPassBlock = 256;
 
   // reference memory image <-> internal representation: the same (canonical Montgomery residues)
   ARK_DM static void from_image(Pt&) {}
@@ -105,6 +110,24 @@ struct Bn254G1 {
   ARK_DM static void neg(Pt& p) { K::neg(p.Y, p.Y); }
   ARK_DM static void cache(Cached& c, const Pt& p) { c = p; }
   ARK_DM static void cached_neg(Cached& c) { K::neg(c.Y, c.Y); }
+  // Y^2 = X^3 + 3 Z^6 (Jacobian); the identity (Z = 0) is on the curve.  G1 has cofactor 1: on-curve is in-subgroup.
+  ARK_DM static bool on_curve(const Pt& p) {
+    if (is_identity(p)) return true;
+    fe8 y2, x3, z2, z6, b, t;
+    K::sqr(y2, p.Y);
+    K::sqr(x3, p.X);
+    K::mul(x3, x3, p.X);
+    K::sqr(z2, p.Z);
+    K::sqr(z6, z2);
+    K::mul(z6, z6, z2);
+    K::one(b);
+    K::add(t, b, b);
+    K::add(b, t, b);  // 3
+    K::mul(z6, z6, b);
+    K::add(x3, x3, z6);
+    return K::eq(y2, x3);
+  }
+  static constexpr bool kNeedsSubgroupCheck = false;
 
   // dbl-2009-l (2M + 5S); Z = 0 stays Z = 0
   ARK_DM static void dbl(Pt& p, bool = true) {
@@ -244,6 +267,7 @@ struct Ed25519 {
   static constexpr bool kDualChain = false;  // measured slower here (8.68 -> 7.2-7.9 M mults/s): the 128-register build already keeps 16 warps busy
   static constexpr int kMinBlocks = 4;  // 128 registers, <= 216 B of spills, +5 % over the unconstrained 230-register build
   static constexpr int kAffWords = 24;
+  static constexpr int kTwoPassBlock = 512;  // one 16-warp block per SM at 128 registers per thread (see Bn254G1::kTwoPassBlock)
 
   ARK_DM static void from_image(Pt& p) { K::from_image(p.X, p.X); K::from_image(p.Y, p.Y); K::from_image(p.T, p.T); K::from_image(p.Z, p.Z); }
   ARK_DM static void to_image(Pt& p) { K::to_image(p.X, p.X); K::to_image(p.Y, p.Y); K::to_image(p.T, p.T); K::to_image(p.Z, p.Z); }
@@ -270,6 +294,29 @@ struct Ed25519 {
     K::dbl(c.Z2, p.Z);
     K::mul(c.T2d, p.T, k);
   }
+  // extended twisted Edwards, a = -1: Z != 0, T Z = X Y and 2 (Y^2 - X^2) Z^2 = 2 Z^4 + (2d) X^2 Y^2.  The group has cofactor 8:
+  // membership of the prime-order subgroup is checked separately ([l]P = identity).
+  ARK_DM static bool on_curve(const Pt& p) {
+    if (K::is_zero(p.Z)) return false;
+    fe8 x2, y2, z2, l, r, t, k;
+    K::mul(l, p.T, p.Z);
+    K::mul(r, p.X, p.Y);
+    if (!K::eq(l, r)) return false;
+    K::sqr(x2, p.X);
+    K::sqr(y2, p.Y);
+    K::sqr(z2, p.Z);
+    K::sub(l, y2, x2);
+    K::mul(l, l, z2);
+    K::dbl(l, l);
+    K::sqr(r, z2);
+    K::dbl(r, r);
+    set_2d(k);
+    K::mul(t, x2, y2);
+    K::mul(t, t, k);
+    K::add(r, r, t);
+    return K::eq(l, r);
+  }
+  static constexpr bool kNeedsSubgroupCheck = true;
   ARK_DM static void cached_neg(Cached& c) {  // -(X, Y, T, Z) = (-X, Y, -T, Z): swap Y+X and Y-X, negate 2dT
     const fe8 t = c.YpX;
     c.YpX = c.YmX;
@@ -604,28 +651,34 @@ ARK_D void glv_recode(uint32_t* kk, const uint32_t* k) {
   kk[4] = (uint32_t)(c + k[4] + 0x8u);
 }
 
+// CODE SIZE is the first-order concern in these loops: every field multiplication is ~110-300 inlined instructions, a point
+// addition 900 (Edwards) to 3500 (Jacobian), and a hot loop that does not fit the instruction caches stalls on instruction
+// fetch (ncu `stalled_no_instruction` was the top stall of every variant with several inlined additions per window;
+// profiles/r02e_*).  Each loop below therefore contains exactly ONE copy of the doubling and ONE copy of the addition: the
+// per-window additions are iterations of an inner `unroll 1` loop that only selects operands.
 template <class C, class Tab>
 ARK_D void var_mul_glv(typename C::Pt& acc, const Tab& tab, const uint32_t* k) {
-  uint32_t k1[5], k2[5], r1[5], r2[5];
-  bool n1, n2;
-  glv_decompose_bn254(k, k1, n1, k2, n2);
-  glv_recode(r1, k1);
-  glv_recode(r2, k2);
+  uint32_t k1[5], k2[5], r[2][5];
+  bool n[2];
+  glv_decompose_bn254(k, k1, n[0], k2, n[1]);
+  glv_recode(r[0], k1);
+  glv_recode(r[1], k2);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
   for (int i = kGlvWindows - 1; i >= 0; i--) {
-    const int d1 = glv_digit(r1, i), d2 = glv_digit(r2, i);
-    prefetch_signed(tab, d1);
-    prefetch_signed(tab, d2);
+    prefetch_signed(tab, glv_digit(r[0], i));
+    prefetch_signed(tab, glv_digit(r[1], i));
     if (i != kGlvWindows - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
       for (int j = 0; j < 4; j++) C::dbl(acc, j == 3);
     }
-    glv_add<C>(acc, tab, d1, false, n1);
-    glv_add<C>(acc, tab, d2, true, n2);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int t = 0; t < 2; t++) glv_add<C>(acc, tab, glv_digit(r[t], i), t == 1, n[t]);
   }
 }
 
@@ -670,6 +723,16 @@ ARK_D void var_mul2_glv(typename C::Pt& acc0, typename C::Pt& acc1, const Tab& t
 // and each pass then runs over half the windows with two additions per window: for 256-bit scalars 128 + 2 x 124 doublings
 // instead of 2 x 252 (Edwards), for the 33-window GLV halves 68 + 2 x 64 instead of 2 x 128 (BN254).  Additions are unchanged.
 // ----------------------------------------------------------------------------------------------
+// ARK_PHASE_SYNC: the warps of a block re-converge after every point operation of the two-pass loops.  The loop body (one
+// doubling + one addition, 35 KB of SASS on Curve25519, 110 KB on BN254) is larger than the SM's 32 KB instruction cache and is
+// walked cyclically, the worst case for an LRU cache: every line misses, for every warp.  Keeping the block's warps within one
+// operation of each other makes one fetch from L2 serve all of them.  The callers make the trip counts uniform per block.
+#if defined(__CUDA_ARCH__) && !defined(ARK_NO_PHASE_SYNC)
+#define ARK_PHASE_SYNC() __syncthreads()
+#else
+#define ARK_PHASE_SYNC() do { } while (0)
+#endif
+
 constexpr int kSplitWindows = kWindows / 2;            // 32 windows = 128 bits
 constexpr int kGlvSplitWindows = (kGlvWindows + 1) / 2;  // 17 windows = 68 bits
 
@@ -688,32 +751,40 @@ ARK_D int split_shift_windows() { return C::kGlv ? kGlvSplitWindows : kSplitWind
 template <class C, class Tab>
 ARK_D void var_mul_split(typename C::Pt& acc, const Tab& lo, const Tab& hi, const uint32_t* k) {
   if constexpr (C::kGlv) {
-    uint32_t k1[5], k2[5], r1[5], r2[5];
-    bool n1, n2;
-    glv_decompose_bn254(k, k1, n1, k2, n2);
-    glv_recode(r1, k1);
-    glv_recode(r2, k2);
+    uint32_t k1[5], k2[5], r[2][5];
+    bool n[2];
+    glv_decompose_bn254(k, k1, n[0], k2, n[1]);
+    glv_recode(r[0], k1);
+    glv_recode(r[1], k2);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
     for (int i = kGlvSplitWindows - 1; i >= 0; i--) {
-      const bool has_hi = i + kGlvSplitWindows < kGlvWindows;
-      const int l1 = glv_digit(r1, i), l2 = glv_digit(r2, i);
-      const int h1 = has_hi ? glv_digit(r1, i + kGlvSplitWindows) : 0, h2 = has_hi ? glv_digit(r2, i + kGlvSplitWindows) : 0;
-      prefetch_signed(lo, l1);
-      prefetch_signed(lo, l2);
-      prefetch_signed(hi, h1);
-      prefetch_signed(hi, h2);
+      const int ih = i + kGlvSplitWindows;  // the top half has one window fewer: window 33 does not exist
+      prefetch_signed(lo, glv_digit(r[0], i));
+      prefetch_signed(lo, glv_digit(r[1], i));
+      if (ih < kGlvWindows) {
+        prefetch_signed(hi, glv_digit(r[0], ih));
+        prefetch_signed(hi, glv_digit(r[1], ih));
+      }
       if (i != kGlvSplitWindows - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-        for (int j = 0; j < 4; j++) C::dbl(acc, j == 3);
+        for (int j = 0; j < 4; j++) {
+          ARK_PHASE_SYNC();
+          C::dbl(acc, j == 3);
+        }
       }
-      glv_add<C>(acc, lo, l1, false, n1);
-      glv_add<C>(acc, lo, l2, true, n2);
-      glv_add<C>(acc, hi, h1, false, n1);
-      glv_add<C>(acc, hi, h2, true, n2);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+      for (int t = 0; t < 4; t++) {  // (k1, lo) (k2, lo) (k1, hi) (k2, hi): one inlined addition serves all four
+        const int w = (t & 2) ? ih : i;
+        const int digit = w < kGlvWindows ? glv_digit(r[t & 1], w) : 0;
+        ARK_PHASE_SYNC();
+        glv_add<C>(acc, (t & 2) ? hi : lo, digit, (t & 1) != 0, n[t & 1]);
+      }
     }
   } else {
     uint32_t kk[8];
@@ -722,17 +793,24 @@ ARK_D void var_mul_split(typename C::Pt& acc, const Tab& lo, const Tab& hi, cons
 #pragma unroll 1
 #endif
     for (int i = kSplitWindows - 1; i >= 0; i--) {
-      const int dl = (int)window4(kk, i) - 8, dh = (int)window4(kk, i + kSplitWindows) - 8;
-      prefetch_signed(lo, dl);
-      prefetch_signed(hi, dh);
+      prefetch_signed(lo, (int)window4(kk, i) - 8);
+      prefetch_signed(hi, (int)window4(kk, i + kSplitWindows) - 8);
       if (i != kSplitWindows - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-        for (int j = 0; j < 4; j++) C::dbl(acc, j == 3);
+        for (int j = 0; j < 4; j++) {
+          ARK_PHASE_SYNC();
+          C::dbl(acc, j == 3);
+        }
       }
-      add_signed<C>(acc, lo, dl);
-      add_signed<C>(acc, hi, dh);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+      for (int t = 0; t < 2; t++) {
+        ARK_PHASE_SYNC();
+        add_signed<C>(acc, t ? hi : lo, (int)window4(kk, i + (t ? kSplitWindows : 0)) - 8);
+      }
     }
   }
 }

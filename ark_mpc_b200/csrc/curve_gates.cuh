@@ -40,10 +40,14 @@ ARK_D void pt_mul_elem(typename C::Pt& out, const fe8& s, const typename C::Pt& 
 // tables of P and of P' = 2^s P for the split two-pass multiplications (curve.cuh)
 template <class C, class Tab>
 ARK_D void build_split_tables(Tab& lo, Tab& hi, const typename C::Pt& P) {
-  build_table<C>(lo, P);
-  typename C::Pt P2 = P;
-  shift_windows<C>(P2, split_shift_windows<C>());
-  build_table<C>(hi, P2);
+  typename C::Pt Q = P;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int h = 0; h < 2; h++) {  // one inlined copy of the table construction
+    if (h) shift_windows<C>(Q, split_shift_windows<C>());
+    build_table<C>(h ? hi : lo, Q);
+  }
 }
 
 // (out0, out1) = (s0 * P, s1 * P): the two passes share the tables of P and 2^s P
@@ -105,6 +109,29 @@ template <class C>
 ARK_D void pt_mac_check_elem(typename C::Pt& out, const fe8& key, const typename C::Pt& opened, const typename C::Pt& mac) {
   LocalTab<C> tab;
   pt_mac_check_elem<C>(tab, out, key, opened, mac);
+}
+
+// What arkworks' point deserialisation enforces on values from the peer (curve.rs:105-135: on the curve AND in the prime-order
+// subgroup) and what the regrouped recombination relies on for E_peer (scalars are combined mod r before multiplying).
+template <class C, class Tab>
+ARK_D bool pt_valid_elem(Tab& tab, const typename C::Pt& P) {
+  if (!C::on_curve(P)) return false;
+  if constexpr (C::kNeedsSubgroupCheck) {
+    // [r]P with the UNREDUCED group order as the scalar (var_mul only needs k < 2^254)
+    using R = typename C::R;
+    const uint32_t k[8] = {R::P0, R::P1, R::P2, R::P3, R::P4, R::P5, R::P6, R::P7};
+    typename C::Pt acc;
+    build_table<C>(tab, P);
+    C::set_identity(acc);
+    var_mul<C>(acc, tab, k);
+    return C::is_identity(acc);
+  }
+  return true;
+}
+template <class C>
+ARK_D bool pt_valid_elem(const typename C::Pt& P) {
+  LocalTab<C> tab;
+  return pt_valid_elem<C>(tab, P);
 }
 
 template <class C>

@@ -85,18 +85,24 @@ struct GlobalTab {
   __device__ __forceinline__ void prefetch(int idx) const { asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + idx * 128)); }
 };
 
-// all threads of the block call both; `token` identifies the slot between claim and release
+// All threads of the block call both; `token` identifies the claim between the two.  A block of B = 128 u threads claims u
+// consecutive units (aligned to u) of its SM's kTabSlotsPerSm units.
 template <class C>
 __device__ __forceinline__ GlobalTab<C> tab_claim(const TabScratch& ts, unsigned int& token) {
   __shared__ unsigned int s_token;
+  const unsigned int units = blockDim.x / kPtBlock;
   if (threadIdx.x == 0) {
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned int want = (1u << units) - 1u;
     unsigned int b = 0;
-    for (;;) {  // more resident blocks than slots simply wait for one to be released
-      const unsigned int bit = 1u << b;
-      if (!(atomicOr(ts.masks + smid, bit) & bit)) break;
-      b = (b + 1) % kTabSlotsPerSm;
+    for (;;) {  // more resident blocks than units simply wait for one to be released
+      const unsigned int bits = want << b;
+      const unsigned int old = atomicOr(ts.masks + smid, bits);
+      if (!(old & bits)) break;
+      atomicAnd(ts.masks + smid, ~(bits & ~old));  // give back the units that were free before our attempt
+      b += units;
+      if (b + units > (unsigned)kTabSlotsPerSm) b = 0;
     }
     s_token = smid * kTabSlotsPerSm + b;
   }
@@ -106,7 +112,10 @@ __device__ __forceinline__ GlobalTab<C> tab_claim(const TabScratch& ts, unsigned
 }
 __device__ __forceinline__ void tab_release(const TabScratch& ts, unsigned int token) {
   __syncthreads();
-  if (threadIdx.x == 0) atomicAnd(ts.masks + token / kTabSlotsPerSm, ~(1u << (token % kTabSlotsPerSm)));
+  if (threadIdx.x == 0) {
+    const unsigned int units = blockDim.x / kPtBlock;
+    atomicAnd(ts.masks + token / kTabSlotsPerSm, ~(((1u << units) - 1u) << (token % kTabSlotsPerSm)));
+  }
 }
 
 static __global__ void nsmid_kernel(unsigned int* out) {
@@ -186,20 +195,25 @@ __global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_mul_kernel(size_t 
 
 // out[i] = (s_share[i] * P[i], s_mac[i] * P[i])   (batch_mul_authenticated curve.rs:483-517)
 template <class C>
-__global__ void __launch_bounds__(kPtBlock) pt_mul_auth_kernel(size_t n, Vec s_share, Vec s_mac, PVec P, PMVec out_s, PMVec out_m, TabScratch ts) {
+__global__ void __launch_bounds__(C::kTwoPassBlock, 1) pt_mul_auth_kernel(size_t n, Vec s_share, Vec s_mac, PVec P, PMVec out_s, PMVec out_m, TabScratch ts) {
   unsigned int token;
   GlobalTab<C> tab = tab_claim<C>(ts, token);
-  const size_t step = (size_t)gridDim.x * kPtBlock;
-  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+  GlobalTab<C> tab_hi{tab.rec + kTabHalfBytes};
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  // block-uniform trip count (the two-pass loops synchronise the block, ARK_PHASE_SYNC): idle lanes recompute element n-1
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += step) {
+    const bool live = base + threadIdx.x < n;
+    const size_t i = live ? base + threadIdx.x : n - 1;
     typename C::Pt x, r0, r1;
     fe8 k0, k1;
     ld_pt<C>(x, P, i);
     ld_fe(k0, s_share, i);
     ld_fe(k1, s_mac, i);
-    GlobalTab<C> tab_hi{tab.rec + kTabHalfBytes};
     pt_mul2_elem<C>(tab, tab_hi, r0, r1, k0, k1, x);
-    st_pt<C>(out_s, i, r0);
-    st_pt<C>(out_m, i, r1);
+    if (live) {
+      st_pt<C>(out_s, i, r0);
+      st_pt<C>(out_m, i, r1);
+    }
   }
   tab_release(ts, token);
 }
@@ -265,6 +279,22 @@ __global__ void __launch_bounds__(kPtBlock) pt_sum_is_identity_kernel(size_t n, 
   if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(flag, 0);
 }
 
+// flag (initialised to 1) is cleared if any point is off the curve or outside the prime-order subgroup
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_validate_kernel(size_t n, PVec a, int* flag, TabScratch ts) {
+  unsigned int token;
+  GlobalTab<C> tab = tab_claim<C>(ts, token);
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  bool ok = true;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt x;
+    ld_pt<C>(x, a, i);
+    ok = ok && pt_valid_elem<C>(tab, x);
+  }
+  if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(flag, 0);
+  tab_release(ts, token);
+}
+
 // affine (x, y), 64 B per point; parity with the reference is defined on this form
 template <class C>
 __global__ void __launch_bounds__(kPtBlock) pt_normalize_kernel(size_t n, PVec a, MVec out_x, MVec out_y) {
@@ -311,12 +341,16 @@ struct PtRecombineArgs {
 };
 
 template <class C>
-__global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_beaver_recombine_kernel(size_t n, const __grid_constant__ PtRecombineArgs g,
+__global__ void __launch_bounds__(C::kTwoPassBlock, 1) pt_beaver_recombine_kernel(size_t n, const __grid_constant__ PtRecombineArgs g,
                                                                       const typename C::Aff* __restrict__ gtab, TabScratch ts) {
   unsigned int token;
   GlobalTab<C> tab = tab_claim<C>(ts, token);
-  const size_t step = (size_t)gridDim.x * kPtBlock;
-  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+  GlobalTab<C> tab_hi{tab.rec + kTabHalfBytes};
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  // block-uniform trip count (the two-pass loops synchronise the block, ARK_PHASE_SYNC): idle lanes recompute element n-1
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += step) {
+    const bool live = base + threadIdx.x < n;
+    const size_t i = live ? base + threadIdx.x : n - 1;
     fe8 dm, dp, as, am, bs, bm, cs, cm, d;
     typename C::Pt Em, Ep, E;
     ld_fe(dm, g.d_mine, i);
@@ -329,10 +363,9 @@ __global__ void __launch_bounds__(kPtBlock, C::kMinBlocks) pt_beaver_recombine_k
     ld_fe(bm, g.b_m, i);
     ld_fe(cs, g.c_s, i);
     ld_fe(cm, g.c_m, i);
-    GlobalTab<C> tab_hi{tab.rec + kTabHalfBytes};
     pt_beaver_recombine_elem<C, C::kDualChain>(tab, tab_hi, d, E, g.party, g.key, dm, dp, Em, Ep, as, am, bs, bm, cs, cm, gtab,
-                                [&](int which, const typename C::Pt& r) { st_pt<C>(which ? g.out_m : g.out_s, i, r); });
-    if (g.open) {
+                                [&](int which, const typename C::Pt& r) { if (live) st_pt<C>(which ? g.out_m : g.out_s, i, r); });
+    if (g.open && live) {
       st_fe(g.d_open, i, d);
       st_pt<C>(g.E_open, i, E);
     }

@@ -22,6 +22,7 @@ struct CurveOps {
                           const void* c_m, void* out_ps, void* d_open, void* E_open);
   int (*mac_check)(arkmpc_ctx*, const ark::fe8& key, size_t n, const void* opened, const void* a_ps, void* check);
   int (*sum_is_identity)(arkmpc_ctx*, size_t n, const void* mine, const void* peer, int* flag_dev);
+  int (*validate)(arkmpc_ctx*, size_t n, const void* pts, int* flag_dev);
   int (*normalize)(arkmpc_ctx*, size_t n, const void* pts, void* out_xy);
   int (*copy)(arkmpc_ctx*, size_t n, const void* in, uint32_t in_stride, void* out, uint32_t out_stride);
   int (*sum)(arkmpc_ctx*, size_t n, const void* in, uint32_t in_stride, void* out_point);
@@ -50,10 +51,10 @@ inline PMVec pmvec(void* p, uint32_t stride) { return PMVec{static_cast<char*>(p
 // One element per thread (hardware block scheduling): measured 6-8 % faster than persistent grids capped at 2-4 resident
 // blocks per SM for the scalar-multiplication kernels (profiles/r01e_pt_grid_ab.txt).  ARKMPC_PT_BLOCKS=k (k > 0) selects a
 // persistent grid of k blocks per SM instead.
-inline unsigned pt_grid(const arkmpc_ctx* ctx, size_t n, int /*blocks_per_sm_hint*/) {
+inline unsigned pt_grid(const arkmpc_ctx* ctx, size_t n, int /*blocks_per_sm_hint*/, int block = kPtBlock) {
   static const int persistent_blocks = [] { const char* v = getenv("ARKMPC_PT_BLOCKS"); return v ? atoi(v) : 0; }();
-  if (persistent_blocks > 0) return grid_for(ctx, n, persistent_blocks, kPtBlock);
-  size_t need = (n + kPtBlock - 1) / kPtBlock;
+  if (persistent_blocks > 0) return grid_for(ctx, n, persistent_blocks, block);
+  size_t need = (n + block - 1) / block;
   return (unsigned)(need < (1u << 30) ? (need ? need : 1) : (1u << 30));
 }
 
@@ -171,7 +172,7 @@ struct CurveLaunch {
     TabScratch ts;
     int trc = tab_scratch(ctx, &ts);
     if (trc != ARKMPC_OK) return trc;
-    pt_mul_auth_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, vec(s_share), vec(s_mac), pvec(pts, PB), pmvec(o, 2 * PB), pmvec(o + PB, 2 * PB), ts);
+    pt_mul_auth_kernel<C><<<pt_grid(ctx, n, 1, C::kTwoPassBlock), C::kTwoPassBlock, 0, ctx->stream>>>(n, vec(s_share), vec(s_mac), pvec(pts, PB), pmvec(o, 2 * PB), pmvec(o + PB, 2 * PB), ts);
     return post_launch(ctx, "pt_mul_auth_kernel");
   }
 #else
@@ -224,7 +225,7 @@ struct CurveLaunch {
     TabScratch ts;
     int trc = tab_scratch(ctx, &ts);
     if (trc != ARKMPC_OK) return trc;
-    pt_beaver_recombine_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, g, gt, ts);
+    pt_beaver_recombine_kernel<C><<<pt_grid(ctx, n, 1, C::kTwoPassBlock), C::kTwoPassBlock, 0, ctx->stream>>>(n, g, gt, ts);
     return post_launch(ctx, "pt_beaver_recombine_kernel");
   }
 #else
@@ -248,6 +249,18 @@ struct CurveLaunch {
   {
     pt_sum_is_identity_kernel<C><<<pt_grid(ctx, n, 4), kPtBlock, 0, ctx->stream>>>(n, pvec(mine, PB), pvec(peer, PB), flag_dev);
     return post_launch(ctx, "pt_sum_is_identity_kernel");
+  }
+#else
+  ;
+#endif
+  static int validate(arkmpc_ctx* ctx, size_t n, const void* pts, int* flag_dev)
+#if ARK_IN_PART(0)
+  {
+    TabScratch ts;
+    int trc = tab_scratch(ctx, &ts);
+    if (trc != ARKMPC_OK) return trc;
+    pt_validate_kernel<C><<<pt_grid(ctx, n, 2), kPtBlock, 0, ctx->stream>>>(n, pvec(pts, PB), flag_dev, ts);
+    return post_launch(ctx, "pt_validate_kernel");
   }
 #else
   ;
@@ -358,7 +371,7 @@ struct CurveLaunch {
   static const CurveOps* ops()
 #if ARK_IN_PART(0)
   {
-    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, normalize, copy, sum, msm};
+    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, validate, normalize, copy, sum, msm};
     return &t;
   }
 #else

@@ -356,6 +356,13 @@ class Engine:
         self._call("arkmpc_pt_sum_is_identity", self._curve(), mine.shape[0], self._p(mine), self._p(peer), C.byref(flag))
         return bool(flag.value)
 
+    def pt_validate(self, pts) -> bool:
+        """True iff every point is on the curve and in the prime-order subgroup (what the recombination needs of E_peer)."""
+        flag = C.c_int(0)
+        n = pts.numel() * 8 // int(self.lib.arkmpc_point_bytes(self._curve()))
+        self._call("arkmpc_pt_validate", self.curve, n, self._p(pts), C.byref(flag))
+        return bool(flag.value)
+
     def pt_sum(self, pts) -> torch.Tensor:
         out = self.empty_points(1)
         n = pts.numel() * 8 // int(self.lib.arkmpc_point_bytes(self._curve()))

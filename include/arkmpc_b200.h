@@ -330,6 +330,12 @@ int arkmpc_pt_share_sum(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_
 int arkmpc_pt_msm(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* scalars, const uint64_t* pts, uint64_t* out_pt);
 int arkmpc_pt_msm_authenticated(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* s_share, const uint64_t* s_mac,
                                 const uint64_t* pts, uint64_t* out_ps);
+/* *all_valid_host = 1 iff every point is on the curve AND in the prime-order subgroup ([r]P = identity; BN254 G1 has cofactor
+ * 1, Curve25519 has cofactor 8): the check arkworks' deserialisation applies to points that arrive from the peer
+ * (curve.rs:105-135).  arkmpc_pt_beaver_recombine regroups the reference's scalar multiplications as
+ * ((a + d) mod r) * E, which equals a*E + d*E only for E in the prime-order subgroup: a shim validates E_peer (or takes it
+ * from a validating deserialiser) before the recombination.  One scalar multiplication per point on Curve25519.  Synchronous. */
+int arkmpc_pt_validate(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, int* all_valid_host);
 /* PointShare vector <-> separate vectors of share points and mac points (either output of split may be NULL) */
 int arkmpc_pt_share_split(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* a_ps, uint64_t* share_pts, uint64_t* mac_pts);
 int arkmpc_pt_share_join(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* share_pts, const uint64_t* mac_pts, uint64_t* out_ps);

@@ -37,6 +37,8 @@ template <class F> static void run(int op, const uint32_t* in, uint32_t* out, in
     case 11: o[0] = v[0]; Fp<F>::csub_p(o[0]); break;
     case 12: Fp<F>::set_one(o[0]); Fp<F>::set_r2(o[1]); break;
     case 13: Fp<F>::sqr(o[0], v[0]); break;
+    case 17: Fp<F>::inv_plain(o[0], v[0]); break;
+    case 18: Fp<F>::inv_mont(o[0], v[0]); break;
     case 14: if constexpr (F::kBits <= 254) { Fp<F>::mul_ctab_lazy(o[0], tab_of<F>(v[0]), v[1]); } break;  // lazy: s * a / R, any 256-bit a
     case 15: if constexpr (F::kBits <= 254) { Fp<F>::mul_ctab(o[0], tab_of<F>(v[0]), v[1]); } break;
     case 16: if constexpr (F::kBits <= 254) { CTab t = tab_of<F>(v[0]); memcpy(o, &t, sizeof t); } break;       // the table itself (8 elements)
@@ -102,6 +104,7 @@ template <class C> static void run_curve(int op, const uint32_t* in, uint32_t* o
     } break;
     case 11: { Pt p; C::set_generator(p); put(0, p); C::set_identity(p); put(K, p); } break;
     case 12: { Pt p = pt(0); C::neg(p); put(0, p); } break;
+    case 14: { o[0].v[0] = pt_valid_elem<C>(pt(0)) ? 1u : 0u; } break;
   }
 }
 

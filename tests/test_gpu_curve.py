@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import coracle as co
+from oracle import pyoracle as po
 from tests.util import split_aos
 from tests.util_curve import CURVE_BY_ID, CURVE_NAME, TwoPartyPointData, points_from_affine
 
@@ -275,3 +276,33 @@ def test_point_and_ntt_argument_errors(engines):
     assert lib.arkmpc_fr_fft(ctx, 0, 2, 0, p(s), p(s)) == nat.ERR_INVALID                             # in place is not supported
     assert lib.arkmpc_fr_fft(ctx, 0, 40, 0, p(s), p(pts)) == nat.ERR_INVALID                          # domain too large
     assert lib.arkmpc_pt_mul(ctx, 0, 0, None, None, None) == nat.OK                                   # empty batch is a no-op
+
+
+@pytest.mark.parametrize("cv", [0, 1])
+def test_point_validation_rejects_off_curve_and_torsion(cv):
+    """arkmpc_pt_validate: on-curve and prime-order-subgroup membership of points received from the peer (curve.rs:105-135), the
+    precondition of the regrouped recombination.  Curve25519 (cofactor 8): a point with a torsion component is on the curve and
+    must be rejected."""
+    from ark_mpc_b200.engine import Engine
+
+    E = Engine(0, ["bn254_fr", "curve25519_fr"][cv])
+    n = 300
+    pts = E.pt_mul_generator_public(E.random(5, 0, n))
+    assert E.pt_validate(pts)
+    assert E.pt_validate(E.pt_mul_generator_public(E.upload(np.zeros((4, 4), dtype=np.uint64))))  # identities
+    bad = pts.clone()
+    bad[n - 3, 0] += 1  # X coordinate off by one (Montgomery image): off the curve
+    assert not E.pt_validate(bad)
+    if cv == 1:
+        F = po.FIELDS["curve25519_fq"]
+        q = F.p
+        M = lambda v: [(F.to_mont(v) >> (64 * i)) & (2**64 - 1) for i in range(4)]
+        # the order-2 point (0, -1) in extended coordinates (X, Y, T, Z) = (0, -1, 0, 1)
+        t2 = np.array([M(0) + M(q - 1) + M(0) + M(1)], dtype=np.uint64)
+        T2 = E.upload_points(t2)
+        assert not E.pt_validate(T2)
+        mixed = pts.clone()
+        mixed[7:8] = E.pt_add(pts[7:8].contiguous(), T2)  # on the curve, outside the prime-order subgroup
+        assert not E.pt_validate(mixed)
+        assert E.pt_validate(E.pt_add(mixed[7:8].contiguous(), T2))  # adding the order-2 point twice removes it
+    E.close()

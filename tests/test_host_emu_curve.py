@@ -239,3 +239,41 @@ def test_f25519_special_form_field(emu):
     for a in vals[:12] + vals[-6:]:
         inv = run(5, [a])[0]
         assert inv % p == (pow(a, -1, p) if a % p else 0)
+
+
+@pytest.mark.parametrize("Cv,cid", CURVES)
+def test_point_validation_on_curve_and_subgroup(emu, Cv, cid):
+    """pt_valid_elem (arkmpc_pt_validate): what arkworks' deserialisation checks on peer points (curve.rs:105-135) and what the
+    regrouped recombination needs of E_peer.  Curve25519 has cofactor 8: a point with a torsion component is ON the curve but
+    must be rejected; ((a + d) mod r) * E differs from a*E + d*E exactly for such points."""
+    rng = random.Random(99 + cid)
+    q, r = Cv.fq.p, Cv.fr.p
+    valid = lambda c: emu(Cv, cid, 14, [], [c], 1)[0] & 1
+    for _ in range(4):
+        assert valid(to_proj(Cv, rand_point(Cv, rng), rng)) == 1
+    assert valid(to_proj(Cv, Cv.identity, rng)) == 1
+    assert valid(to_proj(Cv, Cv.generator, rng)) == 1
+    # off the curve
+    P = rand_point(Cv, rng)
+    bad = to_proj(Cv, P, rng)
+    bad[0] = (bad[0] + 1) % q
+    if Cv.kind != "sw":
+        bad[2] = bad[0] * bad[1] % q * pow(bad[3], -1, q) % q  # keep T consistent so that only the curve equation fails
+    assert valid(bad) == 0
+    if Cv.kind != "sw":
+        # inconsistent T
+        c = to_proj(Cv, P, rng)
+        c[2] = (c[2] + 1) % q
+        assert valid(c) == 0
+        # torsion: (0, -1) has order 2, (sqrt(-1), 0) has order 4; P + T is on the curve and outside the prime-order subgroup
+        T2 = (0, q - 1)
+        i = pow(2, (q - 1) // 4, q)
+        T4 = (i, 0)
+        for T in (T2, T4):
+            assert Cv.mul(T, 8) == Cv.identity and T != Cv.identity
+            assert valid(to_proj(Cv, T, rng)) == 0
+            PT = Cv.add(P, T)
+            assert valid(to_proj(Cv, PT, rng)) == 0
+            # the reason the guard exists: scalars combined mod r do not act on the torsion component like separate products
+            a, d = r - 1, 2
+            assert Cv.mul(PT, (a + d) % r) != Cv.add(Cv.mul(PT, a), Cv.mul(PT, d))

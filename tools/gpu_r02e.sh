@@ -3,7 +3,7 @@
 TAG=${1:-r02e}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-echo "== pytest -m gpu (curve, fabric, golden)"; timeout 1500 python -m pytest tests -m gpu -x -q -k "curve or fabric or golden or host" > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 $OUT/pytest_gpu.log
+echo "== pytest -m gpu (curve, fabric, golden)"; timeout 1500 python -m pytest tests -m gpu -x -q -k "curve or fabric or golden or host or offline" > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 $OUT/pytest_gpu.log
 echo "== bench_points 17"; timeout 600 python tools/bench_points.py 17 > $OUT/bench_points_17.txt 2>&1; cat $OUT/bench_points_17.txt
 echo "== bench point_mul"; timeout 600 python bench.py --workload point_mul > $OUT/bench_point_mul.json 2> $OUT/bench.err; cat $OUT/bench_point_mul.json
 timeout 600 python bench.py --workload point_mul --field bn254_fr > $OUT/bench_point_mul_bn254.json 2>> $OUT/bench.err; cat $OUT/bench_point_mul_bn254.json
