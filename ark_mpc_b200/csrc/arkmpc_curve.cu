@@ -214,4 +214,10 @@ int arkmpc_pt_normalize(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pt
   return ops->normalize(ctx, n, pts, out_xy);
 }
 
+/* inverse of arkmpc_pt_normalize */
+int arkmpc_pt_from_affine(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* xy, uint64_t* out_pts) {
+  ARK_PT_PROLOGUE(xy, out_pts);
+  return ops->from_affine(ctx, n, xy, out_pts);
+}
+
 }  // extern "C"

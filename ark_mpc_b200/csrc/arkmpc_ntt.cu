@@ -83,9 +83,49 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
   ARK_CHECK_CTX(ctx);
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, a && out && aligned32(a) && aligned32(out), "null or misaligned plane");
-  const size_t groups = (n + kInvGroup - 1) / kInvGroup;
-  ARK_FIELD_SWITCH(ctx, field, (fr_batch_inverse_kernel<F><<<grid_for(ctx, groups, 4), kBlock, 0, ctx->stream>>>(n, groups, vec(a), mvec(out))));
-  return post_launch(ctx, "arkmpc_fr_batch_inverse");
+  ARK_REQUIRE(ctx, field == ARKMPC_BN254_FR || field == ARKMPC_CURVE25519_FR, "unknown field id");
+  // level sizes n_0 = n, n_(l+1) = ceil(n_l / kInvGroup) until <= kInvTop
+  size_t sizes[16];
+  int levels = 0;
+  sizes[0] = n;
+  while (sizes[levels] > kInvTop && levels < 14) {
+    sizes[levels + 1] = (sizes[levels] + kInvGroup - 1) / kInvGroup;
+    levels++;
+  }
+  // scratch: prefix_l (n_l) for l < levels, products x_(l+1) (n_(l+1)) and their inverses (n_(l+1))
+  size_t elems = 0;
+  for (int l = 0; l < levels; l++) elems += sizes[l] + 2 * sizes[l + 1];
+  cudaStream_t s = ctx->stream;
+  char* scratch = nullptr;
+  if (elems) ARK_CUDA(ctx, cudaMallocAsync(&scratch, elems * 32, s));
+  const char* xs[16];
+  char *prefix[16], *inv[16];
+  xs[0] = reinterpret_cast<const char*>(a);
+  inv[0] = reinterpret_cast<char*>(out);
+  char* p = scratch;
+  for (int l = 0; l < levels; l++) {
+    prefix[l] = p; p += sizes[l] * 32;
+    xs[l + 1] = p; p += sizes[l + 1] * 32;
+    inv[l + 1] = p; p += sizes[l + 1] * 32;
+  }
+  auto blocks = [](size_t work) { return (unsigned)((work + kBlock - 1) / kBlock); };
+  int rc = ARKMPC_OK;
+  ARK_FIELD_SWITCH(ctx, field, {
+    for (int l = 0; l < levels && rc == ARKMPC_OK; l++) {
+      fr_inv_up_kernel<F><<<blocks(sizes[l + 1]), kBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(prefix[l]), mvec(const_cast<char*>(xs[l + 1])));
+      rc = post_launch(ctx, "fr_inv_up_kernel");
+    }
+    if (rc == ARKMPC_OK) {
+      fr_inv_top_kernel<F><<<(unsigned)((sizes[levels] + kInvTopBlock - 1) / kInvTopBlock), kInvTopBlock, 0, s>>>(sizes[levels], vec(xs[levels]), mvec(inv[levels]));
+      rc = post_launch(ctx, "fr_inv_top_kernel");
+    }
+    for (int l = levels - 1; l >= 0 && rc == ARKMPC_OK; l--) {
+      fr_inv_down_kernel<F><<<blocks(sizes[l + 1]), kBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(prefix[l]), vec(inv[l + 1]), mvec(inv[l]));
+      rc = post_launch(ctx, "fr_inv_down_kernel");
+    }
+  });
+  if (scratch) cudaFreeAsync(scratch, s);
+  return rc;
 }
 
 int arkmpc_fr_fft(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t* in, uint64_t* out) {

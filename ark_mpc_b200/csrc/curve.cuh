@@ -244,6 +244,13 @@ struct Bn254G1 {
     K::mul(y, p.Y, zi2);
   }
   ARK_DM static void to_aff(Aff& a, const Pt& p) { normalize(a.x, a.y, p); }
+  // inverse of normalize: canonical affine image (Montgomery residues) -> projective point with Z = 1; (0, 0) is the identity
+  ARK_DM static void from_affine(Pt& p, const fe8& x, const fe8& y) {
+    if (K::is_zero(x) && K::is_zero(y)) { set_identity(p); return; }
+    p.X = x;
+    p.Y = y;
+    K::one(p.Z);
+  }
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -400,6 +407,13 @@ struct Ed25519 {
     affine(x, y, p);
     K::to_image(x, x);
     K::to_image(y, y);
+  }
+  // inverse of normalize: canonical affine image (Montgomery residues) -> extended point (x, y, xy, 1), internal residues
+  ARK_DM static void from_affine(Pt& p, const fe8& x, const fe8& y) {
+    K::from_image(p.X, x);
+    K::from_image(p.Y, y);
+    K::mul(p.T, p.X, p.Y);
+    K::one(p.Z);
   }
   ARK_DM static void to_aff(Aff& a, const Pt& p) {
     fe8 x, y, k;

@@ -309,6 +309,20 @@ __global__ void __launch_bounds__(kPtBlock) pt_normalize_kernel(size_t n, PVec a
   }
 }
 
+// inverse of pt_normalize_kernel: affine (x, y) images -> points in the reference's projective image (Z = 1)
+template <class C>
+__global__ void __launch_bounds__(kPtBlock) pt_from_affine_kernel(size_t n, Vec in_x, Vec in_y, PMVec out) {
+  const size_t step = (size_t)gridDim.x * kPtBlock;
+  for (size_t i = (size_t)blockIdx.x * kPtBlock + threadIdx.x; i < n; i += step) {
+    typename C::Pt p;
+    fe8 x, y;
+    ld_fe(x, in_x, i);
+    ld_fe(y, in_y, i);
+    C::from_affine(p, x, y);
+    st_pt<C>(out, i, p);
+  }
+}
+
 // Point Beaver phase 1
 template <class C>
 __global__ void __launch_bounds__(kPtBlock) pt_beaver_mask_kernel(size_t n, Vec x_s, Vec a_s, Vec b_s, PVec P_s,

@@ -23,6 +23,7 @@ struct CurveOps {
   int (*mac_check)(arkmpc_ctx*, const ark::fe8& key, size_t n, const void* opened, const void* a_ps, void* check);
   int (*sum_is_identity)(arkmpc_ctx*, size_t n, const void* mine, const void* peer, int* flag_dev);
   int (*validate)(arkmpc_ctx*, size_t n, const void* pts, int* flag_dev);
+  int (*from_affine)(arkmpc_ctx*, size_t n, const void* xy, void* out_pts);
   int (*normalize)(arkmpc_ctx*, size_t n, const void* pts, void* out_xy);
   int (*copy)(arkmpc_ctx*, size_t n, const void* in, uint32_t in_stride, void* out, uint32_t out_stride);
   int (*sum)(arkmpc_ctx*, size_t n, const void* in, uint32_t in_stride, void* out_point);
@@ -276,6 +277,17 @@ struct CurveLaunch {
   ;
 #endif
 
+  static int from_affine(arkmpc_ctx* ctx, size_t n, const void* xy, void* out_pts)
+#if ARK_IN_PART(0)
+  {
+    const char* i = static_cast<const char*>(xy);
+    pt_from_affine_kernel<C><<<pt_grid(ctx, n, 8), kPtBlock, 0, ctx->stream>>>(n, vec(i, 64), vec(i + 32, 64), pmvec(out_pts, PB));
+    return post_launch(ctx, "pt_from_affine_kernel");
+  }
+#else
+  ;
+#endif
+
   static int copy(arkmpc_ctx* ctx, size_t n, const void* in, uint32_t in_stride, void* out, uint32_t out_stride)
 #if ARK_IN_PART(0)
   {
@@ -371,7 +383,7 @@ struct CurveLaunch {
   static const CurveOps* ops()
 #if ARK_IN_PART(0)
   {
-    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, validate, normalize, copy, sum, msm};
+    static const CurveOps t = {PB, binary, neg, share_add_public, mul, mul_auth, mul_gen, beaver_mask, beaver_recombine, mac_check, sum_is_identity, validate, from_affine, normalize, copy, sum, msm};
     return &t;
   }
 #else

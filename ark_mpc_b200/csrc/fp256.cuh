@@ -468,66 +468,54 @@ struct Fp {
     csub_p(r);
   }
 
-  // a^-1 mod p for 0 < a < p by the binary extended Euclidean algorithm on plain integers (shifts, adds and subtractions only:
-  // ~25 k simple instructions against the ~320 dependent 256-bit multiplications of a Fermat inversion, each of which holds
-  // the wide-multiplier pipe for ~520 cycles even for a lone warp).  Used where ONE inversion is on the critical path (the top
-  // of the batch-inversion product tree).  Not constant time, like the arkworks inversion the reference calls (scalar.rs:93-100).
+  // a^-1 mod p for 0 < a < p: binary extended Euclid on plain integers, BRANCH-FREE with a fixed 2 * kBits iterations, so the 32
+  // lanes of a warp (32 different inputs) never diverge — a data-dependent version measured 127 k warp-instructions (274 us) for
+  // 2048 inversions because every lane waits for the union of all lanes' paths (profiles/r02i_ntt_inverse_full.txt).  Invariants:
+  // x1 * a = u, x2 * a = v (mod p), u odd.  Each iteration makes v even (subtracting the smaller odd value from the larger) and
+  // halves it, so len(u) + len(v) drops by at least one per iteration: 2 * kBits iterations end with v = 0, u = 1, x1 = a^-1.
+  // Shifts, adds and subtractions only: used where ONE inversion sits on the critical path (top of the batch-inversion tree), in
+  // place of a Fermat chain whose ~320 dependent multiplications each hold the wide-multiplier pipe ~520 cycles.
   ARK_DM static void inv_plain(fe8& r, const fe8& a) {
     uint32_t p[8];
     load_p(p);
     uint32_t u[8], v[8], x1[8], x2[8];
-    ARK_UNROLL for (int j = 0; j < 8; j++) { u[j] = a.v[j]; v[j] = p[j]; x1[j] = 0; x2[j] = 0; }
-    x1[0] = 1;
-    // halve x modulo p: x even -> x/2, x odd -> (x + p)/2 (the sum may carry into bit 256)
-    auto half_mod = [&](uint32_t* x) {
-      const uint32_t odd = 0u - (x[0] & 1u);
-      uint64_t c = 0;
-      ARK_UNROLL for (int j = 0; j < 8; j++) { c += (uint64_t)x[j] + (p[j] & odd); x[j] = (uint32_t)c; c >>= 32; }
-      ARK_UNROLL for (int j = 0; j < 7; j++) x[j] = (x[j] >> 1) | (x[j + 1] << 31);
-      x[7] = (x[7] >> 1) | ((uint32_t)c << 31);
-    };
-    auto shr1 = [&](uint32_t* x) {
-      ARK_UNROLL for (int j = 0; j < 7; j++) x[j] = (x[j] >> 1) | (x[j + 1] << 31);
-      x[7] >>= 1;
-    };
-    auto is_one = [&](const uint32_t* x) {
-      uint32_t o = x[0] ^ 1u;
-      ARK_UNROLL for (int j = 1; j < 8; j++) o |= x[j];
-      return o == 0;
-    };
-    auto geq = [&](const uint32_t* x, const uint32_t* y) {  // x >= y
-      uint64_t b = 0;
-      ARK_UNROLL for (int j = 0; j < 8; j++) { const uint64_t t = (uint64_t)x[j] - y[j] - b; b = (t >> 32) & 1u; }
-      return b == 0;
-    };
-    auto sub_in = [&](uint32_t* x, const uint32_t* y) {  // x -= y (x >= y)
-      uint64_t b = 0;
-      ARK_UNROLL for (int j = 0; j < 8; j++) { const uint64_t t = (uint64_t)x[j] - y[j] - b; x[j] = (uint32_t)t; b = (t >> 32) & 1u; }
-    };
-    auto sub_mod = [&](uint32_t* x, const uint32_t* y) {  // x = x - y mod p
-      uint64_t b = 0;
-      ARK_UNROLL for (int j = 0; j < 8; j++) { const uint64_t t = (uint64_t)x[j] - y[j] - b; x[j] = (uint32_t)t; b = (t >> 32) & 1u; }
-      const uint32_t m = 0u - (uint32_t)b;
-      uint64_t c = 0;
-      ARK_UNROLL for (int j = 0; j < 8; j++) { c += (uint64_t)x[j] + (p[j] & m); x[j] = (uint32_t)c; c >>= 32; }
-    };
-    // invariants: x1 * a = u, x2 * a = v (mod p); gcd(u, v) = 1; terminates with u = 1 or v = 1 in at most ~2 * 256 halvings
+    ARK_UNROLL for (int j = 0; j < 8; j++) { u[j] = p[j]; v[j] = a.v[j]; x1[j] = 0; x2[j] = 0; }
+    x2[0] = 1;
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-    for (int guard = 0; guard < 1024 && !is_one(u) && !is_one(v); guard++) {
-#if defined(__CUDACC__)
-#pragma unroll 1
-#endif
-      while (!(u[0] & 1u)) { shr1(u); half_mod(x1); }
-#if defined(__CUDACC__)
-#pragma unroll 1
-#endif
-      while (!(v[0] & 1u)) { shr1(v); half_mod(x2); }
-      if (geq(u, v)) { sub_in(u, v); sub_mod(x1, x2); } else { sub_in(v, u); sub_mod(x2, x1); }
+    for (int it = 0; it < 2 * F::kBits; it++) {
+      const uint32_t odd = 0u - (v[0] & 1u);
+      // v < u ?  (borrow of v - u; carry-chain primitives: one instruction per limb)
+      (void)sub_cc(v[0], u[0]);
+      ARK_UNROLL for (int j = 1; j < 8; j++) (void)subc_cc(v[j], u[j]);
+      const uint32_t sw = odd & subc(0u, 0u);
+      // v odd and v < u: swap (u, v) and (x1, x2), so that the odd value being reduced is the larger one
+      ARK_UNROLL for (int j = 0; j < 8; j++) {
+        const uint32_t tu = (u[j] ^ v[j]) & sw, tx = (x1[j] ^ x2[j]) & sw;
+        u[j] ^= tu; v[j] ^= tu; x1[j] ^= tx; x2[j] ^= tx;
+      }
+      // v odd: v <- v - u (>= 0), x2 <- x2 - x1 mod p
+      v[0] = sub_cc(v[0], u[0] & odd);
+      ARK_UNROLL for (int j = 1; j < 7; j++) v[j] = subc_cc(v[j], u[j] & odd);
+      v[7] = subc(v[7], u[7] & odd);
+      x2[0] = sub_cc(x2[0], x1[0] & odd);
+      ARK_UNROLL for (int j = 1; j < 8; j++) x2[j] = subc_cc(x2[j], x1[j] & odd);
+      const uint32_t neg = subc(0u, 0u);
+      x2[0] = add_cc(x2[0], p[0] & neg);
+      ARK_UNROLL for (int j = 1; j < 7; j++) x2[j] = addc_cc(x2[j], p[j] & neg);
+      x2[7] = addc(x2[7], p[7] & neg);
+      // v is even now: v /= 2, x2 /= 2 mod p (x2 odd -> (x2 + p) / 2, the sum may carry into bit 256)
+      ARK_UNROLL for (int j = 0; j < 7; j++) v[j] = (v[j] >> 1) | (v[j + 1] << 31);
+      v[7] >>= 1;
+      const uint32_t xo = 0u - (x2[0] & 1u);
+      x2[0] = add_cc(x2[0], p[0] & xo);
+      ARK_UNROLL for (int j = 1; j < 8; j++) x2[j] = addc_cc(x2[j], p[j] & xo);
+      const uint32_t top = addc(0u, 0u);
+      ARK_UNROLL for (int j = 0; j < 7; j++) x2[j] = (x2[j] >> 1) | (x2[j + 1] << 31);
+      x2[7] = (x2[7] >> 1) | (top << 31);
     }
-    const bool from_u = is_one(u);
-    ARK_UNROLL for (int j = 0; j < 8; j++) r.v[j] = from_u ? x1[j] : x2[j];
+    ARK_UNROLL for (int j = 0; j < 8; j++) r.v[j] = x1[j];
   }
 
   // Montgomery image of a^-1 from the Montgomery image of a != 0: (aR)^-1 = a^-1 R^-1, then two multiplications by R^2

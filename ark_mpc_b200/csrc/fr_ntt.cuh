@@ -13,45 +13,90 @@
 namespace ark {
 
 // ---------------------------------------------------------------------------------------------
-// Batch inversion, Montgomery's trick per thread: K elements share one Fermat inversion (~380 multiplications),
-// so an element costs 3 + 380/K multiplications (K = 32: the prefix products live in 1 KiB of local memory per thread).  Element j of group g is a[g + j*groups]: coalesced across threads.
+// Batch inversion (scalar.rs:93-100 -> ark_ff::batch_inversion: zeros stay zero): Montgomery's trick as a product TREE.
+//   up    every thread multiplies a group of kInvGroup elements (element j of group g is x[g + j*groups]: coalesced), stores the
+//         running products and hands the group product to the next level; levels shrink by kInvGroup until <= kInvTop remain;
+//   top   one binary-Euclid inversion per remaining element (Fp::inv_mont: no multiplications on the critical path);
+//   down  every thread walks its group backwards: inverse_j = I * prefix_(j-1), I *= x_j.
+// 3 multiplications per element (the minimum of the trick) at full occupancy at every batch size, and ONE inversion latency on the
+// critical path — round 1 ran a 380-multiplication Fermat chain per 32 elements on n/32 threads: 320 us at n = 2^16 and at 2^20.
 // ---------------------------------------------------------------------------------------------
-constexpr int kInvGroup = 32;  // 3 + 380/32 = 15 multiplications per element (16 per group measured 1.5x slower, profiles/r01g_inverse_ab.txt)
+constexpr int kInvGroup = 8;
+constexpr size_t kInvTop = 2048;
+
+// Both sweeps issue all the loads of a group before the first multiplication: the upper levels of the tree are a few thousand
+// threads, nothing hides a load there, and eight serial load-multiply round trips cost 12 us per level (profiles/r02i_*).
+template <class F>
+__global__ void __launch_bounds__(kBlock) fr_inv_up_kernel(size_t n, size_t groups, Vec x, MVec prefix, MVec prod) {
+  const size_t g = (size_t)blockIdx.x * kBlock + threadIdx.x;
+  if (g >= groups) return;
+  fe8 v[kInvGroup];
+#pragma unroll
+  for (int j = 0; j < kInvGroup; j++) {
+    const size_t i = g + (size_t)j * groups;
+    if (i < n) ld_fe(v[j], x, i); else Fp<F>::set_zero(v[j]);
+  }
+  fe8 acc;
+  Fp<F>::set_one(acc);
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < kInvGroup; j++) {
+    const size_t i = g + (size_t)j * groups;
+    if (i < n) {
+      if (!Fp<F>::is_zero(v[j])) {  // zeros are skipped, as ark_ff::batch_inversion does
+        if (any) Fp<F>::mul(acc, acc, v[j]); else acc = v[j];
+        any = true;
+      }
+      st_fe(prefix, i, acc);
+    }
+  }
+  st_fe(prod, g, acc);
+}
+
+// One warp per block: the <= 2048 inversions at the top are latency-bound, so they are spread over as many SMs as there are warps.
+constexpr int kInvTopBlock = 32;
+template <class F>
+__global__ void __launch_bounds__(kInvTopBlock) fr_inv_top_kernel(size_t n, Vec x, MVec out) {
+  const size_t i = (size_t)blockIdx.x * kInvTopBlock + threadIdx.x;
+  if (i >= n) return;
+  fe8 v, r;
+  ld_fe(v, x, i);
+  if (Fp<F>::is_zero(v)) r = v; else Fp<F>::inv_mont(r, v);
+  st_fe(out, i, r);
+}
 
 template <class F>
-__global__ void __launch_bounds__(kBlock) fr_batch_inverse_kernel(size_t n, size_t groups, Vec a, MVec out) {
-  const size_t step = (size_t)gridDim.x * kBlock;
-  fe8 one;
-  Fp<F>::set_one(one);
-  for (size_t g = (size_t)blockIdx.x * kBlock + threadIdx.x; g < groups; g += step) {
-    fe8 prefix[kInvGroup];
-    fe8 acc = one;
-#pragma unroll 1
-    for (int j = 0; j < kInvGroup; j++) {
-      const size_t i = g + (size_t)j * groups;
-      if (i < n) {
-        fe8 x;
-        ld_fe(x, a, i);
-        if (!Fp<F>::is_zero(x)) Fp<F>::mul(acc, acc, x);
-      }
-      prefix[j] = acc;
+__global__ void __launch_bounds__(kBlock) fr_inv_down_kernel(size_t n, size_t groups, Vec x, Vec prefix, Vec ginv, MVec out) {
+  const size_t g = (size_t)blockIdx.x * kBlock + threadIdx.x;
+  if (g >= groups) return;
+  fe8 inv, v[kInvGroup], pre[kInvGroup];
+  ld_fe(inv, ginv, g);
+#pragma unroll
+  for (int j = 0; j < kInvGroup; j++) {
+    const size_t i = g + (size_t)j * groups;
+    if (i < n) {
+      ld_fe(v[j], x, i);
+      if (j > 0) ld_fe(pre[j], prefix, i - groups);  // product of the nonzero elements before this one (one, if there are none)
+    } else {
+      Fp<F>::set_zero(v[j]);
     }
-    fe8 inv;
-    Fq<F>::inv(inv, acc);
-#pragma unroll 1
-    for (int j = kInvGroup - 1; j >= 0; j--) {
-      const size_t i = g + (size_t)j * groups;
-      if (i >= n) continue;
-      fe8 x, r;
-      ld_fe(x, a, i);
-      if (Fp<F>::is_zero(x)) {  // ark_ff::batch_inversion leaves zeros untouched
-        st_fe(out, i, x);
-        continue;
-      }
-      if (j == 0) r = inv; else Fp<F>::mul(r, inv, prefix[j - 1]);
-      Fp<F>::mul(inv, inv, x);
-      st_fe(out, i, r);
+  }
+#pragma unroll
+  for (int j = kInvGroup - 1; j >= 0; j--) {
+    const size_t i = g + (size_t)j * groups;
+    if (i >= n) continue;
+    if (Fp<F>::is_zero(v[j])) {  // zeros stay zero
+      st_fe(out, i, v[j]);
+      continue;
     }
+    fe8 r;
+    if (j == 0) {
+      r = inv;
+    } else {
+      Fp<F>::mul(r, inv, pre[j]);
+      Fp<F>::mul(inv, inv, v[j]);
+    }
+    st_fe(out, i, r);
   }
 }
 
@@ -117,7 +162,7 @@ __global__ void __launch_bounds__(kBlock) fr_ntt_twiddle_kernel(size_t half, con
 
 constexpr int kNttTileLog = 10;               // 1024 elements (32 KiB) per block in shared memory
 constexpr int kNttTile = 1 << kNttTileLog;
-constexpr int kNttThreads = kNttTile / 2;     // one butterfly per thread per stage
+constexpr int kNttThreads = kNttTile / 4;     // one radix-4 group (two stages of two butterflies) per thread per double stage
 
 template <class F>
 __device__ __forceinline__ void ntt_butterfly(fe8& lo, fe8& hi, const fe8& w) {
@@ -130,15 +175,20 @@ __device__ __forceinline__ void ntt_butterfly(fe8& lo, fe8& hi, const fe8& w) {
 }
 
 // Stages 1..min(log2n, 10): a bit-reversed gather of one tile into shared memory, the butterflies in place, a coalesced store.
-// Twiddle of butterfly j in stage s: w^(j * n / 2^s) = tw[j << (log2n - s)].
+// Twiddle of butterfly j in stage s: w^(j * n / 2^s) = tw[j << (log2n - s)]; the tile's 2^tile_log-th roots of unity are staged in
+// shared memory once.  Stages are taken two at a time: a thread owns the four elements {b, b + h, b + 2h, b + 3h} (h = 2^(s-1)),
+// runs the two butterflies of stage s and the two of stage s + 1 in registers, and the block synchronises once per PAIR of
+// stages — half the barriers and half the shared-memory round trips of one butterfly per thread per stage.
 template <class F>
 __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec in, Vec tw, MVec out) {
   extern __shared__ __align__(32) unsigned char ntt_smem[];
+  __shared__ __align__(32) fe8 stw[kNttTile / 2];  // stw[k] = w^(k n / 2^tile_log)
   fe8* x = reinterpret_cast<fe8*>(ntt_smem);
   const int tile_log = log2n < kNttTileLog ? log2n : kNttTileLog;
   const size_t tile = (size_t)1 << tile_log;
   const size_t base = (size_t)blockIdx.x * tile;
   const int t = threadIdx.x;
+  for (size_t k = t; k < tile / 2; k += kNttThreads) ld_fe(stw[k], tw, k << (log2n - tile_log));
   // gather: out position p <- in[bitrev(p)]
   for (size_t e = t; e < tile; e += kNttThreads) {
     const size_t p = base + e;
@@ -146,14 +196,28 @@ __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec
     ld_fe(x[e], in, src);
   }
   __syncthreads();
-  for (int s = 1; s <= tile_log; s++) {
-    const size_t half = (size_t)1 << (s - 1);
-    for (size_t b = t; b < tile / 2; b += kNttThreads) {
-      const size_t j = b & (half - 1);
-      const size_t i0 = ((b >> (s - 1)) << s) + j;
-      fe8 w;
-      ld_fe(w, tw, j << (log2n - s));
-      ntt_butterfly<F>(x[i0], x[i0 + half], w);
+  int s = 1;
+  for (; s + 1 <= tile_log; s += 2) {
+    const size_t h = (size_t)1 << (s - 1);
+    for (size_t q = t; q < tile / 4; q += kNttThreads) {
+      const size_t j = q & (h - 1);
+      const size_t b = ((q >> (s - 1)) << (s + 1)) + j;
+      fe8 e0 = x[b], e1 = x[b + h], e2 = x[b + 2 * h], e3 = x[b + 3 * h];
+      const fe8 w1 = stw[j << (tile_log - s)];                 // stage s: both butterflies use w^(j n / 2^s)
+      ntt_butterfly<F>(e0, e1, w1);
+      ntt_butterfly<F>(e2, e3, w1);
+      ntt_butterfly<F>(e0, e2, stw[j << (tile_log - s - 1)]);         // stage s + 1: positions j and j + h
+      ntt_butterfly<F>(e1, e3, stw[(j + h) << (tile_log - s - 1)]);
+      x[b] = e0; x[b + h] = e1; x[b + 2 * h] = e2; x[b + 3 * h] = e3;
+    }
+    __syncthreads();
+  }
+  if (s <= tile_log) {  // an odd number of stages: the last one on its own
+    const size_t h = (size_t)1 << (s - 1);
+    for (size_t b2 = t; b2 < tile / 2; b2 += kNttThreads) {
+      const size_t j = b2 & (h - 1);
+      const size_t i0 = ((b2 >> (s - 1)) << s) + j;
+      ntt_butterfly<F>(x[i0], x[i0 + h], stw[j << (tile_log - s)]);
     }
     __syncthreads();
   }
@@ -179,15 +243,22 @@ __global__ void __launch_bounds__(kNttStrideThreads) fr_ntt_strided_kernel(int l
   const Vec xr{x.p, x.stride};
   for (int k = row; k < rows; k += kNttStrideThreads / 32) ld_fe(sm[k * 32 + lane], xr, base + ((size_t)k << s0));
   __syncthreads();
+  // One butterfly per thread per level when T = 5; the twiddle of the NEXT level is requested before this level's arithmetic so
+  // that its L2 round trip overlaps the multiplication and the barrier (long-scoreboard was the top stall, profiles/r02i_*).
+  auto tw_index = [&](int t, int b) -> size_t {
+    const int kl = b & ((1 << (t - 1)) - 1);
+    return (((size_t)kl << s0) + lo) << (log2n - (s0 + t));  // j << (log2n - s), j = i0 mod 2^(s-1)
+  };
+  fe8 w_next;
+  if (row < rows / 2) ld_fe(w_next, tw, tw_index(1, row));
   for (int t = 1; t <= T; t++) {
-    const int s = s0 + t;
     const int halfk = 1 << (t - 1);
     for (int b = row; b < rows / 2; b += kNttStrideThreads / 32) {
+      fe8 w;
+      if (b == row) w = w_next; else ld_fe(w, tw, tw_index(t, b));
+      if (b == row && t < T) ld_fe(w_next, tw, tw_index(t + 1, row));
       const int kl = b & (halfk - 1);
       const int k = ((b >> (t - 1)) << t) + kl;
-      const size_t j = ((size_t)kl << s0) + lo;           // i0 mod 2^(s-1)
-      fe8 w;
-      ld_fe(w, tw, j << (log2n - s));
       ntt_butterfly<F>(sm[k * 32 + lane], sm[(k + halfk) * 32 + lane], w);
     }
     __syncthreads();

@@ -392,6 +392,13 @@ class Engine:
         self._call("arkmpc_pt_normalize", self.curve, n, self._p(pts), self._p(out))
         return out
 
+    def pt_from_affine(self, xy) -> torch.Tensor:
+        """(n, 8) canonical affine (x, y) Montgomery limbs -> (n, words) projective image with Z = 1."""
+        n = xy.shape[0]
+        out = self.empty_points(n)
+        self._call("arkmpc_pt_from_affine", self.curve, n, self._p(xy), self._p(out))
+        return out
+
     # -- layout ---------------------------------------------------------------------------------
     def share_unzip(self, aos: torch.Tensor) -> Planes:
         """(n, 8) AoS ScalarShare image -> (share, mac) planes."""

@@ -22,6 +22,8 @@ FIELD_OF_CURVE = {"bn254_g1": "bn254_fr", "curve25519_edwards": "curve25519_fr"}
 BASE_FIELD_OF_CURVE = {"bn254_g1": "bn254_fq", "curve25519_edwards": "curve25519_fq"}
 CURVE_OF_FIELD = {v: k for k, v in FIELD_OF_CURVE.items()}
 POINT_WORDS = {"bn254_g1": 12, "curve25519_edwards": 16}
+# base-field modulus by native curve id (arkmpc_curve): 0 BN254 G1, 1 Curve25519 Edwards
+BASE_MODULUS = {0: MODULUS["bn254_fq"], 1: MODULUS["curve25519_fq"]}
 
 
 def int_to_limbs(v: int) -> np.ndarray:

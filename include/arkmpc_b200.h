@@ -341,6 +341,9 @@ int arkmpc_pt_share_split(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* 
 int arkmpc_pt_share_join(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* share_pts, const uint64_t* mac_pts, uint64_t* out_ps);
 /* Canonical affine form: out_xy[i] = (x, y) Montgomery, 64 B; the BN254 identity maps to (0,0), the Edwards identity is (0,1). */
 int arkmpc_pt_normalize(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* pts, uint64_t* out_xy);
+/* The inverse: affine images -> points in the reference's projective memory image with Z = 1 (BN254: (0,0) -> identity).  Used to
+ * ingest PointBatch payloads from the wire (ark_mpc_b200/wire.py); the caller validates peer points with arkmpc_pt_validate. */
+int arkmpc_pt_from_affine(arkmpc_ctx* ctx, int curve, size_t n, const uint64_t* xy, uint64_t* out_pts);
 
 /* ---- end-to-end over HOST buffers (reference AoS images), both protocol phases ----
  * begin: uploads x, y and the triple (a, b, c) (n ScalarShares each, AoS, host), runs the mask kernel and

@@ -102,3 +102,28 @@ def test_cuda_reproduces_golden(idx):
     last = E.upload(L(g["x_plain"])[-1:])
     assert bytes(E.to_bytes_be(last).cpu().numpy().reshape(-1)).hex() == g["bytes_be_x0"]
     E.close()
+
+
+def test_fixtures_say_who_generated_them():
+    """The committed fixtures come from oracle/pyoracle.py (tests/golden/make_golden*.py), NOT from a run of the reference: the
+    reference cannot be built in this image.  oracle/ref_recipe/ holds the recipe that produces a reference-run file."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for gen in ("make_golden.py", "make_golden_curve.py"):
+        assert "oracle" in open(os.path.join(root, "tests", "golden", gen)).read()
+    for f in ("regen.sh", "gen_golden.rs", "compare_reference.py", "README.md"):
+        assert os.path.exists(os.path.join(root, "oracle", "ref_recipe", f))
+
+
+def test_reference_run_fixture_when_present():
+    """If a maintainer has run oracle/ref_recipe/regen.sh, tests/golden/reference_party_id.json holds the REFERENCE's own outputs
+    for the PartyIDBeaverSource case: they must equal the oracle-generated fixture (that equality is what pins parity)."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "tests", "golden", "reference_party_id.json")
+    if not os.path.exists(ref):
+        pytest.skip("parity unpinned: no reference-run fixture (the reference is Rust and cannot be built in this image; see oracle/ref_recipe)")
+    spec = importlib.util.spec_from_file_location("compare_reference", os.path.join(root, "oracle", "ref_recipe", "compare_reference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.compare(ref) == []

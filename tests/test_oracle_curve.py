@@ -47,6 +47,57 @@ def test_known_answers():
     assert enc.hex() == "d75a980182b10ab7d54bfed3c964073a0ee172f3daa62325af021a68f707511a"
 
 
+# RFC 8032 section 7.1, tests 1-3 and the 1023-byte-message test: (secret key, public key).  The public key is the compressed
+# encoding of clamp(SHA-512(sk)[:32]) * B, so each vector pins the fixed-base multiplication, the group law and the base point of
+# the Edwards oracle at a full-size scalar.
+RFC8032_KEYS = [
+    ("9d61b19deffd5a60ba844af492ec2cc44449c5697b326919703bac031cae7f60", "d75a980182b10ab7d54bfed3c964073a0ee172f3daa62325af021a68f707511a"),
+    ("4ccd089b28ff96da9db6c346ec114e0f5b8a319f35aba624da8cf6ed4fb8a6fb", "3d4017c3e843895a92b70aa74d1b7ebc9c982ccf2ec4968cc0cd55f12af4660c"),
+    ("c5aa8df43f9f837bedb7442f31dcb7b166d38535076f094b85ce3a2e0b4458f7", "fc51cd8e6218a1a38da47ed00230f0580816ed13ba3303ac5deb911548908025"),
+    ("f5e5767cf153319517630f226876b86c8160cc583bc013744c6bf255f5cc0ee5", "278117fc144c72340f67d0f2316e8386ceffbf2b2428c9c51fef7c597f1d426e"),
+]
+
+
+def _rfc8032_scalar(sk_hex):
+    import hashlib
+
+    h = bytearray(hashlib.sha512(bytes.fromhex(sk_hex)).digest()[:32])
+    h[0] &= 248
+    h[31] &= 127
+    h[31] |= 64
+    return int.from_bytes(h, "little")
+
+
+@pytest.mark.parametrize("sk,pk", RFC8032_KEYS)
+def test_rfc8032_public_keys(sk, pk):
+    l = po.CURVE25519_FR.p
+    s = _rfc8032_scalar(sk)
+    for where, (x, y) in (("python oracle", po.CURVE25519_EDWARDS.mul(po.CURVE25519_EDWARDS.generator, s % l)),
+                          ("C oracle", affine_ints(1, co.pt_mul_generator(1, co.to_mont(1, co.ints_to_limbs([s % l]))))[0])):
+        assert (y | ((x & 1) << 255)).to_bytes(32, "little").hex() == pk, where
+
+
+def test_bn254_g1_known_multiples():
+    """EIP-196 precompile vectors (go-ethereum / py_ecc): small multiples of (1, 2), and the group order as published in EIP-196:
+    r * G is the point at infinity, (r - 1) * G = -G = (1, p - 2)."""
+    Cv = po.BN254_G1
+    r, q = po.BN254_FR.p, Cv.fq.p
+    assert r == 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    assert q == 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    mul = lambda k: affine_ints(0, co.pt_mul_generator(0, co.to_mont(0, co.ints_to_limbs([k % r]))))[0]
+    two_g = (1368015179489954701390400359078579693043519447331113978918064868415326638035,
+             9918110051302171585080402603319702774565515993150576347155970296011118125764)
+    three_g = (3353031288059533942658390886683067124040920775575537747144343083137631628272,
+               19321533766552368860946552437480515441416830039777911637913418824951667761761)
+    assert mul(2) == two_g == Cv.mul(Cv.generator, 2)
+    assert mul(3) == three_g == Cv.add(two_g, Cv.generator)
+    assert mul(r - 1) == (1, q - 2)
+    assert Cv.mul(Cv.generator, r) is None
+    # on-curve: y^2 = x^3 + 3
+    for x, y in (two_g, three_g):
+        assert (y * y - x * x * x - 3) % q == 0
+
+
 @pytest.mark.parametrize("cv", CURVES)
 def test_scalar_mul_matches_python(cv):
     Cv = CURVE_BY_ID[cv]
