@@ -66,7 +66,7 @@ def load_traffic(kernel_substr="beaver_recombine_kernel"):
             if line.startswith("## "):
                 cur = line
             m = re.search(r"traffic \(dram read\+write\) bytes per launch\s+(\d+)", line)
-            if m and cur and kernel_substr in cur:
+            if m and cur and kernel_substr in cur and "pt_" + kernel_substr not in cur:
                 vals.append(int(m.group(1)))
         if vals:
             best = (sum(vals) / len(vals), os.path.relpath(path, ROOT))
@@ -542,12 +542,28 @@ def measure_config0(local_rank, iters=20):
             times.append(max(t0, t1))
     times.sort()
     med = times[len(times) // 2]
-    out = {"metric": METRIC, "value": n / med, "unit": UNIT, "ms_per_iter": 1e3 * med, "iters": iters,
+    py = {"value": n / med, "ms_per_iter": 1e3 * med, "host": "ark_mpc_b200/fabric.py (Python mirror, two threads)"}
+    # the same flow through the compiled C++ host mirror (host/arkmpc_host.hpp over the C ABI): what a Rust host's latency looks like
+    cpp = None
+    exe = os.path.join(ROOT, "tools", "host_bench", "bench_config0")
+    if os.path.exists(exe):
+        try:
+            r = subprocess.run([exe, str(n), "30", "1"], capture_output=True, text=True, timeout=300)
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            if "error" not in j:
+                cpp = {"value": j["mults_per_s"], "ms_per_iter": 1e3 * j["median_s"], "ms_per_iter_min": 1e3 * j["min_s"], "iters": j["iters"],
+                       "host": "tools/host_bench/bench_config0.cpp over host/arkmpc_host.hpp (compiled C++ mirror, two threads)"}
+        except Exception as ex:  # noqa: BLE001
+            cpp = {"error": repr(ex)[:200]}
+    best = cpp if cpp and "value" in cpp else py
+    med = best["ms_per_iter"] * 1e-3
+    out = {"metric": METRIC, "value": n / med, "unit": UNIT, "ms_per_iter": 1e3 * med, "iters": iters, "python_mirror": py, "cpp_host_mirror": cpp,
            "config": {"workload": "1024-element share + AuthenticatedScalar batch_mul + open_authenticated over Curve25519 Fr, 2 parties in one process, "
                                   "in-memory mock net, PartyIDBeaverSource (BASELINE.json configs[0]; benches/batch_ops.rs:20-40)",
                       "field": field, "batch": n, "parties": 2},
-           "note": "host wall clock from inside each party's closure to the opened values on the host, slower party, median; at n = 1024 the "
-                   "GPU path is bound by ~25 kernel launches, 8 message hand-offs and two host SHA3 commitments per party, not by arithmetic",
+           "note": "host wall clock from inside each party's closure to the opened values on the host, slower party, median; `value` is the compiled "
+                   "C++ host mirror when its binary is present (python_mirror beside it); at n = 1024 the GPU path is bound by ~25 kernel launches, "
+                   "8 message hand-offs and two host SHA3 commitments per party, not by arithmetic",
            "roofline": None}
     # CPU arm: the same gate sequence restated in C, both parties, arithmetic only (no executor, no commitment hash)
     from oracle import coracle as co
