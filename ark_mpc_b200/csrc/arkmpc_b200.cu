@@ -184,7 +184,8 @@ int arkmpc_ctx_destroy(arkmpc_ctx* ctx) {
   if (ctx->flag_host) cudaFreeHost(ctx->flag_host);
   for (int c = 0; c < kNumCurves; c++)
     if (ctx->gtab[c]) cudaFree(ctx->gtab[c]);
-  if (ctx->ntt_tw) cudaFree(ctx->ntt_tw);
+  for (int d = 0; d < 2; d++)
+    if (ctx->ntt_tw[d]) cudaFree(ctx->ntt_tw[d]);
   if (ctx->tab_scratch) cudaFree(ctx->tab_scratch);
   if (ctx->tab_masks) cudaFree(ctx->tab_masks);
   }  // the guard (and the lock it holds) must be gone before the context is
@@ -593,6 +594,7 @@ int arkmpc_fr_beaver_recombine_sum(arkmpc_ctx* ctx, int field, int party_id, con
                                    const uint64_t* c_mac, uint64_t* out_share, uint64_t* out_mac) {
   ARK_CHECK_CTX(ctx);
   ARK_REQUIRE(ctx, party_id == 0 || party_id == 1, "party_id must be 0 or 1");
+  ARK_REQUIRE(ctx, field == ARKMPC_BN254_FR || field == ARKMPC_CURVE25519_FR, "unknown field id");  // before any scratch is allocated
   ARK_REQUIRE(ctx, out_share && out_mac && aligned32(out_share) && aligned32(out_mac), "null or misaligned pointer");
   if (n == 0) return sum_impl(ctx, field, 0, out_share, out_mac, out_share, out_mac);  // the additive identity, like an empty sum()
   ARK_REQUIRE(ctx, key_host && d_mine && e_mine && d_peer && e_peer && a_share && a_mac && b_share && b_mac && c_share && c_mac, "null pointer");

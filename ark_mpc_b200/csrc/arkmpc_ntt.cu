@@ -7,30 +7,40 @@ using namespace arkctx;
 
 namespace {
 
-// Twiddles w^k (k < n/2) followed by the two constants {w, n^-1}; cached for the last (field, log2n, direction).
+// Twiddles w^k (k < n/2) followed by the two constants {w, n^-1}; one cached table per direction, keyed by (field, log2n), allocated
+// and freed in stream order (no host synchronisation when the size changes).
 template <class F>
 int ntt_table(arkmpc_ctx* ctx, int field, int log2n, int inverse, const char** tw, const fe8** consts) {
   const size_t half = log2n ? (size_t)1 << (log2n - 1) : 1;
-  const long key = ((long)field << 16) | ((long)log2n << 1) | (inverse ? 1 : 0);
-  if (ctx->ntt_key != key) {
-    if (ctx->ntt_tw) {
-      ARK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      ARK_CUDA(ctx, cudaFree(ctx->ntt_tw));
-      ctx->ntt_tw = nullptr;
-      ctx->ntt_key = -1;
+  const int dir = inverse ? 1 : 0;
+  const long key = ((long)field << 16) | (long)log2n;
+  if (ctx->ntt_key[dir] != key) {
+    if (ctx->ntt_tw[dir]) {
+      cudaFreeAsync(ctx->ntt_tw[dir], ctx->stream);  // after every transform already enqueued on this stream
+      ctx->ntt_tw[dir] = nullptr;
+      ctx->ntt_key[dir] = -1;
     }
     void* mem = nullptr;
-    ARK_CUDA(ctx, cudaMalloc(&mem, (half + 2) * 32));
+    ARK_CUDA(ctx, cudaMallocAsync(&mem, (half + 2) * 32, ctx->stream));
     fe8* c = reinterpret_cast<fe8*>(static_cast<char*>(mem) + half * 32);
     fr_ntt_setup_kernel<F><<<1, 1, 0, ctx->stream>>>(log2n, inverse, c);
     ctx->launches++;
     fr_ntt_twiddle_kernel<F><<<grid_for(ctx, half, 4), kBlock, 0, ctx->stream>>>(half, c, mvec(mem));
     int rc = post_launch(ctx, "fr_ntt_twiddle_kernel");
-    if (rc != ARKMPC_OK) { cudaFree(mem); return rc; }
-    ctx->ntt_tw = mem;
-    ctx->ntt_key = key;
+    if (rc != ARKMPC_OK) { cudaFreeAsync(mem, ctx->stream); return rc; }
+    ctx->ntt_tw[dir] = mem;
+    ctx->ntt_key[dir] = key;
+    ctx->ntt_stream[dir] = ctx->stream;
+  } else if (ctx->ntt_stream[dir] != ctx->stream) {
+    // the context was re-pointed at another stream since the table was built: order this stream after the builder
+    cudaEvent_t ev;
+    ARK_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaEventRecord(ev, ctx->ntt_stream[dir]);
+    cudaStreamWaitEvent(ctx->stream, ev, 0);
+    cudaEventDestroy(ev);
+    ctx->ntt_stream[dir] = ctx->stream;
   }
-  *tw = static_cast<const char*>(ctx->ntt_tw);
+  *tw = static_cast<const char*>(ctx->ntt_tw[dir]);
   *consts = reinterpret_cast<const fe8*>(*tw + half * 32);
   return ARKMPC_OK;
 }

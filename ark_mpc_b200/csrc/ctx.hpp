@@ -53,8 +53,9 @@ struct arkmpc_ctx {
   std::mutex gtab_mutex;
   void* tab_scratch = nullptr;  // window-table records of the variable-base multiplications (curve_kernels.cuh), L2-resident
   void* tab_masks = nullptr;    // per-SM slot claim masks
-  void* ntt_tw = nullptr;    // twiddle table + constants of the last (field, log2n, direction) transform (arkmpc_ntt.cu)
-  long ntt_key = -1;
+  void* ntt_tw[2] = {nullptr, nullptr};  // twiddle table + constants of the last forward [0] and inverse [1] transform (arkmpc_ntt.cu):
+  cudaStream_t ntt_stream[2] = {nullptr, nullptr};  // the stream each table was built on
+  long ntt_key[2] = {-1, -1};            // FFT -> batch_mul -> IFFT (authenticated_poly.rs:377-401) alternates directions without rebuilding
   void* nccl = nullptr;      // ncclComm_t of arkmpc_nccl_init (arkmpc_comm.cu)
   int nccl_world = 0, nccl_rank = -1;
 };

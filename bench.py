@@ -196,8 +196,10 @@ def workload_config(args, world):
             "field": args.field, "log2_batch_per_gpu": args.log2_batch, "parties": 2,
             "sharding": f"index-range x{world}, no data-path collective",
             "l2_hygiene": "inputs larger than L2: ~0.9 GB touched per step vs 126 MB L2",
-            "launch_order": "mask(p0) mask(p1) recombine(p0) recombine(p1); " + ("every launch ordered after its predecessor" if args.no_hint else
-                            "the second launch of each phase carries the independence hint (overlaps the first's drain)")}
+            "launch_order": "mask(p0) mask(p1) recombine(p0) recombine(p1); " + (
+                "every launch ordered after its predecessor" if (args.no_hint or args.hint_level == 0) else
+                "the second launch of each phase carries the independence hint (overlaps the first's drain)" if args.hint_level == 1 else
+                "alternate steps write alternate d/e planes; every launch but recombine(p0) carries the independence hint")}
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -481,8 +483,7 @@ def measure_supplementary(args, rank, world, local_rank, workload, log2_batch, f
                     s0, s1, _, _ = co.two_party_point_mul(cv, cores, keys, (cuts(x0), cuts(x1)), Ps, (cuts(a0), cuts(a1)), (cuts(b0), cuts(b1)),
                                                           (cuts(c0), cuts(c1)), want_open=False)
                     gs = [E.download(E.pt_normalize(outs[p][::stride].contiguous())) for p in (0, 1)]
-                    same = same and all(np.array_equal(co.pt_normalize(cv, o.reshape(-1, o0.shape[-1] // 2 if o.ndim > 1 else 1).reshape(2 * gs[0].shape[0] // 2, -1)), g)
-                                        for o, g in zip((s0, s1), gs))
+                    same = same and all(np.array_equal(co.pt_normalize(cv, o.reshape(2 * o.shape[0], -1)), g) for o, g in zip((s0, s1), gs))
                     line["parity"] = f"both parties' outputs equal the CPU oracle on the first {m} gates and on every {stride}th gate of the batch (affine form)"
                     if not same:
                         raise SystemExit("point_mul: GPU result differs from the CPU oracle on the benchmark inputs")
@@ -632,6 +633,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hint", action="store_true", help="A/B: launch every kernel ordered after its predecessor (no independence hints)")
+    ap.add_argument("--hint-level", type=int, default=2, choices=[0, 1, 2], help="0 none; 1 the second launch of each phase; 2 also the next step's masks")
     ap.add_argument("--unfused-sum", action="store_true", help="inner_product: separate recombine and share_sum launches (A/B)")
     ap.add_argument("--configs", default="all", help="'all' (default), 'none', or a comma list of 0,2,3,4: which BASELINE.json configs ride along "
                                                      "under the `configs` key of the headline line")
@@ -698,26 +700,38 @@ def main():
         D = BeaverData(E, n, shard_seed(base_seed, rank), shard_seed(base_seed, rank) + 900)
         P, key, key0, key1, xv, yv = D.P, D.key, D.key0, D.key1, D.xv, D.yv
         x0, x1, y0, y1, a0, a1, b0, b1, c0, c1 = D.X[0], D.X[1], D.Y[0], D.Y[1], D.A[0], D.A[1], D.B[0], D.B[1], D.C[0], D.C[1]
-        de = [(E.empty(n), E.empty(n)) for _ in range(2)]
+        # two sets of d/e planes, used by alternate steps: like an executor that gives every gate fresh output buffers, so that the
+        # masks of step i+1 do not overwrite what the recombines of step i read (no write-after-read edge between steps)
+        de_sets = [[(E.empty(n), E.empty(n)) for _ in range(2)] for _ in range(2)]
+        de = de_sets[0]
         out = [(E.empty(n), E.empty(n)) for _ in range(2)]
 
-        # The two parties' launches of one phase are independent of each other (different operands, different outputs): the
-        # second carries the executor's independence hint (arkmpc_ctx_hint_independent), so its ramp-up overlaps the first's drain.
-        hint = (lambda: None) if args.no_hint else E.hint_independent
+        # Independence hints (arkmpc_ctx_hint_independent).  Level 1: the second launch of each phase (the other party's
+        # kernel: different operands, different outputs) overlaps the first's drain.  Level 2: with the alternating d/e sets the masks of
+        # the NEXT step are independent of this step's recombines too, so only recombine(p0) — which reads what the masks just wrote —
+        # is ordered after its predecessors.
+        level = 0 if args.no_hint else args.hint_level
+        hint = E.hint_independent
 
-        def mask_both():
-            E.beaver_mask(P[0]["x"][0], P[0]["y"][0], P[0]["a"][0], P[0]["b"][0], out=de[0])
-            hint()
-            E.beaver_mask(P[1]["x"][0], P[1]["y"][0], P[1]["a"][0], P[1]["b"][0], out=de[1])
+        def mask_both(i=0):
+            d = de_sets[i & 1]
+            if level >= 2 and i > 0:
+                hint()
+            E.beaver_mask(P[0]["x"][0], P[0]["y"][0], P[0]["a"][0], P[0]["b"][0], out=d[0])
+            if level >= 1:
+                hint()
+            E.beaver_mask(P[1]["x"][0], P[1]["y"][0], P[1]["a"][0], P[1]["b"][0], out=d[1])
 
-        def recombine_both():
-            E.beaver_recombine(0, P[0]["key"], de[0][0], de[0][1], de[1][0], de[1][1], P[0]["a"], P[0]["b"], P[0]["c"], out=out[0])
-            hint()
-            E.beaver_recombine(1, P[1]["key"], de[1][0], de[1][1], de[0][0], de[0][1], P[1]["a"], P[1]["b"], P[1]["c"], out=out[1])
+        def recombine_both(i=0):
+            d = de_sets[i & 1]
+            E.beaver_recombine(0, P[0]["key"], d[0][0], d[0][1], d[1][0], d[1][1], P[0]["a"], P[0]["b"], P[0]["c"], out=out[0])
+            if level >= 1:
+                hint()
+            E.beaver_recombine(1, P[1]["key"], d[1][0], d[1][1], d[0][0], d[0][1], P[1]["a"], P[1]["b"], P[1]["c"], out=out[1])
 
-        def step():
-            mask_both()
-            recombine_both()
+        def step(i=0):
+            mask_both(i)
+            recombine_both(i)
 
         # correctness gate before timing: opened product == x*y, MAC shares sum to key*x*y (whole batch, on device)
         step()
@@ -727,8 +741,8 @@ def main():
             raise SystemExit("correctness gate failed: opened product != x*y")
         del xy
 
-        for _ in range(args.warmup):
-            step()
+        for w in range(args.warmup):
+            step(w)
         stream.synchronize()
         if world > 1:
             dist.barrier()
@@ -743,13 +757,13 @@ def main():
         launches0 = E.launches
         ev0.record(stream)
         for i in range(args.steps):
-            mask_both()
+            mask_both(i)
             if i % sample_every == 0:
                 kev[i // sample_every][0].record(stream)
-                recombine_both()
+                recombine_both(i)
                 kev[i // sample_every][1].record(stream)
             else:
-                recombine_both()
+                recombine_both(i)
         ev1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
@@ -841,7 +855,7 @@ def main():
                 raise
             except Exception as ex:  # e.g. CUDA IPC unavailable in a restricted container: the headline numbers do not depend on it
                 open_gather = {"error": repr(ex)[:300]}
-        del de, out
+        del de, de_sets, out
 
         # ---- configs[4]: 2^log2_total gates sharded over the N GPUs, gather inside the step ----
         if world > 1 and 4 in which and args.field == "bn254_fr":

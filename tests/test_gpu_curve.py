@@ -6,6 +6,7 @@ import random
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import coracle as co
 from oracle import pyoracle as po
@@ -193,6 +194,18 @@ def test_point_beaver_mul_opens_to_product_large(engines, cv):
     idx = [0, 1, n // 2, n - 1]
     xs = E.download(E.mul(xv, sv))[idx]
     assert np.array_equal(want_share[idx], co.pt_normalize(cv, co.pt_mul_generator(cv, np.ascontiguousarray(xs))))
+    # and BOTH parties' PointShare outputs against the unfused oracle on a strided sample across the whole batch (every 256th gate)
+    from tests.util import aos
+
+    sel = torch.arange(0, n, 256, device=outs[0].device)
+    m = sel.numel()
+    cut = lambda pl: aos(E.download(pl[0][sel].contiguous()), E.download(pl[1][sel].contiguous()))
+    ins = ((key0, key1), (cut(x0), cut(x1)), tuple(E.download(P[p][sel].contiguous()) for p in (0, 1)), (cut(a0), cut(a1)), (cut(b0), cut(b1)),
+           (cut(c0), cut(c1)))
+    o0, o1, _, _ = co.two_party_point_mul(cv, 4, *ins, want_open=False)
+    for p, o in ((0, o0), (1, o1)):
+        got_p = E.download(E.pt_normalize(outs[p][sel].contiguous()))
+        assert np.array_equal(got_p, co.pt_normalize(cv, o.reshape(2 * m, -1))), f"party {p}: strided sample differs from the unfused oracle"
 
 
 @pytest.mark.parametrize("cv", CURVES)
