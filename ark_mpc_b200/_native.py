@@ -48,6 +48,8 @@ _PROTOS = {
     "arkmpc_ctx_launch_count": [_vp],
     "arkmpc_malloc": [_vp, _sz, C.POINTER(_vp)],
     "arkmpc_free": [_vp, _vp],
+    "arkmpc_mem_trim": [_vp],
+    "arkmpc_mem_cached_bytes": [_vp, C.POINTER(_sz)],
     "arkmpc_host_alloc": [_vp, _sz, C.POINTER(_vp)],
     "arkmpc_host_free": [_vp, _vp],
     "arkmpc_memcpy_h2d": [_vp, _vp, _vp, _sz],

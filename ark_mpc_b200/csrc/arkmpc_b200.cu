@@ -165,6 +165,7 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
     const char* c = getenv("ARKMPC_CHUNK_LOG2");
     if (c && atoi(c) >= 10 && atoi(c) <= 24) ctx->chunk_elems = (size_t)1 << atoi(c);
   }
+  mem_register(ctx);
   *out = ctx;
   return ARKMPC_OK;
 }
@@ -173,6 +174,8 @@ int arkmpc_ctx_destroy(arkmpc_ctx* ctx) {
   if (!ctx) return ARKMPC_OK;
   {
   CallGuard guard(ctx);
+  mem_unregister(ctx);  // arkmpc_free stops recording events on this context's stream ...
+  if (ctx->stream && ctx->stream != ctx->own_stream) cudaStreamSynchronize(ctx->stream);  // ... so what it still runs finishes here
   arkmpc_nccl_destroy(ctx);
   if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
   for (int i = 0; i < kSlots; i++) {
@@ -196,7 +199,7 @@ int arkmpc_ctx_destroy(arkmpc_ctx* ctx) {
 int arkmpc_ctx_set_stream(arkmpc_ctx* ctx, void* cuda_stream) {
   if (!ctx) return ARKMPC_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  mem_set_stream(ctx, static_cast<cudaStream_t>(cuda_stream));
   return ARKMPC_OK;
 }
 int arkmpc_ctx_hint_independent(arkmpc_ctx* ctx) {
@@ -208,7 +211,7 @@ int arkmpc_ctx_hint_independent(arkmpc_ctx* ctx) {
 int arkmpc_ctx_reset_stream(arkmpc_ctx* ctx) {
   if (!ctx) return ARKMPC_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  ctx->stream = ctx->own_stream;
+  mem_set_stream(ctx, ctx->own_stream);
   return ARKMPC_OK;
 }
 void* arkmpc_ctx_get_stream(arkmpc_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
@@ -223,40 +226,7 @@ int arkmpc_ctx_sync(arkmpc_ctx* ctx) {
   return ARKMPC_OK;
 }
 
-// ---- memory ----
-int arkmpc_malloc(arkmpc_ctx* ctx, size_t bytes, void** dev_ptr) {
-  ARK_CHECK_CTX(ctx);
-  ARK_REQUIRE(ctx, dev_ptr, "null out pointer");
-  *dev_ptr = nullptr;
-  if (bytes == 0) return ARKMPC_OK;
-  ARK_CUDA(ctx, cudaMalloc(dev_ptr, bytes));
-  return ARKMPC_OK;
-}
-int arkmpc_free(arkmpc_ctx* ctx, void* dev_ptr) {
-  ARK_CHECK_CTX(ctx);
-  if (dev_ptr) ARK_CUDA(ctx, cudaFree(dev_ptr));
-  return ARKMPC_OK;
-}
-int arkmpc_host_alloc(arkmpc_ctx* ctx, size_t bytes, void** pinned_ptr) {
-  ARK_CHECK_CTX(ctx);
-  ARK_REQUIRE(ctx, pinned_ptr, "null out pointer");
-  *pinned_ptr = nullptr;
-  if (bytes == 0) return ARKMPC_OK;
-  ARK_CUDA(ctx, cudaMallocHost(pinned_ptr, bytes));
-  return ARKMPC_OK;
-}
-int arkmpc_host_free(arkmpc_ctx* ctx, void* pinned_ptr) {
-  ARK_CHECK_CTX(ctx);
-  if (pinned_ptr) ARK_CUDA(ctx, cudaFreeHost(pinned_ptr));
-  return ARKMPC_OK;
-}
-int arkmpc_memcpy_h2d(arkmpc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
-  ARK_CHECK_CTX(ctx);
-  if (bytes == 0) return ARKMPC_OK;
-  ARK_REQUIRE(ctx, dst_dev && src_host, "null pointer");
-  ARK_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  return ARKMPC_OK;
-}
+// ---- memory ---- (arkmpc_malloc / arkmpc_free / arkmpc_host_alloc / arkmpc_host_free / arkmpc_memcpy_h2d: arkmpc_mem.cu)
 int arkmpc_memcpy_d2h(arkmpc_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
   ARK_CHECK_CTX(ctx);
   if (bytes == 0) return ARKMPC_OK;

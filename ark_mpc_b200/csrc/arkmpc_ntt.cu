@@ -102,27 +102,26 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
     sizes[levels + 1] = (sizes[levels] + kInvGroup - 1) / kInvGroup;
     levels++;
   }
-  // scratch: prefix_l (n_l) for l < levels, products x_(l+1) (n_(l+1)) and their inverses (n_(l+1))
+  // scratch: the group products x_(l+1) (n_(l+1) elements) and their inverses, for every level above the input
   size_t elems = 0;
-  for (int l = 0; l < levels; l++) elems += sizes[l] + 2 * sizes[l + 1];
+  for (int l = 0; l < levels; l++) elems += 2 * sizes[l + 1];
   cudaStream_t s = ctx->stream;
   char* scratch = nullptr;
   if (elems) ARK_CUDA(ctx, cudaMallocAsync(&scratch, elems * 32, s));
   const char* xs[16];
-  char *prefix[16], *inv[16];
+  char* inv[16];
   xs[0] = reinterpret_cast<const char*>(a);
   inv[0] = reinterpret_cast<char*>(out);
   char* p = scratch;
   for (int l = 0; l < levels; l++) {
-    prefix[l] = p; p += sizes[l] * 32;
     xs[l + 1] = p; p += sizes[l + 1] * 32;
     inv[l + 1] = p; p += sizes[l + 1] * 32;
   }
-  auto blocks = [](size_t work) { return (unsigned)((work + kBlock - 1) / kBlock); };
+  auto blocks = [](size_t work) { return (unsigned)((work + kInvBlock - 1) / kInvBlock); };
   int rc = ARKMPC_OK;
   ARK_FIELD_SWITCH(ctx, field, {
     for (int l = 0; l < levels && rc == ARKMPC_OK; l++) {
-      fr_inv_up_kernel<F><<<blocks(sizes[l + 1]), kBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(prefix[l]), mvec(const_cast<char*>(xs[l + 1])));
+      fr_inv_up_kernel<F><<<blocks(sizes[l + 1]), kInvBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(const_cast<char*>(xs[l + 1])));
       rc = post_launch(ctx, "fr_inv_up_kernel");
     }
     if (rc == ARKMPC_OK) {
@@ -130,7 +129,7 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
       rc = post_launch(ctx, "fr_inv_top_kernel");
     }
     for (int l = levels - 1; l >= 0 && rc == ARKMPC_OK; l--) {
-      fr_inv_down_kernel<F><<<blocks(sizes[l + 1]), kBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(prefix[l]), vec(inv[l + 1]), mvec(inv[l]));
+      fr_inv_down_kernel<F><<<blocks(sizes[l + 1]), kInvBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(inv[l + 1]), mvec(inv[l]));
       rc = post_launch(ctx, "fr_inv_down_kernel");
     }
   });

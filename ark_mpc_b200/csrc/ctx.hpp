@@ -62,6 +62,12 @@ struct arkmpc_ctx {
 
 namespace arkctx {
 
+// arkmpc_mem.cu: the device-memory cache records events on every live context's current stream, so contexts register with it
+// and change `stream` under its lock
+void mem_register(arkmpc_ctx* ctx);
+void mem_unregister(arkmpc_ctx* ctx);
+void mem_set_stream(arkmpc_ctx* ctx, cudaStream_t s);
+
 inline std::string& thread_error() {
   static thread_local std::string e;
   return e;

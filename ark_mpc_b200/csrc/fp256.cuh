@@ -518,10 +518,128 @@ struct Fp {
     ARK_UNROLL for (int j = 0; j < 8; j++) r.v[j] = x1[j];
   }
 
+  // a^-1 mod p for 0 < a < p by Bernstein-Yang division steps ("safegcd", half-delta variant; the published algorithm, arranged as
+  // in the 32-bit modular inverse of Pieter Wuille's bitcoin-core implementation notes): 20 rounds of 30 division steps.  A round
+  // runs its 30 steps on the LOW 32 bits of f and g only (about 20 integer instructions per step, nothing 256-bit), collects them
+  // in a 2x2 matrix t with |entries| <= 2^30, and then applies t once to the full-width pairs (f, g) and (d, e), kept as nine
+  // signed 30-bit limbs so every column sum fits a signed 64-bit accumulator (IMAD.WIDE, signed).  Invariants: d * a = f and
+  // e * a = g (mod p); f, g shrink by exact division by 2^30 per round, (d, e) by Montgomery-style division mod p.  590 steps
+  // suffice for any 256-bit odd modulus; 600 leave f = +-1, g = 0, d = +-a^-1.  Branch-free and fixed-length like inv_plain, with
+  // a third of its instructions: 33 us for 16 k inversions spread one warp per scheduler (profiles/r02m_*), inv_plain took 81.
+  static constexpr int32_t kM30 = 0x3fffffff;
+  ARK_HDM static constexpr uint32_t p_word(int j) {
+    return j == 0 ? F::P0 : j == 1 ? F::P1 : j == 2 ? F::P2 : j == 3 ? F::P3 : j == 4 ? F::P4 : j == 5 ? F::P5 : j == 6 ? F::P6 : j == 7 ? F::P7 : 0u;
+  }
+  // limb i of p in radix 2^30
+  ARK_HDM static constexpr int32_t p_limb30(int i) {
+    const int bit = 30 * i, w = bit >> 5, sh = bit & 31;
+    const uint64_t two = (uint64_t)p_word(w) | ((uint64_t)p_word(w + 1) << 32);
+    return (int32_t)((two >> sh) & (uint64_t)kM30);
+  }
+  ARK_DM static void inv_safegcd(fe8& r, const fe8& a) {
+    constexpr uint32_t kPInv30 = (0u - F::INV) & (uint32_t)kM30;  // p^-1 mod 2^30 (F::INV is -p^-1 mod 2^32)
+    int32_t f[9], g[9], d[9], e[9], pl[9];
+    ARK_UNROLL for (int i = 0; i < 9; i++) {
+      const int bit = 30 * i, w = bit >> 5, sh = bit & 31;
+      const uint32_t lo = a.v[w], hi = w + 1 < 8 ? a.v[w + 1] : 0u;
+      g[i] = (int32_t)((sh ? (lo >> sh) | (hi << (32 - sh)) : lo) & (uint32_t)kM30);
+      pl[i] = p_limb30(i);
+      f[i] = pl[i];
+      d[i] = 0;
+      e[i] = 0;
+    }
+    e[0] = 1;
+    int32_t zeta = -1;  // -(delta + 1/2), delta = 1/2
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int round = 0; round < 20; round++) {
+      // 30 division steps on the low words; (u, v, q, r) accumulate the transition matrix scaled by 2^30
+      uint32_t u = 1, v = 0, q = 0, rr = 1;
+      uint32_t fl = (uint32_t)f[0] | ((uint32_t)f[1] << 30), gl = (uint32_t)g[0] | ((uint32_t)g[1] << 30);
+      ARK_UNROLL for (int i = 0; i < 30; i++) {
+        uint32_t c1 = (uint32_t)(zeta >> 31);   // zeta < 0  (delta > 0)
+        const uint32_t c2 = 0u - (gl & 1u);     // g odd
+        const uint32_t x = (fl ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;  // (f, u, v) negated when delta > 0
+        gl += x & c2;
+        q += y & c2;
+        rr += z & c2;
+        c1 &= c2;                               // delta > 0 and g odd: the step swaps
+        zeta = (int32_t)(((uint32_t)zeta ^ c1) - 1u);
+        fl += gl & c1;
+        u += q & c1;
+        v += rr & c1;
+        gl >>= 1;
+        u <<= 1;
+        v <<= 1;
+      }
+      const int32_t tu = (int32_t)u, tv = (int32_t)v, tq = (int32_t)q, tr = (int32_t)rr;
+      // (d, e) <- t * (d, e) / 2^30 mod p; a multiple of p chosen per row clears the low 30 bits; both stay in (-2p, p)
+      {
+        const int32_t sd = d[8] >> 31, se = e[8] >> 31;
+        int32_t md = (tu & sd) + (tv & se), me = (tq & sd) + (tr & se);
+        int64_t cd = (int64_t)tu * d[0] + (int64_t)tv * e[0];
+        int64_t ce = (int64_t)tq * d[0] + (int64_t)tr * e[0];
+        md -= (int32_t)((kPInv30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)kM30);
+        me -= (int32_t)((kPInv30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)kM30);
+        cd += (int64_t)pl[0] * md;
+        ce += (int64_t)pl[0] * me;
+        cd >>= 30;
+        ce >>= 30;
+        ARK_UNROLL for (int i = 1; i < 9; i++) {
+          const int32_t di = d[i], ei = e[i];
+          cd += (int64_t)tu * di + (int64_t)tv * ei + (int64_t)pl[i] * md;
+          ce += (int64_t)tq * di + (int64_t)tr * ei + (int64_t)pl[i] * me;
+          d[i - 1] = (int32_t)cd & kM30;
+          e[i - 1] = (int32_t)ce & kM30;
+          cd >>= 30;
+          ce >>= 30;
+        }
+        d[8] = (int32_t)cd;
+        e[8] = (int32_t)ce;
+      }
+      // (f, g) <- t * (f, g) / 2^30, exactly
+      {
+        int64_t cf = (int64_t)tu * f[0] + (int64_t)tv * g[0];
+        int64_t cg = (int64_t)tq * f[0] + (int64_t)tr * g[0];
+        cf >>= 30;
+        cg >>= 30;
+        ARK_UNROLL for (int i = 1; i < 9; i++) {
+          const int32_t fi = f[i], gi = g[i];
+          cf += (int64_t)tu * fi + (int64_t)tv * gi;
+          cg += (int64_t)tq * fi + (int64_t)tr * gi;
+          f[i - 1] = (int32_t)cf & kM30;
+          g[i - 1] = (int32_t)cg & kM30;
+          cf >>= 30;
+          cg >>= 30;
+        }
+        f[8] = (int32_t)cf;
+        g[8] = (int32_t)cg;
+      }
+    }
+    // d = sign(f) * a^-1 in (-2p, p): add p if negative, negate if f = -1, add p again if still negative -> [0, p)
+    {
+      int32_t add = d[8] >> 31;
+      const int32_t neg = f[8] >> 31;
+      ARK_UNROLL for (int i = 0; i < 9; i++) d[i] = ((d[i] + (pl[i] & add)) ^ neg) - neg;
+      ARK_UNROLL for (int i = 0; i < 8; i++) { d[i + 1] += d[i] >> 30; d[i] &= kM30; }
+      add = d[8] >> 31;
+      ARK_UNROLL for (int i = 0; i < 9; i++) d[i] += pl[i] & add;
+      ARK_UNROLL for (int i = 0; i < 8; i++) { d[i + 1] += d[i] >> 30; d[i] &= kM30; }
+    }
+    ARK_UNROLL for (int j = 0; j < 8; j++) {  // radix 2^30 -> 2^32
+      const int bit = 32 * j, i = bit / 30, sh = bit % 30;
+      uint32_t w = (uint32_t)d[i] >> sh;
+      w |= (uint32_t)d[i + 1] << (30 - sh);
+      if (60 - sh < 32 && i + 2 < 9) w |= (uint32_t)d[i + 2] << (60 - sh);
+      r.v[j] = w;
+    }
+  }
+
   // Montgomery image of a^-1 from the Montgomery image of a != 0: (aR)^-1 = a^-1 R^-1, then two multiplications by R^2
   ARK_DM static void inv_mont(fe8& r, const fe8& a_mont) {
     fe8 y, r2;
-    inv_plain(y, a_mont);
+    inv_safegcd(y, a_mont);
     set_r2(r2);
     mul(y, y, r2);
     mul(r, y, r2);

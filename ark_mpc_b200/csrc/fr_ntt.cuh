@@ -14,46 +14,55 @@ namespace ark {
 
 // ---------------------------------------------------------------------------------------------
 // Batch inversion (scalar.rs:93-100 -> ark_ff::batch_inversion: zeros stay zero): Montgomery's trick as a product TREE.
-//   up    every thread multiplies a group of kInvGroup elements (element j of group g is x[g + j*groups]: coalesced), stores the
-//         running products and hands the group product to the next level; levels shrink by kInvGroup until <= kInvTop remain;
-//   top   one binary-Euclid inversion per remaining element (Fp::inv_mont: no multiplications on the critical path);
-//   down  every thread walks its group backwards: inverse_j = I * prefix_(j-1), I *= x_j.
-// 3 multiplications per element (the minimum of the trick) at full occupancy at every batch size, and ONE inversion latency on the
-// critical path — round 1 ran a 380-multiplication Fermat chain per 32 elements on n/32 threads: 320 us at n = 2^16 and at 2^20.
+//   up    every thread multiplies a group of kInvGroup = 8 elements (element j of group g is x[g + j*groups]: coalesced) as a
+//         balanced binary tree — 4 + 2 + 1 multiplications, depth 3 — and hands the group product to the next level; levels
+//         shrink by 8 until <= kInvTop remain.  Zeros (and the padding of a ragged last group) enter the product as one;
+//   top   one safegcd inversion per remaining element (Fp::inv_mont): up to 16 k of them cost the latency of one, a warp per
+//         SM sub-partition;
+//   down  every thread rebuilds its group's tree from the inputs (6 multiplications instead of 8 stored partial products: at
+//         2^20 the stores and re-loads were 64 MB of traffic and an eight-deep dependent chain) and walks it down: the inverse
+//         of a node times its sibling's product is the inverse of the other child — 2 + 4 + 8 independent multiplications.
+// 27 multiplications per 8 elements, dependent depth 3 + 3 (the serial prefix form: 24, depth 7 + 8, and 12 % occupancy gave
+// nothing to hide it behind), and ONE inversion latency on the critical path — round 1 ran a 380-multiplication Fermat chain per
+// 32 elements on n/32 threads: 320 us at n = 2^16 and at 2^20.
 // ---------------------------------------------------------------------------------------------
 constexpr int kInvGroup = 8;
-constexpr size_t kInvTop = 2048;
+constexpr size_t kInvTop = 16384;
+constexpr int kInvBlock = 128;  // 2^17 groups at n = 2^20: 1024 blocks spread evenly over 148 SMs (256-thread blocks: 3 or 4 per SM)
 
-// Both sweeps issue all the loads of a group before the first multiplication: the upper levels of the tree are a few thousand
-// threads, nothing hides a load there, and eight serial load-multiply round trips cost 12 us per level (profiles/r02i_*).
+// loads the eight elements of group g (all loads issued before the first use), replaces zeros and out-of-range slots by one and
+// returns the mask of the slots that hold a non-zero input
 template <class F>
-__global__ void __launch_bounds__(kBlock) fr_inv_up_kernel(size_t n, size_t groups, Vec x, MVec prefix, MVec prod) {
-  const size_t g = (size_t)blockIdx.x * kBlock + threadIdx.x;
-  if (g >= groups) return;
-  fe8 v[kInvGroup];
+__device__ __forceinline__ uint32_t inv_load_group(fe8 (&z)[kInvGroup], size_t n, size_t groups, size_t g, Vec x) {
 #pragma unroll
   for (int j = 0; j < kInvGroup; j++) {
     const size_t i = g + (size_t)j * groups;
-    if (i < n) ld_fe(v[j], x, i); else Fp<F>::set_zero(v[j]);
+    if (i < n) ld_fe(z[j], x, i); else Fp<F>::set_zero(z[j]);
   }
-  fe8 acc;
-  Fp<F>::set_one(acc);
-  bool any = false;
+  uint32_t live = 0;
 #pragma unroll
   for (int j = 0; j < kInvGroup; j++) {
-    const size_t i = g + (size_t)j * groups;
-    if (i < n) {
-      if (!Fp<F>::is_zero(v[j])) {  // zeros are skipped, as ark_ff::batch_inversion does
-        if (any) Fp<F>::mul(acc, acc, v[j]); else acc = v[j];
-        any = true;
-      }
-      st_fe(prefix, i, acc);
-    }
+    if (Fp<F>::is_zero(z[j])) Fp<F>::set_one(z[j]); else live |= 1u << j;
   }
-  st_fe(prod, g, acc);
+  return live;
 }
 
-// One warp per block: the <= 2048 inversions at the top are latency-bound, so they are spread over as many SMs as there are warps.
+template <class F>
+__global__ void __launch_bounds__(kInvBlock) fr_inv_up_kernel(size_t n, size_t groups, Vec x, MVec prod) {
+  const size_t g = (size_t)blockIdx.x * kInvBlock + threadIdx.x;
+  if (g >= groups) return;
+  fe8 z[kInvGroup];
+  (void)inv_load_group<F>(z, n, groups, g, x);
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) Fp<F>::mul(z[j], z[j], z[j + 1]);
+  Fp<F>::mul(z[0], z[0], z[2]);
+  Fp<F>::mul(z[4], z[4], z[6]);
+  Fp<F>::mul(z[0], z[0], z[4]);
+  st_fe(prod, g, z[0]);
+}
+
+// One warp per block: the <= 16384 inversions at the top are latency-bound, so they are spread one warp per SM sub-partition
+// (512 blocks over 148 SMs x 4 schedulers) and cost the latency of a single inversion.
 constexpr int kInvTopBlock = 32;
 template <class F>
 __global__ void __launch_bounds__(kInvTopBlock) fr_inv_top_kernel(size_t n, Vec x, MVec out) {
@@ -66,36 +75,28 @@ __global__ void __launch_bounds__(kInvTopBlock) fr_inv_top_kernel(size_t n, Vec 
 }
 
 template <class F>
-__global__ void __launch_bounds__(kBlock) fr_inv_down_kernel(size_t n, size_t groups, Vec x, Vec prefix, Vec ginv, MVec out) {
-  const size_t g = (size_t)blockIdx.x * kBlock + threadIdx.x;
+__global__ void __launch_bounds__(kInvBlock) fr_inv_down_kernel(size_t n, size_t groups, Vec x, Vec ginv, MVec out) {
+  const size_t g = (size_t)blockIdx.x * kInvBlock + threadIdx.x;
   if (g >= groups) return;
-  fe8 inv, v[kInvGroup], pre[kInvGroup];
+  fe8 z[kInvGroup], p[4], q[2], inv;
   ld_fe(inv, ginv, g);
+  const uint32_t live = inv_load_group<F>(z, n, groups, g, x);
+#pragma unroll
+  for (int k = 0; k < 4; k++) Fp<F>::mul(p[k], z[2 * k], z[2 * k + 1]);
+  Fp<F>::mul(q[0], p[0], p[1]);
+  Fp<F>::mul(q[1], p[2], p[3]);
+  fe8 iq[2], ip[4];
+  Fp<F>::mul(iq[0], inv, q[1]);
+  Fp<F>::mul(iq[1], inv, q[0]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) Fp<F>::mul(ip[k], iq[k >> 1], p[k ^ 1]);
 #pragma unroll
   for (int j = 0; j < kInvGroup; j++) {
     const size_t i = g + (size_t)j * groups;
-    if (i < n) {
-      ld_fe(v[j], x, i);
-      if (j > 0) ld_fe(pre[j], prefix, i - groups);  // product of the nonzero elements before this one (one, if there are none)
-    } else {
-      Fp<F>::set_zero(v[j]);
-    }
-  }
-#pragma unroll
-  for (int j = kInvGroup - 1; j >= 0; j--) {
-    const size_t i = g + (size_t)j * groups;
     if (i >= n) continue;
-    if (Fp<F>::is_zero(v[j])) {  // zeros stay zero
-      st_fe(out, i, v[j]);
-      continue;
-    }
     fe8 r;
-    if (j == 0) {
-      r = inv;
-    } else {
-      Fp<F>::mul(r, inv, pre[j]);
-      Fp<F>::mul(inv, inv, v[j]);
-    }
+    Fp<F>::mul(r, ip[j >> 1], z[j ^ 1]);
+    if (!((live >> j) & 1u)) Fp<F>::set_zero(r);  // zeros stay zero
     st_fe(out, i, r);
   }
 }

@@ -18,8 +18,12 @@
 // `ark_mpc_b200/fabric.py` is the same mirror for the Python test-suite; tests/host_cpp/test_host.cpp exercises this one.
 #pragma once
 #include <array>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -47,44 +51,56 @@ struct AuthenticationError : MpcError { AuthenticationError() : MpcError("MAC ch
 // SHA3-256 (FIPS 202) for the hash commitment; the reference uses the `sha3` crate (commitment.rs:36-41).
 // ---------------------------------------------------------------------------------------------------------------
 namespace detail {
+inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+// Keccak-f[1600], the 25 lanes in locals and each round written out (theta, rho + pi, chi, iota): ~2.5 ns per absorbed byte; the
+// commitment hashes n x 32 bytes per open_authenticated_batch and was 80 % of a 1024-gate iteration with a table-driven round.
 inline void keccak_f(uint64_t st[25]) {
   static const uint64_t RC[24] = {0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull, 0x000000000000808bull,
                                   0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008aull, 0x0000000000000088ull,
                                   0x0000000080008009ull, 0x000000008000000aull, 0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull,
                                   0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
                                   0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
-  static const int ROT[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
-  static const int PIL[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+  uint64_t a00 = st[0], a01 = st[1], a02 = st[2], a03 = st[3], a04 = st[4], a05 = st[5], a06 = st[6], a07 = st[7], a08 = st[8], a09 = st[9],
+           a10 = st[10], a11 = st[11], a12 = st[12], a13 = st[13], a14 = st[14], a15 = st[15], a16 = st[16], a17 = st[17], a18 = st[18],
+           a19 = st[19], a20 = st[20], a21 = st[21], a22 = st[22], a23 = st[23], a24 = st[24];
   for (int r = 0; r < 24; r++) {
-    uint64_t bc[5];
-    for (int i = 0; i < 5; i++) bc[i] = st[i] ^ st[i + 5] ^ st[i + 10] ^ st[i + 15] ^ st[i + 20];
-    for (int i = 0; i < 5; i++) {
-      uint64_t t = bc[(i + 4) % 5] ^ ((bc[(i + 1) % 5] << 1) | (bc[(i + 1) % 5] >> 63));
-      for (int j = 0; j < 25; j += 5) st[j + i] ^= t;
-    }
-    uint64_t t = st[1];
-    for (int i = 0; i < 24; i++) {
-      int j = PIL[i];
-      uint64_t b = st[j];
-      st[j] = (t << ROT[i]) | (t >> (64 - ROT[i]));
-      t = b;
-    }
-    for (int j = 0; j < 25; j += 5) {
-      for (int i = 0; i < 5; i++) bc[i] = st[j + i];
-      for (int i = 0; i < 5; i++) st[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5];
-    }
-    st[0] ^= RC[r];
+    // theta
+    const uint64_t c0 = a00 ^ a05 ^ a10 ^ a15 ^ a20, c1 = a01 ^ a06 ^ a11 ^ a16 ^ a21, c2 = a02 ^ a07 ^ a12 ^ a17 ^ a22,
+                   c3 = a03 ^ a08 ^ a13 ^ a18 ^ a23, c4 = a04 ^ a09 ^ a14 ^ a19 ^ a24;
+    const uint64_t d0 = c4 ^ rotl64(c1, 1), d1 = c0 ^ rotl64(c2, 1), d2 = c1 ^ rotl64(c3, 1), d3 = c2 ^ rotl64(c4, 1), d4 = c3 ^ rotl64(c0, 1);
+    // rho + pi: b[y][2x+3y] = rot(a[x][y])
+    const uint64_t b00 = a00 ^ d0, b10 = rotl64(a01 ^ d1, 1), b20 = rotl64(a02 ^ d2, 62), b05 = rotl64(a03 ^ d3, 28), b15 = rotl64(a04 ^ d4, 27),
+                   b16 = rotl64(a05 ^ d0, 36), b01 = rotl64(a06 ^ d1, 44), b11 = rotl64(a07 ^ d2, 6), b21 = rotl64(a08 ^ d3, 55), b06 = rotl64(a09 ^ d4, 20),
+                   b07 = rotl64(a10 ^ d0, 3), b17 = rotl64(a11 ^ d1, 10), b02 = rotl64(a12 ^ d2, 43), b12 = rotl64(a13 ^ d3, 25), b22 = rotl64(a14 ^ d4, 39),
+                   b23 = rotl64(a15 ^ d0, 41), b08 = rotl64(a16 ^ d1, 45), b18 = rotl64(a17 ^ d2, 15), b03 = rotl64(a18 ^ d3, 21), b13 = rotl64(a19 ^ d4, 8),
+                   b14 = rotl64(a20 ^ d0, 18), b24 = rotl64(a21 ^ d1, 2), b09 = rotl64(a22 ^ d2, 61), b19 = rotl64(a23 ^ d3, 56), b04 = rotl64(a24 ^ d4, 14);
+    // chi (+ iota on lane 0)
+    a00 = b00 ^ (~b01 & b02) ^ RC[r]; a01 = b01 ^ (~b02 & b03); a02 = b02 ^ (~b03 & b04); a03 = b03 ^ (~b04 & b00); a04 = b04 ^ (~b00 & b01);
+    a05 = b05 ^ (~b06 & b07); a06 = b06 ^ (~b07 & b08); a07 = b07 ^ (~b08 & b09); a08 = b08 ^ (~b09 & b05); a09 = b09 ^ (~b05 & b06);
+    a10 = b10 ^ (~b11 & b12); a11 = b11 ^ (~b12 & b13); a12 = b12 ^ (~b13 & b14); a13 = b13 ^ (~b14 & b10); a14 = b14 ^ (~b10 & b11);
+    a15 = b15 ^ (~b16 & b17); a16 = b16 ^ (~b17 & b18); a17 = b17 ^ (~b18 & b19); a18 = b18 ^ (~b19 & b15); a19 = b19 ^ (~b15 & b16);
+    a20 = b20 ^ (~b21 & b22); a21 = b21 ^ (~b22 & b23); a22 = b22 ^ (~b23 & b24); a23 = b23 ^ (~b24 & b20); a24 = b24 ^ (~b20 & b21);
   }
+  st[0] = a00; st[1] = a01; st[2] = a02; st[3] = a03; st[4] = a04; st[5] = a05; st[6] = a06; st[7] = a07; st[8] = a08; st[9] = a09;
+  st[10] = a10; st[11] = a11; st[12] = a12; st[13] = a13; st[14] = a14; st[15] = a15; st[16] = a16; st[17] = a17; st[18] = a18; st[19] = a19;
+  st[20] = a20; st[21] = a21; st[22] = a22; st[23] = a23; st[24] = a24;
 }
 }  // namespace detail
 
 class Sha3_256 {
  public:
   void update(const uint8_t* data, size_t len) {
-    for (size_t i = 0; i < len; i++) {
-      reinterpret_cast<uint8_t*>(st_)[pos_++] ^= data[i];
-      if (pos_ == kRate) { detail::keccak_f(st_); pos_ = 0; }
+    size_t i = 0;
+    for (; i < len && pos_ != 0; i++) absorb_byte(data[i]);  // finish a partial block
+    for (; i + kRate <= len; i += kRate) {                   // whole blocks, a lane at a time (little-endian host)
+      for (size_t j = 0; j < kRate / 8; j++) {
+        uint64_t w;
+        memcpy(&w, data + i + 8 * j, 8);
+        st_[j] ^= w;
+      }
+      detail::keccak_f(st_);
     }
+    for (; i < len; i++) absorb_byte(data[i]);
   }
   std::array<uint8_t, 32> finalize() {
     reinterpret_cast<uint8_t*>(st_)[pos_] ^= 0x06;
@@ -97,9 +113,39 @@ class Sha3_256 {
 
  private:
   static constexpr size_t kRate = 136;
+  void absorb_byte(uint8_t v) {
+    reinterpret_cast<uint8_t*>(st_)[pos_++] ^= v;
+    if (pos_ == kRate) { detail::keccak_f(st_); pos_ = 0; }
+  }
   uint64_t st_[25] = {0};
   size_t pos_ = 0;
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host-side profile (ARKMPC_HOST_PROFILE=1): wall time spent per category, summed over both parties' threads.  At the reference
+// bench's n = 1024 the arithmetic is microseconds; this says where the milliseconds go.
+// ---------------------------------------------------------------------------------------------------------------
+namespace prof {
+enum Cat { kMalloc, kFree, kSync, kH2D, kD2H, kWait, kHash, kSource, kCats };
+inline const char* name(int c) { static const char* n[] = {"malloc", "free", "sync", "h2d", "d2h", "peer_wait", "sha3", "preprocessing"}; return n[c]; }
+inline bool enabled() { static const bool on = [] { const char* e = std::getenv("ARKMPC_HOST_PROFILE"); return e && *e && *e != '0'; }(); return on; }
+inline std::atomic<uint64_t>& ns(int c) { static std::atomic<uint64_t> v[kCats]; return v[c]; }
+inline std::atomic<uint64_t>& calls(int c) { static std::atomic<uint64_t> v[kCats]; return v[c]; }
+struct Scope {
+  int c;
+  std::chrono::steady_clock::time_point t0;
+  explicit Scope(int cat) : c(cat) { if (enabled()) t0 = std::chrono::steady_clock::now(); }
+  ~Scope() {
+    if (!enabled()) return;
+    ns(c) += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    calls(c)++;
+  }
+};
+inline void reset() { for (int c = 0; c < kCats; c++) { ns(c) = 0; calls(c) = 0; } }
+inline void report(FILE* f, double per) {  // `per`: divide by (e.g. the number of iterations)
+  for (int c = 0; c < kCats; c++) fprintf(f, "  %-14s %9.1f us  %6.1f calls\n", name(c), ns(c) / 1e3 / per, calls(c) / per);
+}
+}  // namespace prof
 
 // ---------------------------------------------------------------------------------------------------------------
 // Context and device memory
@@ -118,7 +164,7 @@ class Context {
   void check(int rc, const char* what) const {
     if (rc != ARKMPC_OK) throw MpcError(std::string(what) + ": " + arkmpc_status_string(rc) + ": " + arkmpc_last_error(raw_));
   }
-  void sync() const { check(arkmpc_ctx_sync(raw_), "arkmpc_ctx_sync"); }
+  void sync() const { prof::Scope ps(prof::kSync); check(arkmpc_ctx_sync(raw_), "arkmpc_ctx_sync"); }
 
  private:
   arkmpc_ctx* raw_ = nullptr;
@@ -127,9 +173,10 @@ class Context {
 class DevBuf {
  public:
   DevBuf(std::shared_ptr<Context> ctx, size_t bytes) : ctx_(std::move(ctx)), bytes_(bytes) {
+    prof::Scope ps(prof::kMalloc);
     ctx_->check(arkmpc_malloc(ctx_->raw(), bytes, &p_), "arkmpc_malloc");
   }
-  ~DevBuf() { if (p_) arkmpc_free(ctx_->raw(), p_); }
+  ~DevBuf() { prof::Scope ps(prof::kFree); if (p_) arkmpc_free(ctx_->raw(), p_); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   uint64_t* u64() const { return static_cast<uint64_t*>(p_); }
@@ -184,6 +231,7 @@ class Channel {
  public:
   void put(Message m) { { std::lock_guard<std::mutex> l(mu_); q_.push(std::move(m)); } cv_.notify_one(); }
   Message get() {
+    prof::Scope ps(prof::kWait);
     std::unique_lock<std::mutex> l(mu_);
     cv_.wait(l, [&] { return !q_.empty(); });
     Message m = std::move(q_.front());
@@ -336,13 +384,13 @@ class MpcFabric {
   Buf alloc(size_t bytes) const { return std::make_shared<DevBuf>(ctx_, bytes ? bytes : 32); }
   Buf upload(const uint64_t* host, size_t bytes) const {
     Buf b = alloc(bytes);
-    if (bytes) ctx_->check(arkmpc_memcpy_h2d(raw(), b->u64(), host, bytes), "arkmpc_memcpy_h2d");
-    ctx_->sync();  // the host vector may be a temporary
+    { prof::Scope ps(prof::kH2D); if (bytes) ctx_->check(arkmpc_memcpy_h2d(raw(), b->u64(), host, bytes), "arkmpc_memcpy_h2d"); }
+    // no synchronisation: arkmpc_memcpy_h2d has read a pageable source (every host vector here) when it returns
     return b;
   }
   std::vector<uint64_t> download(const Buf& b, size_t bytes) const {
     std::vector<uint64_t> out(bytes / 8);
-    if (bytes) ctx_->check(arkmpc_memcpy_d2h(raw(), out.data(), b->u64(), bytes), "arkmpc_memcpy_d2h");
+    { prof::Scope ps(prof::kD2H); if (bytes) ctx_->check(arkmpc_memcpy_d2h(raw(), out.data(), b->u64(), bytes), "arkmpc_memcpy_d2h"); }
     ctx_->sync();
     return out;
   }
@@ -359,18 +407,18 @@ class MpcFabric {
     const size_t n = s.n();
     Buf aos = upload(s.aos.data(), n * 64), sh = alloc(n * 32), mc = alloc(n * 32);
     ctx_->check(arkmpc_share_unzip(raw(), n, aos->u64(), sh->u64(), mc->u64()), "arkmpc_share_unzip");
-    ctx_->sync();  // `aos` is released on return
+    // `aos` is released on return: arkmpc_free is ordered after the work submitted so far (include/arkmpc_b200.h, memory)
     return AuthenticatedScalarResult{this, sh, mc, n};
   }
   std::tuple<AuthenticatedScalarResult, AuthenticatedScalarResult, AuthenticatedScalarResult> next_triple_batch(size_t n) {  // fabric.rs:894-915
     std::tuple<HostShares, HostShares, HostShares> t;
-    { std::lock_guard<std::mutex> l(src_mu_); t = src_->next_triplet_batch(n); }
+    { prof::Scope ps(prof::kSource); std::lock_guard<std::mutex> l(src_mu_); t = src_->next_triplet_batch(n); }
     return {allocate_scalar_shares(std::get<0>(t)), allocate_scalar_shares(std::get<1>(t)), allocate_scalar_shares(std::get<2>(t))};
   }
 
   AuthenticatedScalarResult random_shared_scalars(size_t n) {  // fabric.rs:950-965
     HostShares v;
-    { std::lock_guard<std::mutex> l(src_mu_); v = src_->next_shared_value_batch(n); }
+    { prof::Scope ps(prof::kSource); std::lock_guard<std::mutex> l(src_mu_); v = src_->next_shared_value_batch(n); }
     return allocate_scalar_shares(v);
   }
 
@@ -402,12 +450,12 @@ class MpcFabric {
     HostShares mask_shares;
     if (party_ == sender) {
       std::pair<HostScalars, HostShares> m;
-      { std::lock_guard<std::mutex> l(src_mu_); m = src_->next_local_input_mask_batch(n); }
+      { prof::Scope ps(prof::kSource); std::lock_guard<std::mutex> l(src_mu_); m = src_->next_local_input_mask_batch(n); }
       ScalarResult masks = allocate_scalars(m.first);
       masked = share_plaintext(ScalarResult::batch_sub(*vals, masks).values, sender);
       mask_shares = std::move(m.second);
     } else {
-      { std::lock_guard<std::mutex> l(src_mu_); mask_shares = src_->next_counterparty_input_mask_batch(n); }
+      { prof::Scope ps(prof::kSource); std::lock_guard<std::mutex> l(src_mu_); mask_shares = src_->next_counterparty_input_mask_batch(n); }
       masked = share_plaintext(nullptr, sender);
     }
     return AuthenticatedScalarResult::batch_add_public(allocate_scalar_shares(mask_shares), ScalarResult{this, masked, n});
@@ -418,7 +466,7 @@ class MpcFabric {
     HostShares mask_shares;
     if (party_ == sender) {
       std::pair<HostScalars, HostShares> m;
-      { std::lock_guard<std::mutex> l(src_mu_); m = src_->next_local_input_mask_batch(n); }
+      { prof::Scope ps(prof::kSource); std::lock_guard<std::mutex> l(src_mu_); m = src_->next_local_input_mask_batch(n); }
       ScalarResult masks = allocate_scalars(m.first);
       Buf mg = alloc(n * pb), diff = alloc(n * pb);
       ctx_->check(arkmpc_pt_mul_generator_public(raw(), cv_.curve, n, masks.values->u64(), mg->u64()), "arkmpc_pt_mul_generator_public");
@@ -426,7 +474,7 @@ class MpcFabric {
       masked = share_plaintext(diff, sender);
       mask_shares = std::move(m.second);
     } else {
-      { std::lock_guard<std::mutex> l(src_mu_); mask_shares = src_->next_counterparty_input_mask_batch(n); }
+      { prof::Scope ps(prof::kSource); std::lock_guard<std::mutex> l(src_mu_); mask_shares = src_->next_counterparty_input_mask_batch(n); }
       masked = share_plaintext(nullptr, sender);
     }
     AuthenticatedPointResult masks_g = AuthenticatedPointResult::batch_mul_generator(allocate_scalar_shares(mask_shares));
@@ -435,6 +483,7 @@ class MpcFabric {
 
   // commitment.rs:63-89
   Limbs commit(const std::vector<uint8_t>& value_bytes, const Limbs& blinder_plain) const {
+    prof::Scope ps(prof::kHash);
     Sha3_256 h;
     h.update(value_bytes.data(), value_bytes.size());
     uint8_t be[32];
@@ -494,7 +543,8 @@ class PartyIDBeaverSource : public PreprocessingPhase {
   std::pair<HostScalars, HostShares> next_local_input_mask_batch(size_t n) override {
     HostScalars m;
     Limbs three = mont_(3);
-    for (size_t i = 0; i < n; i++) m.limbs.insert(m.limbs.end(), three.begin(), three.end());
+    m.limbs.resize(n * 4);
+    for (size_t i = 0; i < n; i++) memcpy(m.limbs.data() + 4 * i, three.data(), 32);
     return {m, fill(party_ * 3, party_ * 3, n)};
   }
   HostShares next_counterparty_input_mask_batch(size_t n) override { return fill(3 * party_, party_ * 3 * party_, n); }
@@ -504,8 +554,9 @@ class PartyIDBeaverSource : public PreprocessingPhase {
   HostShares fill(uint64_t share, uint64_t mac, size_t n) {
     Limbs s = mont_(share), m = mont_(mac);
     HostShares out;
-    out.aos.reserve(n * 8);
-    for (size_t i = 0; i < n; i++) { out.aos.insert(out.aos.end(), s.begin(), s.end()); out.aos.insert(out.aos.end(), m.begin(), m.end()); }
+    out.aos.resize(n * 8);
+    uint64_t* w = out.aos.data();
+    for (size_t i = 0; i < n; i++, w += 8) { memcpy(w, s.data(), 32); memcpy(w + 4, m.data(), 32); }
     return out;
   }
   uint64_t party_;
@@ -625,7 +676,7 @@ inline AuthenticatedScalarResult AuthenticatedScalarResult::batch_mul(const Auth
   f->ctx()->check(arkmpc_fr_beaver_recombine(f->raw(), fid, f->party_id(), f->mac_key().data(), n, de_mine->u64(), de_mine->at(n * 32), de_peer->u64(),
                                              de_peer->at(n * 32), ba.share->u64(), ba.mac->u64(), bb.share->u64(), bb.mac->u64(), bc.share->u64(),
                                              bc.mac->u64(), s->u64(), m->u64(), nullptr, nullptr), "arkmpc_fr_beaver_recombine");
-  f->ctx()->sync();  // the triple planes and de buffers are released on return
+  // the triple planes and de buffers are released on return; arkmpc_free orders their reuse after this kernel
   f->count_gate(2);
   return {f, s, m, n};
 }
@@ -636,7 +687,6 @@ inline ScalarResult AuthenticatedScalarResult::open_batch(const AuthenticatedSca
   Buf peer = f->exchange(v.share);
   Buf o = f->alloc(v.n * 32);
   f->ctx()->check(arkmpc_fr_add(f->raw(), f->curve().field, v.n, v.share->u64(), peer->u64(), o->u64()), "open_batch");
-  f->ctx()->sync();
   f->count_gate();
   return {f, o, v.n};
 }
@@ -777,7 +827,6 @@ inline AuthenticatedPointResult AuthenticatedPointResult::batch_mul(const Authen
   f->ctx()->check(arkmpc_pt_beaver_recombine(f->raw(), cid, f->party_id(), f->mac_key().data(), n, d_mine->u64(), d_peer->u64(), E_mine->u64(), E_peer->u64(),
                                              ba.share->u64(), ba.mac->u64(), bb.share->u64(), bb.mac->u64(), bc.share->u64(), bc.mac->u64(), out->u64(),
                                              nullptr, nullptr), "arkmpc_pt_beaver_recombine");
-  f->ctx()->sync();
   f->count_gate(2);
   return {f, out, n};
 }
@@ -790,7 +839,6 @@ inline CurvePointResult AuthenticatedPointResult::open_batch(const Authenticated
   Buf peer = f->exchange(mine);
   Buf o = f->alloc(n * pb);
   f->ctx()->check(arkmpc_pt_add(f->raw(), f->curve().curve, n, mine->u64(), peer->u64(), o->u64()), "open_batch");
-  f->ctx()->sync();
   f->count_gate();
   return {f, o, n};
 }

@@ -91,12 +91,24 @@ const char* arkmpc_last_error(arkmpc_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t arkmpc_ctx_launch_count(arkmpc_ctx* ctx);
 
-/* ---- memory ---- */
+/* ---- memory ----
+ * The reference allocates a fresh Vec per gate result (fabric/result.rs:47-64); a host that mirrors it allocates and frees
+ * tens of device buffers per batch.  arkmpc_free therefore does not return memory to the driver: the block goes to a
+ * per-device cache (by size class) and the next arkmpc_malloc of that class gets it back without any host synchronisation.
+ * Ordering: arkmpc_free covers the work submitted SO FAR on the current stream of every live context of the device (device
+ * buffers travel between the parties' contexts by reference), and the stream of the context that receives the block waits
+ * for it; work the caller submitted on any other stream must be synchronised before the free.  arkmpc_mem_trim returns the
+ * cached blocks to the driver (synchronising); ARKMPC_ALLOC_CACHE_MB caps the cache (default 4096, 0 = cudaMalloc / cudaFree). */
 int arkmpc_malloc(arkmpc_ctx* ctx, size_t bytes, void** dev_ptr);
 int arkmpc_free(arkmpc_ctx* ctx, void* dev_ptr);
+int arkmpc_mem_trim(arkmpc_ctx* ctx);
+int arkmpc_mem_cached_bytes(arkmpc_ctx* ctx, size_t* bytes); /* bytes held in free blocks on the context's device */
 int arkmpc_host_alloc(arkmpc_ctx* ctx, size_t bytes, void** pinned_ptr); /* pinned host memory */
 int arkmpc_host_free(arkmpc_ctx* ctx, void* pinned_ptr);
-int arkmpc_memcpy_h2d(arkmpc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* async on stream */
+/* Asynchronous on the context stream.  A source of up to 256 KB, and any pageable source, has been read when the call
+ * returns (small copies are staged through a pinned ring); a larger pinned source must stay valid until the stream is
+ * synchronised. */
+int arkmpc_memcpy_h2d(arkmpc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int arkmpc_memcpy_d2h(arkmpc_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on stream */
 int arkmpc_memcpy_d2d(arkmpc_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
 

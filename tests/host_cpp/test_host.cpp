@@ -184,7 +184,24 @@ static void test_points(const CurveInfo& cv, const char* name) {
   printf("%s: point gates done\n", name);
 }
 
-int main() {
+// `test_host --sha3 <len> <seed>`: digest of a deterministic message (byte i = (seed + 131 * i) >> 3), fed in three uneven pieces,
+// so that the commitment hash can be compared with hashlib on a box without a GPU
+static int sha3_mode(size_t len, unsigned seed) {
+  std::vector<uint8_t> msg(len);
+  for (size_t i = 0; i < len; i++) msg[i] = (uint8_t)((seed + 131u * i) >> 3);
+  Sha3_256 h;
+  const size_t c1 = len / 3, c2 = len / 3 + (len > 7 ? 7 : 0);
+  h.update(msg.data(), c1);
+  h.update(msg.data() + c1, c2 - c1 > len - c1 ? len - c1 : c2 - c1);
+  const size_t done = c1 + (c2 - c1 > len - c1 ? len - c1 : c2 - c1);
+  h.update(msg.data() + done, len - done);
+  for (uint8_t b : h.finalize()) printf("%02x", b);
+  printf("\n");
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc == 4 && std::string(argv[1]) == "--sha3") return sha3_mode((size_t)atol(argv[2]), (unsigned)atol(argv[3]));
   int count = 0;
   if (arkmpc_device_count(&count) != ARKMPC_OK || count == 0) { printf("no CUDA device: the host mirror has no CPU fallback\n"); return 2; }
   for (auto& kv : {std::make_pair(bn254(), "bn254"), std::make_pair(curve25519(), "curve25519")}) {

@@ -382,3 +382,87 @@ def test_independence_hint_keeps_results_and_ordering(engines, fid, n):
             assert np.array_equal(dn(E, out[p][0]), want[:, :4]) and np.array_equal(dn(E, out[p][1]), want[:, 4:]), f"rep {rep} party {p}"
     for p, want in ((0, o0), (1, o1)):
         assert np.array_equal(dn(E, out[p][0]), want[:, :4]) and np.array_equal(dn(E, out[p][1]), want[:, 4:])
+
+
+def test_device_memory_cache_reuses_blocks_in_stream_order():
+    """arkmpc_malloc / arkmpc_free (include/arkmpc_b200.h, memory): a freed block is handed to ANOTHER context without a host
+    synchronisation, and that context's writes still land after the work the first context had in flight on the block."""
+    import ctypes as C
+
+    import torch
+
+    import ark_mpc_b200._native as nat
+
+    lib = nat.load()
+    ctx = [C.c_void_p(), C.c_void_p()]
+    for c in ctx:
+        nat.check(lib.arkmpc_ctx_create(0, C.byref(c)), "arkmpc_ctx_create")
+    try:
+        n = 1 << 22
+        nbytes = n * 32
+        nat.check(lib.arkmpc_mem_trim(ctx[0]), "trim", ctx[0])
+        held = C.c_size_t(1)
+        nat.check(lib.arkmpc_mem_cached_bytes(ctx[0], C.byref(held)), "cached", ctx[0])
+        assert held.value == 0
+        dev = torch.device("cuda:0")
+        x, y, keep, want = (torch.empty((n, 4), dtype=torch.int64, device=dev) for _ in range(4))
+        torch.cuda.synchronize()
+        u64 = lambda t: C.c_void_p(t.data_ptr())
+        a = C.c_void_p()
+        nat.check(lib.arkmpc_malloc(ctx[0], nbytes - 8, C.byref(a)), "malloc", ctx[0])  # rounds up to a 2 MiB multiple
+        pa = a
+        nat.check(lib.arkmpc_fr_random(ctx[0], 0, 11, 0, n, u64(want)), "random", ctx[0])
+        nat.check(lib.arkmpc_fr_random(ctx[0], 0, 11, 0, n - 1, pa), "random", ctx[0])
+        nat.check(lib.arkmpc_fr_random(ctx[0], 0, 5, 0, n, u64(x)), "random", ctx[0])
+        for _ in range(24):  # ~10 ms of work queued on context 0 ahead of the read of the block
+            nat.check(lib.arkmpc_fr_batch_inverse(ctx[0], 0, n, u64(x), u64(y)), "inverse", ctx[0])
+        nat.check(lib.arkmpc_memcpy_d2d(ctx[0], C.c_void_p(keep.data_ptr()), a, (n - 1) * 32), "d2d", ctx[0])
+        nat.check(lib.arkmpc_free(ctx[0], a), "free", ctx[0])
+        nat.check(lib.arkmpc_mem_cached_bytes(ctx[0], C.byref(held)), "cached", ctx[0])
+        assert held.value == nbytes  # (n * 32 - 8) rounded up to the 2 MiB class
+        b = C.c_void_p()
+        nat.check(lib.arkmpc_malloc(ctx[1], nbytes, C.byref(b)), "malloc", ctx[1])
+        assert b.value == a.value  # the cached block, no cudaMalloc
+        nat.check(lib.arkmpc_fr_random(ctx[1], 0, 99, 0, n, b), "random", ctx[1])  # overwrites it
+        for c in ctx:
+            nat.check(lib.arkmpc_ctx_sync(c), "sync", c)
+        assert torch.equal(keep[: n - 1], want[: n - 1])  # the copy read the block before context 1's kernel wrote it
+        nat.check(lib.arkmpc_free(ctx[1], b), "free", ctx[1])
+        nat.check(lib.arkmpc_mem_trim(ctx[1]), "trim", ctx[1])
+        nat.check(lib.arkmpc_mem_cached_bytes(ctx[1], C.byref(held)), "cached", ctx[1])
+        assert held.value == 0
+    finally:
+        for c in ctx:
+            lib.arkmpc_ctx_destroy(c)
+
+
+def test_small_host_to_device_copies_are_staged_and_release_the_source():
+    """arkmpc_memcpy_h2d: copies of up to 256 KB go through a pinned ring of 8 slots; the source may be overwritten as soon as
+    the call returns, and more copies than slots in a row stay correct."""
+    import ctypes as C
+
+    import torch
+
+    import ark_mpc_b200._native as nat
+
+    lib = nat.load()
+    ctx = C.c_void_p()
+    nat.check(lib.arkmpc_ctx_create(0, C.byref(ctx)), "arkmpc_ctx_create")
+    try:
+        rng = np.random.default_rng(5)
+        sizes = [32, 100, 4096, 32 * 1024, 256 * 1024, 256 * 1024 + 32, 1 << 20] * 5
+        total = sum(sizes)
+        devbuf = torch.zeros(total, dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize()
+        want = np.empty(total, dtype=np.uint8)
+        off = 0
+        for s in sizes:
+            src = rng.integers(0, 256, s, dtype=np.uint8)
+            want[off:off + s] = src
+            nat.check(lib.arkmpc_memcpy_h2d(ctx, C.c_void_p(devbuf.data_ptr() + off), src.ctypes.data_as(C.c_void_p), s), "h2d", ctx)
+            src[:] = 0xEE  # pageable source: consumed when the call returns
+            off += s
+        nat.check(lib.arkmpc_ctx_sync(ctx), "sync", ctx)
+        assert np.array_equal(devbuf.cpu().numpy(), want)
+    finally:
+        lib.arkmpc_ctx_destroy(ctx)

@@ -67,6 +67,17 @@ def test_host_mirror_compiles_against_the_c_abi_only():
     assert os.path.exists(exe)
 
 
+@pytest.mark.parametrize("length", [0, 1, 3, 135, 136, 137, 271, 272, 32 * 1024 + 32, 100003])
+def test_host_mirror_sha3_matches_hashlib(length):
+    """The commitment hash of open_authenticated (commitment.rs:36-41, `sha3` crate) is SHA3-256 of FIPS 202."""
+    import hashlib
+
+    seed = 17 + length
+    r = subprocess.run([build(), "--sha3", str(length), str(seed)], capture_output=True, text=True, timeout=120)
+    msg = bytes(((seed + 131 * i) & 0xFFFFFFFF) >> 3 & 0xFF for i in range(length))
+    assert r.returncode == 0 and r.stdout.strip() == hashlib.sha3_256(msg).hexdigest()
+
+
 def test_host_mirror_refuses_to_run_without_a_gpu(has_gpu):
     if has_gpu:
         pytest.skip("GPU present")

@@ -190,15 +190,18 @@ def test_constant_multiplier_table(emu, name, fid):
 
 @pytest.mark.parametrize("name,fid", FIELDS)
 def test_binary_euclid_inversion(emu, name, fid):
-    """Fp::inv_plain (binary extended Euclid on plain integers) and Fp::inv_mont (Montgomery image in, Montgomery image out): the
-    single inversion at the top of the batch-inversion product tree (scalar.rs:93-100 -> ark_ff::batch_inversion)."""
+    """Fp::inv_plain (binary extended Euclid), Fp::inv_safegcd (Bernstein-Yang division steps, radix 2^30) and Fp::inv_mont
+    (Montgomery image in, Montgomery image out): the inversions at the top of the batch-inversion product tree (scalar.rs:93-100
+    -> ark_ff::batch_inversion)."""
     F = po.FIELDS[name]
     rng = random.Random(60 + fid)
     vals = [1, 2, 3, F.p - 1, F.p - 2, (F.p - 1) // 2, (F.p + 1) // 2, 1 << 255 if F.p > 1 << 255 else 1 << 252, (1 << 128) - 1, F.r, F.r2]
-    vals += [rng.randrange(1, F.p) for _ in range(150)]
+    vals += [(1 << k) % F.p for k in range(1, 256, 7)] + [F.p - (1 << k) for k in range(0, 250, 11)] + [(1 << 30) - 1, 1 << 30, (1 << 60) + 1]
+    vals += [rng.randrange(1, F.p) for _ in range(400)]
     for a in vals:
         a %= F.p
         if a == 0:
             continue
+        assert emu(fid, 19, [a], 1)[0] == pow(a, -1, F.p)
         assert emu(fid, 17, [a], 1)[0] == pow(a, -1, F.p)
         assert emu(fid, 18, [F.to_mont(a)], 1)[0] == F.to_mont(pow(a, -1, F.p))

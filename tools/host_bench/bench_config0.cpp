@@ -32,6 +32,7 @@ int main(int argc, char** argv) {
   std::vector<double> times;
   std::vector<uint64_t> first;
   for (int it = 0; it < iters + 3; it++) {
+    if (it == 3) prof::reset();
     using Out = std::pair<double, std::vector<uint64_t>>;
     auto res = execute_mock_mpc<Out>(cv, source, [&](MpcFabric& f) {
       const auto t0 = std::chrono::steady_clock::now();
@@ -54,5 +55,9 @@ int main(int argc, char** argv) {
   for (uint64_t w : first) chk = chk * 1000003u + w;
   printf("{\"n\": %zu, \"iters\": %d, \"field\": \"%s\", \"median_s\": %.9f, \"min_s\": %.9f, \"mults_per_s\": %.1f, \"opened_checksum\": \"%016llx\"}\n", n,
          iters, c25519 ? "curve25519_fr" : "bn254_fr", med, times.front(), n / med, (unsigned long long)chk);
+  if (prof::enabled()) {
+    fprintf(stderr, "host profile, per iteration, both parties' threads summed (wall %.1f us per iteration):\n", med * 1e6);
+    prof::report(stderr, iters);
+  }
   return 0;
 }
