@@ -102,18 +102,19 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
     sizes[levels + 1] = (sizes[levels] + kInvGroup - 1) / kInvGroup;
     levels++;
   }
-  // scratch: the group products x_(l+1) (n_(l+1) elements) and their inverses, for every level above the input
+  // scratch per level above the input: the six inner products of every group (6 n_(l+1)), the group products x_(l+1) and their inverses
   size_t elems = 0;
-  for (int l = 0; l < levels; l++) elems += 2 * sizes[l + 1];
+  for (int l = 0; l < levels; l++) elems += 8 * sizes[l + 1];
   cudaStream_t s = ctx->stream;
   char* scratch = nullptr;
   if (elems) ARK_CUDA(ctx, cudaMallocAsync(&scratch, elems * 32, s));
   const char* xs[16];
-  char* inv[16];
+  char *inv[16], *tree[16];
   xs[0] = reinterpret_cast<const char*>(a);
   inv[0] = reinterpret_cast<char*>(out);
   char* p = scratch;
   for (int l = 0; l < levels; l++) {
+    tree[l] = p; p += 6 * sizes[l + 1] * 32;
     xs[l + 1] = p; p += sizes[l + 1] * 32;
     inv[l + 1] = p; p += sizes[l + 1] * 32;
   }
@@ -121,7 +122,7 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
   int rc = ARKMPC_OK;
   ARK_FIELD_SWITCH(ctx, field, {
     for (int l = 0; l < levels && rc == ARKMPC_OK; l++) {
-      fr_inv_up_kernel<F><<<blocks(sizes[l + 1]), kInvBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(const_cast<char*>(xs[l + 1])));
+      fr_inv_up_kernel<F><<<blocks(sizes[l + 1]), kInvBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
       rc = post_launch(ctx, "fr_inv_up_kernel");
     }
     if (rc == ARKMPC_OK) {
@@ -129,7 +130,7 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
       rc = post_launch(ctx, "fr_inv_top_kernel");
     }
     for (int l = levels - 1; l >= 0 && rc == ARKMPC_OK; l--) {
-      fr_inv_down_kernel<F><<<blocks(sizes[l + 1]), kInvBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(inv[l + 1]), mvec(inv[l]));
+      fr_inv_down_kernel<F><<<blocks(sizes[l + 1]), kInvBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
       rc = post_launch(ctx, "fr_inv_down_kernel");
     }
   });

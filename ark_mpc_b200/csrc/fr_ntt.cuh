@@ -15,15 +15,15 @@ namespace ark {
 // ---------------------------------------------------------------------------------------------
 // Batch inversion (scalar.rs:93-100 -> ark_ff::batch_inversion: zeros stay zero): Montgomery's trick as a product TREE.
 //   up    every thread multiplies a group of kInvGroup = 8 elements (element j of group g is x[g + j*groups]: coalesced) as a
-//         balanced binary tree — 4 + 2 + 1 multiplications, depth 3 — and hands the group product to the next level; levels
-//         shrink by 8 until <= kInvTop remain.  Zeros (and the padding of a ragged last group) enter the product as one;
+//         balanced binary tree — 4 + 2 + 1 multiplications, depth 3 — keeps the six inner products and hands the group product
+//         to the next level; levels shrink by 8 until <= kInvTop remain.  Zeros (and the padding of a ragged last group) enter
+//         the product as one;
 //   top   one safegcd inversion per remaining element (Fp::inv_mont): up to 16 k of them cost the latency of one, a warp per
 //         SM sub-partition;
-//   down  every thread rebuilds its group's tree from the inputs (6 multiplications instead of 8 stored partial products: at
-//         2^20 the stores and re-loads were 64 MB of traffic and an eight-deep dependent chain) and walks it down: the inverse
-//         of a node times its sibling's product is the inverse of the other child — 2 + 4 + 8 independent multiplications.
-// 27 multiplications per 8 elements, dependent depth 3 + 3 (the serial prefix form: 24, depth 7 + 8, and 12 % occupancy gave
-// nothing to hide it behind), and ONE inversion latency on the critical path — round 1 ran a 380-multiplication Fermat chain per
+//   down  every thread walks its group's tree down: the inverse of a node times its sibling's product is the inverse of the
+//         other child — 2 + 4 + 8 independent multiplications.
+// 21 multiplications per 8 elements with dependent depth 3 + 3 (the serial prefix form: 24, depth 7 + 8, and at 12 % occupancy
+// nothing hides that chain), and ONE inversion latency on the critical path — round 1 ran a 380-multiplication Fermat chain per
 // 32 elements on n/32 threads: 320 us at n = 2^16 and at 2^20.
 // ---------------------------------------------------------------------------------------------
 constexpr int kInvGroup = 8;
@@ -48,15 +48,21 @@ __device__ __forceinline__ uint32_t inv_load_group(fe8 (&z)[kInvGroup], size_t n
 }
 
 template <class F>
-__global__ void __launch_bounds__(kInvBlock) fr_inv_up_kernel(size_t n, size_t groups, Vec x, MVec prod) {
+__global__ void __launch_bounds__(kInvBlock) fr_inv_up_kernel(size_t n, size_t groups, Vec x, MVec tree, MVec prod) {
   const size_t g = (size_t)blockIdx.x * kInvBlock + threadIdx.x;
   if (g >= groups) return;
   fe8 z[kInvGroup];
   (void)inv_load_group<F>(z, n, groups, g, x);
+  // tree[k * groups + g]: k = 0..3 the pair products, 4..5 the products of four
 #pragma unroll
-  for (int j = 0; j < 8; j += 2) Fp<F>::mul(z[j], z[j], z[j + 1]);
+  for (int k = 0; k < 4; k++) {
+    Fp<F>::mul(z[2 * k], z[2 * k], z[2 * k + 1]);
+    st_fe(tree, (size_t)k * groups + g, z[2 * k]);
+  }
   Fp<F>::mul(z[0], z[0], z[2]);
   Fp<F>::mul(z[4], z[4], z[6]);
+  st_fe(tree, 4 * groups + g, z[0]);
+  st_fe(tree, 5 * groups + g, z[4]);
   Fp<F>::mul(z[0], z[0], z[4]);
   st_fe(prod, g, z[0]);
 }
@@ -75,16 +81,16 @@ __global__ void __launch_bounds__(kInvTopBlock) fr_inv_top_kernel(size_t n, Vec 
 }
 
 template <class F>
-__global__ void __launch_bounds__(kInvBlock) fr_inv_down_kernel(size_t n, size_t groups, Vec x, Vec ginv, MVec out) {
+__global__ void __launch_bounds__(kInvBlock) fr_inv_down_kernel(size_t n, size_t groups, Vec x, Vec tree, Vec ginv, MVec out) {
   const size_t g = (size_t)blockIdx.x * kInvBlock + threadIdx.x;
   if (g >= groups) return;
   fe8 z[kInvGroup], p[4], q[2], inv;
   ld_fe(inv, ginv, g);
-  const uint32_t live = inv_load_group<F>(z, n, groups, g, x);
 #pragma unroll
-  for (int k = 0; k < 4; k++) Fp<F>::mul(p[k], z[2 * k], z[2 * k + 1]);
-  Fp<F>::mul(q[0], p[0], p[1]);
-  Fp<F>::mul(q[1], p[2], p[3]);
+  for (int k = 0; k < 4; k++) ld_fe(p[k], tree, (size_t)k * groups + g);
+  ld_fe(q[0], tree, 4 * groups + g);
+  ld_fe(q[1], tree, 5 * groups + g);
+  const uint32_t live = inv_load_group<F>(z, n, groups, g, x);
   fe8 iq[2], ip[4];
   Fp<F>::mul(iq[0], inv, q[1]);
   Fp<F>::mul(iq[1], inv, q[0]);

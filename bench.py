@@ -554,6 +554,11 @@ def measure_config0(local_rank, iters=20):
             if "error" not in j:
                 cpp = {"value": j["mults_per_s"], "ms_per_iter": 1e3 * j["median_s"], "ms_per_iter_min": 1e3 * j["min_s"], "iters": j["iters"],
                        "host": "tools/host_bench/bench_config0.cpp over host/arkmpc_host.hpp (compiled C++ mirror, two threads)"}
+                # the same flow at 64 x the batch: where the fixed per-iteration host latency stops dominating
+                r = subprocess.run([exe, str(64 * n), "10", "1"], capture_output=True, text=True, timeout=300)
+                j = json.loads(r.stdout.strip().splitlines()[-1])
+                if "error" not in j:
+                    cpp["at_batch_%d" % (64 * n)] = {"value": j["mults_per_s"], "ms_per_iter": 1e3 * j["median_s"]}
         except Exception as ex:  # noqa: BLE001
             cpp = {"error": repr(ex)[:200]}
     best = cpp if cpp and "value" in cpp else py
@@ -564,7 +569,8 @@ def measure_config0(local_rank, iters=20):
                       "field": field, "batch": n, "parties": 2},
            "note": "host wall clock from inside each party's closure to the opened values on the host, slower party, median; `value` is the compiled "
                    "C++ host mirror when its binary is present (python_mirror beside it); at n = 1024 the GPU path is bound by ~25 kernel launches, "
-                   "8 message hand-offs and two host SHA3 commitments per party, not by arithmetic",
+                   "8 message hand-offs, 30 device buffers and two host SHA3 commitments per party (host profile: ARKMPC_HOST_PROFILE=1 "
+                   "tools/host_bench/bench_config0; profiles/r02p_config0_profile.txt), not by arithmetic",
            "roofline": None}
     # CPU arm: the same gate sequence restated in C, both parties, arithmetic only (no executor, no commitment hash)
     from oracle import coracle as co
