@@ -174,10 +174,12 @@ int arkmpc_ctx_destroy(arkmpc_ctx* ctx) {
   if (!ctx) return ARKMPC_OK;
   {
   CallGuard guard(ctx);
-  mem_unregister(ctx);  // arkmpc_free stops recording events on this context's stream ...
-  if (ctx->stream && ctx->stream != ctx->own_stream) cudaStreamSynchronize(ctx->stream);  // ... so what it still runs finishes here
+  // what this context still runs finishes here; only then does the memory cache stop ordering reuse after its stream
+  if (ctx->stream && ctx->stream != ctx->own_stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  mem_unregister(ctx);
   arkmpc_nccl_destroy(ctx);
-  if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   for (int i = 0; i < kSlots; i++) {
     if (ctx->slot_stream[i]) { cudaStreamSynchronize(ctx->slot_stream[i]); cudaStreamDestroy(ctx->slot_stream[i]); }
     if (ctx->slot_event[i]) cudaEventDestroy(ctx->slot_event[i]);

@@ -118,11 +118,12 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
     xs[l + 1] = p; p += sizes[l + 1] * 32;
     inv[l + 1] = p; p += sizes[l + 1] * 32;
   }
-  auto blocks = [](size_t work) { return (unsigned)((work + kInvBlock - 1) / kInvBlock); };
+  static const int inv_block = [] { const char* e = getenv("ARKMPC_INV_BLOCK"); const int v = e ? atoi(e) : 0; return v == 32 || v == 64 || v == 128 ? v : kInvLaunchBlock; }();
+  auto blocks = [](size_t work) { return (unsigned)((work + inv_block - 1) / inv_block); };
   int rc = ARKMPC_OK;
   ARK_FIELD_SWITCH(ctx, field, {
     for (int l = 0; l < levels && rc == ARKMPC_OK; l++) {
-      fr_inv_up_kernel<F><<<blocks(sizes[l + 1]), kInvBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
+      fr_inv_up_kernel<F><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
       rc = post_launch(ctx, "fr_inv_up_kernel");
     }
     if (rc == ARKMPC_OK) {
@@ -130,7 +131,7 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
       rc = post_launch(ctx, "fr_inv_top_kernel");
     }
     for (int l = levels - 1; l >= 0 && rc == ARKMPC_OK; l--) {
-      fr_inv_down_kernel<F><<<blocks(sizes[l + 1]), kInvBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
+      fr_inv_down_kernel<F><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
       rc = post_launch(ctx, "fr_inv_down_kernel");
     }
   });

@@ -57,6 +57,7 @@ struct arkmpc_ctx {
   cudaStream_t ntt_stream[2] = {nullptr, nullptr};  // the stream each table was built on
   long ntt_key[2] = {-1, -1};            // FFT -> batch_mul -> IFFT (authenticated_poly.rs:377-401) alternates directions without rebuilding
   void* nccl = nullptr;      // ncclComm_t of arkmpc_nccl_init (arkmpc_comm.cu)
+  void* stage_ring = nullptr;  // pinned staging ring of arkmpc_memcpy_h2d (arkmpc_mem.cu), borrowed from the device's pool on first use
   int nccl_world = 0, nccl_rank = -1;
 };
 

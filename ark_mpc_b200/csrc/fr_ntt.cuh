@@ -28,7 +28,9 @@ namespace ark {
 // ---------------------------------------------------------------------------------------------
 constexpr int kInvGroup = 8;
 constexpr size_t kInvTop = 16384;
-constexpr int kInvBlock = 128;  // 2^17 groups at n = 2^20: 1024 blocks spread evenly over 148 SMs (256-thread blocks: 3 or 4 per SM)
+constexpr int kInvBlock = 128;  // upper bound (launch bounds); the sweeps are launched with 64-thread blocks: at n = 2^20 the down sweep's 2^17
+                                 // threads at 134 registers are 1.98 waves of 7 blocks per SM (128-thread blocks: 2.31 waves of 3, a third of the last one idle)
+constexpr int kInvLaunchBlock = 64;
 
 // loads the eight elements of group g (all loads issued before the first use), replaces zeros and out-of-range slots by one and
 // returns the mask of the slots that hold a non-zero input
@@ -49,7 +51,7 @@ __device__ __forceinline__ uint32_t inv_load_group(fe8 (&z)[kInvGroup], size_t n
 
 template <class F>
 __global__ void __launch_bounds__(kInvBlock) fr_inv_up_kernel(size_t n, size_t groups, Vec x, MVec tree, MVec prod) {
-  const size_t g = (size_t)blockIdx.x * kInvBlock + threadIdx.x;
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= groups) return;
   fe8 z[kInvGroup];
   (void)inv_load_group<F>(z, n, groups, g, x);
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(kInvTopBlock) fr_inv_top_kernel(size_t n, Vec 
 
 template <class F>
 __global__ void __launch_bounds__(kInvBlock) fr_inv_down_kernel(size_t n, size_t groups, Vec x, Vec tree, Vec ginv, MVec out) {
-  const size_t g = (size_t)blockIdx.x * kInvBlock + threadIdx.x;
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= groups) return;
   fe8 z[kInvGroup], p[4], q[2], inv;
   ld_fe(inv, ginv, g);

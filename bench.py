@@ -582,14 +582,20 @@ def measure_config0(local_rank, iters=20):
     ins = (D.keys, g(D.x), g(D.y), g(D.a), g(D.b), g(D.c))
     v = D.x[0][0]  # a public (n,4) plane for the input-sharing add_public
 
+    import hashlib
+
+    blinder = bytes(32)
+
     def cpu_iter():
         for sh in (ins[1], ins[2]):  # batch_share_scalar: mask shares + add_public of the masked value, both parties
             for pid in (0, 1):
                 co.batch_add_public(fid, pid, D.keys[pid], sh[pid], v)
         o0, o1, _, _ = co.two_party_batch_mul(fid, 1, *ins, want_open=False)
         opened = co.scalar_add(fid, np.ascontiguousarray(o0[:, :4]), np.ascontiguousarray(o1[:, :4]))
-        for pid, o in ((0, o0), (1, o1)):
-            co.mac_check(fid, D.keys[pid], opened, o)
+        checks = [co.mac_check(fid, D.keys[pid], opened, o) for pid, o in ((0, o0), (1, o1))]
+        for pid in (0, 1):  # HashCommitment of the own MAC-check vector, then of the peer's to verify it (commitment.rs:63-89)
+            for who in (pid, 1 - pid):
+                hashlib.sha3_256(np.ascontiguousarray(checks[who]).tobytes() + blinder).digest()
 
     cpu_iter()
     t0 = time.perf_counter()
@@ -598,9 +604,9 @@ def measure_config0(local_rank, iters=20):
         cpu_iter()
     dt = (time.perf_counter() - t0) / reps
     out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                           "sample": f"{reps} iterations of the same 1024-gate flow (input sharing add_public x2, unfused batch_mul, open, MAC-check vector), both "
-                                     "parties on one thread, arithmetic only: omits the reference executor, its per-element result bookkeeping and the "
-                                     "commitment hash, so it flatters the reference"}
+                           "sample": f"{reps} iterations of the same 1024-gate flow (input sharing add_public x2, unfused batch_mul, open, MAC-check vector, "
+                                     "the two SHA3 commitments per party through hashlib), both parties on ONE thread (the reference runs them on two); "
+                                     "omits the reference executor and its per-element result bookkeeping, so it flatters the reference"}
     return out
 
 

@@ -17,6 +17,7 @@
 // mismatch (authenticated_scalar.rs:852) -> std::invalid_argument here; empty batches return empty results (:854-856).
 // `ark_mpc_b200/fabric.py` is the same mirror for the Python test-suite; tests/host_cpp/test_host.cpp exercises this one.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <atomic>
 #include <chrono>
@@ -555,8 +556,11 @@ class PartyIDBeaverSource : public PreprocessingPhase {
     Limbs s = mont_(share), m = mont_(mac);
     HostShares out;
     out.aos.resize(n * 8);
+    if (n == 0) return out;
     uint64_t* w = out.aos.data();
-    for (size_t i = 0; i < n; i++, w += 8) { memcpy(w, s.data(), 32); memcpy(w + 4, m.data(), 32); }
+    memcpy(w, s.data(), 32);
+    memcpy(w + 4, m.data(), 32);
+    for (size_t have = 1; have < n; have *= 2) memcpy(w + 8 * have, w, 64 * std::min(have, n - have));  // doubling fill
     return out;
   }
   uint64_t party_;

@@ -95,9 +95,10 @@ uint64_t arkmpc_ctx_launch_count(arkmpc_ctx* ctx);
  * The reference allocates a fresh Vec per gate result (fabric/result.rs:47-64); a host that mirrors it allocates and frees
  * tens of device buffers per batch.  arkmpc_free therefore does not return memory to the driver: the block goes to a
  * per-device cache (by size class) and the next arkmpc_malloc of that class gets it back without any host synchronisation.
- * Ordering: arkmpc_free covers the work submitted SO FAR on the current stream of every live context of the device (device
- * buffers travel between the parties' contexts by reference), and the stream of the context that receives the block waits
- * for it; work the caller submitted on any other stream must be synchronised before the free.  arkmpc_mem_trim returns the
+ * Ordering: the stream of the context that receives a cached block waits for everything submitted, up to that moment, on
+ * the current stream of every live context of the device (device buffers travel between the parties' contexts by
+ * reference, so any of them may still be working on the block); work the caller submitted on any other stream must be
+ * synchronised before the free.  arkmpc_mem_trim returns the
  * cached blocks to the driver (synchronising); ARKMPC_ALLOC_CACHE_MB caps the cache (default 4096, 0 = cudaMalloc / cudaFree). */
 int arkmpc_malloc(arkmpc_ctx* ctx, size_t bytes, void** dev_ptr);
 int arkmpc_free(arkmpc_ctx* ctx, void* dev_ptr);
