@@ -354,8 +354,8 @@ struct PtRecombineArgs {
   int open;
 };
 
-template <class C>
-__global__ void __launch_bounds__(C::kTwoPassBlock, 1) pt_beaver_recombine_kernel(size_t n, const __grid_constant__ PtRecombineArgs g,
+template <class C, int B = C::kTwoPassBlock>
+__global__ void __launch_bounds__(B, 1) pt_beaver_recombine_kernel(size_t n, const __grid_constant__ PtRecombineArgs g,
                                                                       const typename C::Aff* __restrict__ gtab, TabScratch ts) {
   unsigned int token;
   GlobalTab<C> tab = tab_claim<C>(ts, token);

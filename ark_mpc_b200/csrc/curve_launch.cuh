@@ -226,6 +226,16 @@ struct CurveLaunch {
     TabScratch ts;
     int trc = tab_scratch(ctx, &ts);
     if (trc != ARKMPC_OK) return trc;
+    if constexpr (C::kTwoPassBlock == 256) {
+      // BN254: 12 warps per SM at 166 registers (some spills) beat 8 warps at 224 once the grid is many waves deep — 79.0 against
+      // 82.6 ms at 2^20, but 12.5 against 11.8 ms at 2^17, where the coarser blocks leave a longer tail (profiles/r02t_*).
+      // ARKMPC_PT_BN_BLOCK=256|384 forces one.
+      static const int forced = [] { const char* v = getenv("ARKMPC_PT_BN_BLOCK"); return v ? atoi(v) : 0; }();
+      if (forced == 384 || (forced != 256 && n >= ((size_t)1 << 19))) {
+        pt_beaver_recombine_kernel<C, 384><<<pt_grid(ctx, n, 1, 384), 384, 0, ctx->stream>>>(n, g, gt, ts);
+        return post_launch(ctx, "pt_beaver_recombine_kernel");
+      }
+    }
     pt_beaver_recombine_kernel<C><<<pt_grid(ctx, n, 1, C::kTwoPassBlock), C::kTwoPassBlock, 0, ctx->stream>>>(n, g, gt, ts);
     return post_launch(ctx, "pt_beaver_recombine_kernel");
   }
