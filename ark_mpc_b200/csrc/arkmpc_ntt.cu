@@ -54,14 +54,20 @@ int ntt_plane(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t
   const size_t n = (size_t)1 << log2n;
   const int tile_log = log2n < kNttTileLog ? log2n : kNttTileLog;
   const size_t tiles = n >> tile_log;
-  fr_ntt_tile_kernel<F><<<(unsigned)tiles, kNttThreads, ((size_t)32 << tile_log), ctx->stream>>>(log2n, vec(in), vec(tw), mvec(out));
+  static const int tile_threads = [] { const char* e = getenv("ARKMPC_NTT_TILE_THREADS"); const int v = e ? atoi(e) : 0; return v == 128 || v == 256 ? v : kNttThreads; }();
+  static const int stride_threads = [] { const char* e = getenv("ARKMPC_NTT_STRIDE_THREADS"); const int v = e ? atoi(e) : 0; return v == 128 || v == 256 || v == 512 ? v : 0; }();
+  fr_ntt_tile_kernel<F><<<(unsigned)tiles, tile_threads, ((size_t)32 << tile_log), ctx->stream>>>(log2n, vec(in), vec(tw), mvec(out));
   rc = post_launch(ctx, "fr_ntt_tile_kernel");
   const int rest = log2n > kNttTileLog ? log2n - kNttTileLog : 0;
   int passes = (rest + kNttStrideLog - 1) / kNttStrideLog;
   for (int s0 = kNttTileLog; rc == ARKMPC_OK && s0 < log2n; passes--) {  // the remaining stages, spread evenly over <= 5-stage passes
     const int T = (log2n - s0 + passes - 1) / passes;
     const size_t blocks = n >> (5 + T);
-    fr_ntt_strided_kernel<F><<<(unsigned)blocks, kNttStrideThreads, 0, ctx->stream>>>(log2n, s0, T, vec(tw), mvec(out));
+    // two butterflies per thread per level: blocks half the size of the tile's butterfly count stagger their load, barrier and
+    // store phases under the multiplier roof (2^20: 266 -> 254 us, 2^22: 1219 -> 1039 us, 2^24: 5008 -> 4282 us for the inverse
+    // transform against one butterfly per thread; profiles/r02u_summary.txt)
+    const int threads = stride_threads ? stride_threads : (T >= 3 ? 32 << (T - 3) : 32);
+    fr_ntt_strided_kernel<F><<<(unsigned)blocks, threads, 0, ctx->stream>>>(log2n, s0, T, vec(tw), mvec(out));
     rc = post_launch(ctx, "fr_ntt_strided_kernel");
     s0 += T;
   }

@@ -197,9 +197,9 @@ __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec
   const size_t tile = (size_t)1 << tile_log;
   const size_t base = (size_t)blockIdx.x * tile;
   const int t = threadIdx.x;
-  for (size_t k = t; k < tile / 2; k += kNttThreads) ld_fe(stw[k], tw, k << (log2n - tile_log));
+  for (size_t k = t; k < tile / 2; k += blockDim.x) ld_fe(stw[k], tw, k << (log2n - tile_log));
   // gather: out position p <- in[bitrev(p)]
-  for (size_t e = t; e < tile; e += kNttThreads) {
+  for (size_t e = t; e < tile; e += blockDim.x) {
     const size_t p = base + e;
     const size_t src = log2n ? (size_t)(__brevll((unsigned long long)p) >> (64 - log2n)) : 0;
     ld_fe(x[e], in, src);
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec
   int s = 1;
   for (; s + 1 <= tile_log; s += 2) {
     const size_t h = (size_t)1 << (s - 1);
-    for (size_t q = t; q < tile / 4; q += kNttThreads) {
+    for (size_t q = t; q < tile / 4; q += blockDim.x) {
       const size_t j = q & (h - 1);
       const size_t b = ((q >> (s - 1)) << (s + 1)) + j;
       fe8 e0 = x[b], e1 = x[b + h], e2 = x[b + 2 * h], e3 = x[b + 3 * h];
@@ -223,14 +223,14 @@ __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec
   }
   if (s <= tile_log) {  // an odd number of stages: the last one on its own
     const size_t h = (size_t)1 << (s - 1);
-    for (size_t b2 = t; b2 < tile / 2; b2 += kNttThreads) {
+    for (size_t b2 = t; b2 < tile / 2; b2 += blockDim.x) {
       const size_t j = b2 & (h - 1);
       const size_t i0 = ((b2 >> (s - 1)) << s) + j;
       ntt_butterfly<F>(x[i0], x[i0 + h], stw[j << (tile_log - s)]);
     }
     __syncthreads();
   }
-  for (size_t e = t; e < tile; e += kNttThreads) st_fe(out, base + e, x[e]);
+  for (size_t e = t; e < tile; e += blockDim.x) st_fe(out, base + e, x[e]);
 }
 
 // Stages s0+1 .. s0+T (s0 >= 10, T <= 5) in one pass: a block owns 32 consecutive low indices x 2^T strided positions
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kNttStrideThreads) fr_ntt_strided_kernel(int l
   const size_t base = (hi << (s0 + T)) + lo;
   const int rows = 1 << T;
   const Vec xr{x.p, x.stride};
-  for (int k = row; k < rows; k += kNttStrideThreads / 32) ld_fe(sm[k * 32 + lane], xr, base + ((size_t)k << s0));
+  for (int k = row; k < rows; k += (blockDim.x >> 5)) ld_fe(sm[k * 32 + lane], xr, base + ((size_t)k << s0));
   __syncthreads();
   // One butterfly per thread per level when T = 5; the twiddle of the NEXT level is requested before this level's arithmetic so
   // that its L2 round trip overlaps the multiplication and the barrier (long-scoreboard was the top stall, profiles/r02i_*).
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kNttStrideThreads) fr_ntt_strided_kernel(int l
   if (row < rows / 2) ld_fe(w_next, tw, tw_index(1, row));
   for (int t = 1; t <= T; t++) {
     const int halfk = 1 << (t - 1);
-    for (int b = row; b < rows / 2; b += kNttStrideThreads / 32) {
+    for (int b = row; b < rows / 2; b += (blockDim.x >> 5)) {
       fe8 w;
       if (b == row) w = w_next; else ld_fe(w, tw, tw_index(t, b));
       if (b == row && t < T) ld_fe(w_next, tw, tw_index(t + 1, row));
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kNttStrideThreads) fr_ntt_strided_kernel(int l
     }
     __syncthreads();
   }
-  for (int k = row; k < rows; k += kNttStrideThreads / 32) st_fe(x, base + ((size_t)k << s0), sm[k * 32 + lane]);
+  for (int k = row; k < rows; k += (blockDim.x >> 5)) st_fe(x, base + ((size_t)k << s0), sm[k * 32 + lane]);
 }
 
 }  // namespace ark
