@@ -2,10 +2,15 @@
 #include "ctx.hpp"
 #include "fr_ntt.cuh"
 
+#include <type_traits>
+
 using namespace ark;
 using namespace arkctx;
 
 namespace {
+
+template <class F> struct FieldTag { using type = F; };
+constexpr bool kMulKaraDefault = false;
 
 // Twiddles w^k (k < n/2) followed by the two constants {w, n^-1}; one cached table per direction, keyed by (field, log2n), allocated
 // and freed in stream order (no host synchronisation when the size changes).
@@ -45,7 +50,13 @@ int ntt_table(arkmpc_ctx* ctx, int field, int log2n, int inverse, const char** t
   return ARKMPC_OK;
 }
 
-template <class F>
+// ARKMPC_MUL=cios|kara: the field product of the NTT butterflies and the inversion sweeps
+inline bool use_kara() {
+  static const bool k = [] { const char* e = getenv("ARKMPC_MUL"); return e ? strcmp(e, "kara") == 0 : kMulKaraDefault; }();
+  return k;
+}
+
+template <class F, bool K>
 int ntt_plane(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t* in, uint64_t* out) {
   const char* tw;
   const fe8* consts;
@@ -56,18 +67,19 @@ int ntt_plane(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t
   const size_t tiles = n >> tile_log;
   static const int tile_threads = [] { const char* e = getenv("ARKMPC_NTT_TILE_THREADS"); const int v = e ? atoi(e) : 0; return v == 128 || v == 256 ? v : kNttThreads; }();
   static const int stride_threads = [] { const char* e = getenv("ARKMPC_NTT_STRIDE_THREADS"); const int v = e ? atoi(e) : 0; return v == 128 || v == 256 || v == 512 ? v : 0; }();
-  fr_ntt_tile_kernel<F><<<(unsigned)tiles, tile_threads, ((size_t)32 << tile_log), ctx->stream>>>(log2n, vec(in), vec(tw), mvec(out));
+  fr_ntt_tile_kernel<F, K><<<(unsigned)tiles, tile_threads, ((size_t)32 << tile_log), ctx->stream>>>(log2n, vec(in), vec(tw), mvec(out));
   rc = post_launch(ctx, "fr_ntt_tile_kernel");
   const int rest = log2n > kNttTileLog ? log2n - kNttTileLog : 0;
   int passes = (rest + kNttStrideLog - 1) / kNttStrideLog;
   for (int s0 = kNttTileLog; rc == ARKMPC_OK && s0 < log2n; passes--) {  // the remaining stages, spread evenly over <= 5-stage passes
     const int T = (log2n - s0 + passes - 1) / passes;
     const size_t blocks = n >> (5 + T);
-    // two butterflies per thread per level: blocks half the size of the tile's butterfly count stagger their load, barrier and
-    // store phases under the multiplier roof (2^20: 266 -> 254 us, 2^22: 1219 -> 1039 us, 2^24: 5008 -> 4282 us for the inverse
-    // transform against one butterfly per thread; profiles/r02u_summary.txt)
-    const int threads = stride_threads ? stride_threads : (T >= 3 ? 32 << (T - 3) : 32);
-    fr_ntt_strided_kernel<F><<<(unsigned)blocks, threads, 0, ctx->stream>>>(log2n, s0, T, vec(tw), mvec(out));
+    // large transforms: two butterflies per thread per level — blocks half the size of the tile's butterfly count stagger their
+    // load, barrier and store phases (2^20: 266 -> 254 us, 2^22: 1219 -> 1039 us, 2^24: 5008 -> 4282 us for the inverse transform,
+    // profiles/r02u_summary.txt); small ones keep one butterfly per thread, where the latency of a level is what counts
+    const int one_each = 32 << (T - 1);  // one butterfly per thread per level
+    const int threads = stride_threads ? stride_threads : (log2n >= 19 && one_each >= 64 ? one_each / 2 : one_each);
+    fr_ntt_strided_kernel<F, K><<<(unsigned)blocks, threads, 0, ctx->stream>>>(log2n, s0, T, vec(tw), mvec(out));
     rc = post_launch(ctx, "fr_ntt_strided_kernel");
     s0 += T;
   }
@@ -86,8 +98,9 @@ int fft_impl(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t*
   ARK_REQUIRE(ctx, log2n >= 0 && log2n <= NttRoot::kTwoAdicity, "domain size must be 2^0 .. 2^28");
   ARK_REQUIRE(ctx, in0 && out0 && aligned32(in0) && aligned32(out0) && in0 != out0, "null, misaligned or aliased plane (the transform is out of place)");
   if (in1 || out1) ARK_REQUIRE(ctx, in1 && out1 && aligned32(in1) && aligned32(out1) && in1 != out1, "null, misaligned or aliased plane");
-  int rc = ntt_plane<Bn254Fr>(ctx, field, log2n, inverse, in0, out0);
-  if (rc == ARKMPC_OK && in1) rc = ntt_plane<Bn254Fr>(ctx, field, log2n, inverse, in1, out1);
+  auto plane = use_kara() ? ntt_plane<Bn254Fr, true> : ntt_plane<Bn254Fr, false>;
+  int rc = plane(ctx, field, log2n, inverse, in0, out0);
+  if (rc == ARKMPC_OK && in1) rc = plane(ctx, field, log2n, inverse, in1, out1);
   return rc;
 }
 
@@ -127,9 +140,12 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
   static const int inv_block = [] { const char* e = getenv("ARKMPC_INV_BLOCK"); const int v = e ? atoi(e) : 0; return v == 32 || v == 64 || v == 128 ? v : kInvLaunchBlock; }();
   auto blocks = [](size_t work) { return (unsigned)((work + inv_block - 1) / inv_block); };
   int rc = ARKMPC_OK;
-  ARK_FIELD_SWITCH(ctx, field, {
+  auto sweeps = [&](auto fld, auto kara) -> int {
+    using F = typename decltype(fld)::type;
+    constexpr bool K = decltype(kara)::value;
+    int rc = ARKMPC_OK;
     for (int l = 0; l < levels && rc == ARKMPC_OK; l++) {
-      fr_inv_up_kernel<F><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
+      fr_inv_up_kernel<F, K><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
       rc = post_launch(ctx, "fr_inv_up_kernel");
     }
     if (rc == ARKMPC_OK) {
@@ -137,9 +153,13 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
       rc = post_launch(ctx, "fr_inv_top_kernel");
     }
     for (int l = levels - 1; l >= 0 && rc == ARKMPC_OK; l--) {
-      fr_inv_down_kernel<F><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
+      fr_inv_down_kernel<F, K><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
       rc = post_launch(ctx, "fr_inv_down_kernel");
     }
+    return rc;
+  };
+  ARK_FIELD_SWITCH(ctx, field, {
+    rc = use_kara() ? sweeps(FieldTag<F>{}, std::true_type{}) : sweeps(FieldTag<F>{}, std::false_type{});
   });
   if (scratch) cudaFreeAsync(scratch, s);
   return rc;

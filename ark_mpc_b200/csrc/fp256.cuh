@@ -330,6 +330,93 @@ ARK_D void sqr512(uint32_t* r, const uint32_t* a) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// 512-bit product by one Karatsuba level: a = a0 + a1 2^128, b = b0 + b1 2^128,
+//   a b = z0 + (z0 + z2 + (a0 - a1)(b1 - b0)) 2^128 + z2 2^256,   z0 = a0 b0, z2 = a1 b1.
+// Three 4 x 4-limb products (48 wide multiply-adds instead of 64) and, as compiled, ~170 more add / select instructions per field
+// product.  MEASURED SLOWER (profiles/r02v_summary.txt: NTT 2^20 249 -> 293 us, batch inversion 97 -> 126 us): the wide multiplier
+// is 85-90 % busy in these kernels, but every instruction also costs an issue slot behind a dependent predecessor, and eight extra
+// ALU instructions per multiply saved do not pay.  Kept as ARKMPC_MUL=kara for the A/B, and as the proof that the remaining
+// distance to the multiplier roof is not recoverable by trading multiplies for additions (the same happened to the dedicated
+// square in round 1, curve.cuh).
+// ----------------------------------------------------------------------------------------------
+// r[0..7] = a[0..3] * b[0..3]: the even / odd accumulator of MontAcc, four limbs wide, one word emitted per row
+ARK_D void mul128(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t E[5] = {0, 0, 0, 0, 0}, O[4] = {0, 0, 0, 0}, fold = 0;
+  ARK_UNROLL for (int i = 0; i < 4; i++) {
+    const uint32_t w = b[i];
+    if (i > 0) {
+      E[0] = add_cc(E[0], fold);  // its carry has weight 2^32 == O[0]
+      O[0] = madc_lo_cc(a[1], w, O[0]);
+    } else {
+      O[0] = mad_lo_cc(a[1], w, O[0]);
+    }
+    O[1] = madc_hi_cc(a[1], w, O[1]);
+    O[2] = madc_lo_cc(a[3], w, O[2]);
+    O[3] = madc_hi_cc(a[3], w, O[3]);
+    ARK_EMU_EXPECT_NO_CARRY();
+    E[0] = mad_lo_cc(a[0], w, E[0]);
+    E[1] = madc_hi_cc(a[0], w, E[1]);
+    E[2] = madc_lo_cc(a[2], w, E[2]);
+    E[3] = madc_hi_cc(a[2], w, E[3]);
+    E[4] = addc(E[4], 0u);
+    // emit the low word and shift down by one limb
+    r[i] = E[0];
+    fold = E[1];
+    const uint32_t n0 = E[2], n1 = E[3], n2 = E[4];
+    ARK_UNROLL for (int j = 0; j < 4; j++) E[j] = O[j];
+    E[4] = 0;
+    O[0] = n0; O[1] = n1; O[2] = n2; O[3] = 0;
+  }
+  r[4] = add_cc(E[0], fold);
+  r[5] = addc_cc(E[1], O[0]);
+  r[6] = addc_cc(E[2], O[1]);
+  r[7] = addc_cc(E[3], O[2]);
+  ARK_EMU_EXPECT_NO_CARRY();
+}
+
+// d = |x - y| (four limbs); returns 0xffffffff if x < y
+ARK_D uint32_t absdiff128(uint32_t* d, const uint32_t* x, const uint32_t* y) {
+  d[0] = sub_cc(x[0], y[0]);
+  d[1] = subc_cc(x[1], y[1]);
+  d[2] = subc_cc(x[2], y[2]);
+  d[3] = subc_cc(x[3], y[3]);
+  const uint32_t neg = subc(0u, 0u);
+  d[0] = add_cc(d[0] ^ neg, neg & 1u);
+  d[1] = addc_cc(d[1] ^ neg, 0u);
+  d[2] = addc_cc(d[2] ^ neg, 0u);
+  d[3] = addc(d[3] ^ neg, 0u);
+  return neg;
+}
+
+ARK_D void kara512(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+  uint32_t da[4], db[4], m[8];
+  const uint32_t sa = absdiff128(da, a, a + 4);      // a0 - a1
+  const uint32_t sb = absdiff128(db, b + 4, b);      // b1 - b0
+  mul128(T, a, b);                                   // z0
+  mul128(T + 8, a + 4, b + 4);                       // z2
+  mul128(m, da, db);
+  const uint32_t neg = sa ^ sb;                      // sign of (a0 - a1)(b1 - b0)
+  // mid = z0 + z2 +- m, nine limbs (0 <= mid = a0 b1 + a1 b0 < 2^257)
+  uint32_t mid[9];
+  mid[0] = add_cc(T[0], T[8]);
+  ARK_UNROLL for (int j = 1; j < 8; j++) mid[j] = addc_cc(T[j], T[8 + j]);
+  mid[8] = addc(0u, 0u);
+  mid[0] = add_cc(mid[0], neg & 1u);                 // two's complement of m when negative: ~m + 1, sign-extended
+  ARK_UNROLL for (int j = 1; j < 8; j++) mid[j] = addc_cc(mid[j], 0u);
+  mid[8] = addc(mid[8], 0u);
+  mid[0] = add_cc(mid[0], m[0] ^ neg);
+  ARK_UNROLL for (int j = 1; j < 8; j++) mid[j] = addc_cc(mid[j], m[j] ^ neg);
+  mid[8] = addc(mid[8], neg);
+  // T += mid 2^128
+  T[4] = add_cc(T[4], mid[0]);
+  ARK_UNROLL for (int j = 1; j < 9; j++) T[4 + j] = addc_cc(T[4 + j], mid[j]);
+  T[13] = addc_cc(T[13], 0u);
+  T[14] = addc_cc(T[14], 0u);
+  T[15] = addc_cc(T[15], 0u);
+  ARK_EMU_EXPECT_NO_CARRY();
+}
+
+// ----------------------------------------------------------------------------------------------
 // Field operations
 // ----------------------------------------------------------------------------------------------
 template <class F>
@@ -465,6 +552,34 @@ struct Fp {
       t.E[8] = addc(t.E[8], 0u);
     }
     acc_collapse(r, t);  // < T/R + p < 2p
+    csub_p(r);
+  }
+
+  // word-serial Montgomery reduction of a 16-word value T < p 2^256: r = T / R mod p, r < T / R + p (NOT canonical)
+  ARK_DM static void redc512_lazy(fe8& r, const uint32_t* T) {
+    MontAcc t;
+    ARK_UNROLL for (int j = 0; j < 8; j++) { t.E[j] = T[j]; t.O[j] = 0; }
+    t.E[8] = 0;
+    t.fold = 0;
+    ARK_UNROLL for (int i = 0; i < 8; i++) {
+      if (i > 0) {  // the word folded out by the previous shift; its carry has weight 2^32 == O[0]
+        t.E[0] = add_cc(t.E[0], t.fold);
+        ARK_UNROLL for (int j = 0; j < 8; j++) t.O[j] = addc_cc(t.O[j], 0u);
+        ARK_EMU_EXPECT_NO_CARRY();
+        t.fold = 0;
+      }
+      acc_reduce_shift<F>(t);
+      t.E[7] = add_cc(t.E[7], T[8 + i]);  // next word of the high half enters at relative position 7
+      t.E[8] = addc(t.E[8], 0u);
+    }
+    acc_collapse(r, t);
+  }
+
+  // canonical product of canonical inputs with the Karatsuba 512-bit product: 48 + 64 wide multiply-adds against 128 for mul
+  ARK_DM static void mul_kara(fe8& r, const fe8& a, const fe8& x) {
+    uint32_t T[16];
+    kara512(T, a.v, x.v);
+    redc512_lazy(r, T);  // < p*p/R + p < 2p
     csub_p(r);
   }
 

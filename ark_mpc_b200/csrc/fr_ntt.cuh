@@ -12,6 +12,12 @@
 
 namespace ark {
 
+// K selects the Karatsuba product (Fp::mul_kara: 112 wide multiply-adds) over the interleaved one (Fp::mul: 128)
+template <class F, bool K>
+__device__ __forceinline__ void fmul(fe8& r, const fe8& a, const fe8& b) {
+  if (K) Fp<F>::mul_kara(r, a, b); else Fp<F>::mul(r, a, b);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Batch inversion (scalar.rs:93-100 -> ark_ff::batch_inversion: zeros stay zero): Montgomery's trick as a product TREE.
 //   up    every thread multiplies a group of kInvGroup = 8 elements (element j of group g is x[g + j*groups]: coalesced) as a
@@ -49,7 +55,7 @@ __device__ __forceinline__ uint32_t inv_load_group(fe8 (&z)[kInvGroup], size_t n
   return live;
 }
 
-template <class F>
+template <class F, bool K>
 __global__ void __launch_bounds__(kInvBlock) fr_inv_up_kernel(size_t n, size_t groups, Vec x, MVec tree, MVec prod) {
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= groups) return;
@@ -58,14 +64,14 @@ __global__ void __launch_bounds__(kInvBlock) fr_inv_up_kernel(size_t n, size_t g
   // tree[k * groups + g]: k = 0..3 the pair products, 4..5 the products of four
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    Fp<F>::mul(z[2 * k], z[2 * k], z[2 * k + 1]);
+    fmul<F, K>(z[2 * k], z[2 * k], z[2 * k + 1]);
     st_fe(tree, (size_t)k * groups + g, z[2 * k]);
   }
-  Fp<F>::mul(z[0], z[0], z[2]);
-  Fp<F>::mul(z[4], z[4], z[6]);
+  fmul<F, K>(z[0], z[0], z[2]);
+  fmul<F, K>(z[4], z[4], z[6]);
   st_fe(tree, 4 * groups + g, z[0]);
   st_fe(tree, 5 * groups + g, z[4]);
-  Fp<F>::mul(z[0], z[0], z[4]);
+  fmul<F, K>(z[0], z[0], z[4]);
   st_fe(prod, g, z[0]);
 }
 
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(kInvTopBlock) fr_inv_top_kernel(size_t n, Vec 
   st_fe(out, i, r);
 }
 
-template <class F>
+template <class F, bool K>
 __global__ void __launch_bounds__(kInvBlock) fr_inv_down_kernel(size_t n, size_t groups, Vec x, Vec tree, Vec ginv, MVec out) {
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= groups) return;
@@ -94,16 +100,16 @@ __global__ void __launch_bounds__(kInvBlock) fr_inv_down_kernel(size_t n, size_t
   ld_fe(q[1], tree, 5 * groups + g);
   const uint32_t live = inv_load_group<F>(z, n, groups, g, x);
   fe8 iq[2], ip[4];
-  Fp<F>::mul(iq[0], inv, q[1]);
-  Fp<F>::mul(iq[1], inv, q[0]);
+  fmul<F, K>(iq[0], inv, q[1]);
+  fmul<F, K>(iq[1], inv, q[0]);
 #pragma unroll
-  for (int k = 0; k < 4; k++) Fp<F>::mul(ip[k], iq[k >> 1], p[k ^ 1]);
+  for (int k = 0; k < 4; k++) fmul<F, K>(ip[k], iq[k >> 1], p[k ^ 1]);
 #pragma unroll
   for (int j = 0; j < kInvGroup; j++) {
     const size_t i = g + (size_t)j * groups;
     if (i >= n) continue;
     fe8 r;
-    Fp<F>::mul(r, ip[j >> 1], z[j ^ 1]);
+    fmul<F, K>(r, ip[j >> 1], z[j ^ 1]);
     if (!((live >> j) & 1u)) Fp<F>::set_zero(r);  // zeros stay zero
     st_fe(out, i, r);
   }
@@ -173,10 +179,10 @@ constexpr int kNttTileLog = 10;               // 1024 elements (32 KiB) per bloc
 constexpr int kNttTile = 1 << kNttTileLog;
 constexpr int kNttThreads = kNttTile / 4;     // one radix-4 group (two stages of two butterflies) per thread per double stage
 
-template <class F>
+template <class F, bool K>
 __device__ __forceinline__ void ntt_butterfly(fe8& lo, fe8& hi, const fe8& w) {
   fe8 v, s, d;
-  Fp<F>::mul(v, hi, w);
+  fmul<F, K>(v, hi, w);
   Fp<F>::add(s, lo, v);
   Fp<F>::sub(d, lo, v);
   lo = s;
@@ -188,7 +194,7 @@ __device__ __forceinline__ void ntt_butterfly(fe8& lo, fe8& hi, const fe8& w) {
 // shared memory once.  Stages are taken two at a time: a thread owns the four elements {b, b + h, b + 2h, b + 3h} (h = 2^(s-1)),
 // runs the two butterflies of stage s and the two of stage s + 1 in registers, and the block synchronises once per PAIR of
 // stages — half the barriers and half the shared-memory round trips of one butterfly per thread per stage.
-template <class F>
+template <class F, bool K>
 __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec in, Vec tw, MVec out) {
   extern __shared__ __align__(32) unsigned char ntt_smem[];
   __shared__ __align__(32) fe8 stw[kNttTile / 2];  // stw[k] = w^(k n / 2^tile_log)
@@ -213,10 +219,10 @@ __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec
       const size_t b = ((q >> (s - 1)) << (s + 1)) + j;
       fe8 e0 = x[b], e1 = x[b + h], e2 = x[b + 2 * h], e3 = x[b + 3 * h];
       const fe8 w1 = stw[j << (tile_log - s)];                 // stage s: both butterflies use w^(j n / 2^s)
-      ntt_butterfly<F>(e0, e1, w1);
-      ntt_butterfly<F>(e2, e3, w1);
-      ntt_butterfly<F>(e0, e2, stw[j << (tile_log - s - 1)]);         // stage s + 1: positions j and j + h
-      ntt_butterfly<F>(e1, e3, stw[(j + h) << (tile_log - s - 1)]);
+      ntt_butterfly<F, K>(e0, e1, w1);
+      ntt_butterfly<F, K>(e2, e3, w1);
+      ntt_butterfly<F, K>(e0, e2, stw[j << (tile_log - s - 1)]);         // stage s + 1: positions j and j + h
+      ntt_butterfly<F, K>(e1, e3, stw[(j + h) << (tile_log - s - 1)]);
       x[b] = e0; x[b + h] = e1; x[b + 2 * h] = e2; x[b + 3 * h] = e3;
     }
     __syncthreads();
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec
     for (size_t b2 = t; b2 < tile / 2; b2 += blockDim.x) {
       const size_t j = b2 & (h - 1);
       const size_t i0 = ((b2 >> (s - 1)) << s) + j;
-      ntt_butterfly<F>(x[i0], x[i0 + h], stw[j << (tile_log - s)]);
+      ntt_butterfly<F, K>(x[i0], x[i0 + h], stw[j << (tile_log - s)]);
     }
     __syncthreads();
   }
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec
 constexpr int kNttStrideLog = 5;                         // up to 5 stages per strided pass
 constexpr int kNttStrideThreads = 32 << (kNttStrideLog - 1);  // 512
 
-template <class F>
+template <class F, bool K>
 __global__ void __launch_bounds__(kNttStrideThreads) fr_ntt_strided_kernel(int log2n, int s0, int T, Vec tw, MVec x) {
   __shared__ __align__(32) fe8 sm[32 << kNttStrideLog];  // [k][lo]
   const int lane = threadIdx.x & 31;
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(kNttStrideThreads) fr_ntt_strided_kernel(int l
       if (b == row && t < T) ld_fe(w_next, tw, tw_index(t + 1, row));
       const int kl = b & (halfk - 1);
       const int k = ((b >> (t - 1)) << t) + kl;
-      ntt_butterfly<F>(sm[k * 32 + lane], sm[(k + halfk) * 32 + lane], w);
+      ntt_butterfly<F, K>(sm[k * 32 + lane], sm[(k + halfk) * 32 + lane], w);
     }
     __syncthreads();
   }

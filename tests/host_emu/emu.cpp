@@ -40,6 +40,8 @@ template <class F> static void run(int op, const uint32_t* in, uint32_t* out, in
     case 17: Fp<F>::inv_plain(o[0], v[0]); break;
     case 18: Fp<F>::inv_mont(o[0], v[0]); break;
     case 19: Fp<F>::inv_safegcd(o[0], v[0]); break;
+    case 20: Fp<F>::mul_kara(o[0], v[0], v[1]); break;
+    case 21: { uint32_t T[16]; kara512(T, v[0].v, v[1].v); memcpy(o, T, sizeof T); } break;  // the 512-bit product (two elements)
     case 14: if constexpr (F::kBits <= 254) { Fp<F>::mul_ctab_lazy(o[0], tab_of<F>(v[0]), v[1]); } break;  // lazy: s * a / R, any 256-bit a
     case 15: if constexpr (F::kBits <= 254) { Fp<F>::mul_ctab(o[0], tab_of<F>(v[0]), v[1]); } break;
     case 16: if constexpr (F::kBits <= 254) { CTab t = tab_of<F>(v[0]); memcpy(o, &t, sizeof t); } break;       // the table itself (8 elements)

@@ -205,3 +205,21 @@ def test_binary_euclid_inversion(emu, name, fid):
         assert emu(fid, 19, [a], 1)[0] == pow(a, -1, F.p)
         assert emu(fid, 17, [a], 1)[0] == pow(a, -1, F.p)
         assert emu(fid, 18, [F.to_mont(a)], 1)[0] == F.to_mont(pow(a, -1, F.p))
+
+
+@pytest.mark.parametrize("name,fid", FIELDS)
+def test_karatsuba_product(emu, name, fid):
+    """kara512 (one Karatsuba level: three 4 x 4-limb products) is the exact 512-bit product for ANY 256-bit operands, and
+    Fp::mul_kara (that product + word-serial Montgomery reduction) equals Fp::mul on canonical inputs."""
+    F = po.FIELDS[name]
+    rng = random.Random(90 + fid)
+    full = (1 << 256) - 1
+    halves = [0, 1, (1 << 128) - 1, 1 << 127, (1 << 64) + 1, (1 << 128) - (1 << 32)]
+    raw = [lo | (hi << 128) for lo in halves for hi in halves] + [full, full - 1, 1 << 255] + [rng.getrandbits(256) for _ in range(300)]
+    for a, b in zip(raw, reversed(raw)):
+        lo, hi = emu(fid, 21, [a, b], 2)
+        assert lo | (hi << 256) == a * b
+    A = samples(F, rng, 300)
+    B = list(reversed(samples(F, rng, 300)))
+    for a, b in zip(A, B):
+        assert emu(fid, 20, [a, b], 1)[0] == a * b * F.rinv % F.p
