@@ -123,6 +123,7 @@ _PROTOS = {
     "arkmpc_pt_normalize": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_pt_from_affine": [_vp, _i, _sz, _vp, _vp],
     "arkmpc_fr_batch_mul_begin_host": [_vp, _i, _i, _vp, _sz] + [_vp] * 6 + [C.POINTER(_vp)],
+    "arkmpc_fr_batch_mul_begin_host_shares": [_vp, _i, _i, _vp, _sz] + [_vp] * 6 + [C.POINTER(_vp)],
     "arkmpc_fr_batch_mul_finish_host": [_vp, _vp, _vp, _vp],
     "arkmpc_fr_batch_mul_abort": [_vp],
     "arkmpc_fr_batch_mul_host_bytes": [_vp, _sz, _i, C.POINTER(_u64), C.POINTER(_u64)],

@@ -650,13 +650,11 @@ int session_free(arkmpc_batch_mul* s) {
   delete s;
   return ARKMPC_OK;
 }
-}  // namespace
 
-extern "C" {
-
-int arkmpc_fr_batch_mul_begin_host(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
-                                   const uint64_t* x_host, const uint64_t* y_host, const uint64_t* a_host, const uint64_t* b_host,
-                                   const uint64_t* c_host, uint64_t* de_mine_host, arkmpc_batch_mul** session) {
+// xy_stride: 64 = x_host / y_host are AoS ScalarShare images (share || mac), 32 = planes of the share halves only
+int begin_host_impl(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n, size_t xy_stride,
+                    const uint64_t* x_host, const uint64_t* y_host, const uint64_t* a_host, const uint64_t* b_host,
+                    const uint64_t* c_host, uint64_t* de_mine_host, arkmpc_batch_mul** session) {
   ARK_CHECK_CTX(ctx);
   ARK_REQUIRE(ctx, session, "null session pointer");
   *session = nullptr;
@@ -695,8 +693,8 @@ int arkmpc_fr_batch_mul_begin_host(arkmpc_ctx* ctx, int field, int party_id, con
   char* e_dev = s->de + n * 32;
   // zero-copy needs both buffers pinned and mapped (cudaHostAlloc / cudaHostRegister / arkmpc_host_alloc); pageable memory
   // falls back to the flat copy
-  const char* x_map = ctx->xy_mode == 2 ? mapped_device_pointer(xh) : nullptr;
-  const char* y_map = ctx->xy_mode == 2 ? mapped_device_pointer(yh) : nullptr;
+  const char* x_map = ctx->xy_mode == 2 && xy_stride == 64 ? mapped_device_pointer(xh) : nullptr;
+  const char* y_map = ctx->xy_mode == 2 && xy_stride == 64 ? mapped_device_pointer(yh) : nullptr;
   const bool xy_zero_copy = x_map && y_map;
   s->xy_zero_copy = xy_zero_copy;
   auto run = [&]() -> int {
@@ -714,16 +712,16 @@ int arkmpc_fr_batch_mul_begin_host(arkmpc_ctx* ctx, int field, int party_id, con
       if (xy_zero_copy) {
         xv = vec(x_map + off * 64, 64);
         yv = vec(y_map + off * 64, 64);
-      } else if (ctx->xy_mode == 1) {
+      } else if (ctx->xy_mode == 1 && xy_stride == 64) {
         ARK_CUDA(ctx, cudaMemcpy2DAsync(xs, 32, xh + off * 64, 64, 32, m, cudaMemcpyHostToDevice, st));
         ARK_CUDA(ctx, cudaMemcpy2DAsync(ys, 32, yh + off * 64, 64, 32, m, cudaMemcpyHostToDevice, st));
         xv = vec(xs);
         yv = vec(ys);
       } else {
-        ARK_CUDA(ctx, cudaMemcpyAsync(xs, xh + off * 64, m * 64, cudaMemcpyHostToDevice, st));
-        ARK_CUDA(ctx, cudaMemcpyAsync(ys, yh + off * 64, m * 64, cudaMemcpyHostToDevice, st));
-        xv = vec(xs, 64);
-        yv = vec(ys, 64);
+        ARK_CUDA(ctx, cudaMemcpyAsync(xs, xh + off * xy_stride, m * xy_stride, cudaMemcpyHostToDevice, st));
+        ARK_CUDA(ctx, cudaMemcpyAsync(ys, yh + off * xy_stride, m * xy_stride, cudaMemcpyHostToDevice, st));
+        xv = vec(xs, (uint32_t)xy_stride);
+        yv = vec(ys, (uint32_t)xy_stride);
       }
       ARK_CUDA(ctx, cudaMemcpyAsync(a_dev + off * 64, ah + off * 64, m * 64, cudaMemcpyHostToDevice, st));
       ARK_CUDA(ctx, cudaMemcpyAsync(b_dev + off * 64, bh + off * 64, m * 64, cudaMemcpyHostToDevice, st));
@@ -745,6 +743,20 @@ int arkmpc_fr_batch_mul_begin_host(arkmpc_ctx* ctx, int field, int party_id, con
     *session = nullptr;
   }
   return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int arkmpc_fr_batch_mul_begin_host(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                                   const uint64_t* x_host, const uint64_t* y_host, const uint64_t* a_host, const uint64_t* b_host,
+                                   const uint64_t* c_host, uint64_t* de_mine_host, arkmpc_batch_mul** session) {
+  return begin_host_impl(ctx, field, party_id, key_host, n, 64, x_host, y_host, a_host, b_host, c_host, de_mine_host, session);
+}
+int arkmpc_fr_batch_mul_begin_host_shares(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                                          const uint64_t* x_share_host, const uint64_t* y_share_host, const uint64_t* a_host,
+                                          const uint64_t* b_host, const uint64_t* c_host, uint64_t* de_mine_host, arkmpc_batch_mul** session) {
+  return begin_host_impl(ctx, field, party_id, key_host, n, 32, x_share_host, y_share_host, a_host, b_host, c_host, de_mine_host, session);
 }
 
 int arkmpc_fr_batch_mul_finish_host(arkmpc_batch_mul* s, const uint64_t* de_peer_host, uint64_t* out_host, uint64_t* de_open_host) {

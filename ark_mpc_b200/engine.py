@@ -425,6 +425,17 @@ class Engine:
                    hp(x), hp(y), hp(a), hp(b), hp(c), hp(de_mine), C.byref(sess))
         return sess
 
+    def batch_mul_begin_host_shares(self, party: int, key, x_share: np.ndarray, y_share: np.ndarray, a: np.ndarray, b: np.ndarray,
+                                    c: np.ndarray, de_mine: np.ndarray):
+        """As batch_mul_begin_host with x, y given as (n,4) planes of their share halves (the operands' MACs are not inputs)."""
+        n = x_share.shape[0]
+        k = self.key_limbs(key)
+        sess = C.c_void_p()
+        hp = lambda arr: C.c_void_p(arr.ctypes.data)
+        self._call("arkmpc_fr_batch_mul_begin_host_shares", self.field, int(party), k.ctypes.data_as(C.c_void_p), n,
+                   hp(x_share), hp(y_share), hp(a), hp(b), hp(c), hp(de_mine), C.byref(sess))
+        return sess
+
     def batch_mul_finish_host(self, sess, de_peer: np.ndarray, out: np.ndarray, de_open: Optional[np.ndarray] = None) -> None:
         hp = lambda arr: C.c_void_p(arr.ctypes.data) if arr is not None else None
         nat.check(self.lib.arkmpc_fr_batch_mul_finish_host(sess, hp(de_peer), hp(out), hp(de_open)),

@@ -810,13 +810,19 @@ def main():
             gate = threading.Barrier(2)
             errs = []
 
+            share_operands = [False]  # second pass: x, y as planes of their share halves (arkmpc_fr_batch_mul_begin_host_shares)
+
             def party_steps(p, reps):
                 try:
                     torch.cuda.set_device(local_rank)
                     Ep = engines[p]
                     for _ in range(reps):
-                        sess = Ep.batch_mul_begin_host(p, P[p]["key"], host[p]["x"], host[p]["y"], host[p]["a"], host[p]["b"], host[p]["c"],
-                                                       host[p]["de"])
+                        if share_operands[0]:
+                            sess = Ep.batch_mul_begin_host_shares(p, P[p]["key"], host[p]["xs"], host[p]["ys"], host[p]["a"], host[p]["b"],
+                                                                  host[p]["c"], host[p]["de"])
+                        else:
+                            sess = Ep.batch_mul_begin_host(p, P[p]["key"], host[p]["x"], host[p]["y"], host[p]["a"], host[p]["b"], host[p]["c"],
+                                                           host[p]["de"])
                         gate.wait()  # both parties' d||e are in host memory: the mock network hands over the pointer
                         Ep.batch_mul_finish_host(sess, host[1 - p]["de"], host[p]["out"])
                         gate.wait()
@@ -854,6 +860,35 @@ def main():
                    "h2d_gbs_aggregate": 2 * h2d * world / (e2e_ms * 1e-3) / 1e9, "d2h_gbs_aggregate": 2 * d2h * world / (e2e_ms * 1e-3) / 1e9,
                    "api": "arkmpc_fr_batch_mul_begin_host / arkmpc_fr_batch_mul_finish_host (pinned host AoS buffers, one host thread per party)",
                    "host_numa": numa}
+            # The same step with the operands given as what the gate reads: x, y as planes of their share halves (the operands' MACs
+            # are not inputs of a Beaver multiplication); a, b, c, d || e and the result as before.  Reported beside `e2e`, which keeps
+            # the reference's Vec<ScalarShare> images for every operand.
+            for p in (0, 1):
+                for nm in ("x", "y"):
+                    buf = engines[p].pinned_empty((n, 4))
+                    buf[:] = host[p][nm][:, :4]
+                    host[p][nm + "s"] = buf
+                host[p]["out"][:] = 0
+            share_operands[0] = True
+            e2e_run(1)
+            if not np.array_equal(host[0]["out"], ref):
+                raise SystemExit("e2e path (share-plane operands) result differs from the device-resident path")
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            e2e_run(args.e2e_steps)
+            torch.cuda.synchronize()
+            so_ms = 1e3 * (time.perf_counter() - t0) / args.e2e_steps
+            if world > 1:
+                t = torch.tensor([so_ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                so_ms = float(t.item())
+            so_h2d = h2d - 64 * n
+            e2e["share_plane_operands"] = {"value": n * world / (so_ms * 1e-3), "unit": UNIT, "ms_per_step": so_ms, "h2d_bytes_per_step": 2 * so_h2d,
+                                           "d2h_bytes_per_step": 2 * d2h, "h2d_gbs_aggregate": 2 * so_h2d * world / (so_ms * 1e-3) / 1e9,
+                                           "api": "arkmpc_fr_batch_mul_begin_host_shares / arkmpc_fr_batch_mul_finish_host (x, y: n x 32-byte share "
+                                                  "planes; a, b, c: AoS images)"}
             E1.close()
             del host
 

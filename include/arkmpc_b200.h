@@ -369,6 +369,13 @@ int arkmpc_fr_batch_mul_begin_host(arkmpc_ctx* ctx, int field, int party_id, con
                                    const uint64_t* x_host, const uint64_t* y_host, const uint64_t* a_host,
                                    const uint64_t* b_host, const uint64_t* c_host, uint64_t* de_mine_host,
                                    arkmpc_batch_mul** session);
+/* The same with x and y given as planes of their SHARE halves (n x 32 bytes each): the MACs of the operands are not inputs
+ * of a Beaver multiplication (open_batch sends share.share() only, authenticated_scalar.rs:141-145; the product's MAC comes
+ * from the triple's), so a host that keeps — or receives — the shares on their own uploads 320 instead of 384 bytes per gate. */
+int arkmpc_fr_batch_mul_begin_host_shares(arkmpc_ctx* ctx, int field, int party_id, const uint64_t* key_host, size_t n,
+                                          const uint64_t* x_share_host, const uint64_t* y_share_host,
+                                          const uint64_t* a_host, const uint64_t* b_host, const uint64_t* c_host,
+                                          uint64_t* de_mine_host, arkmpc_batch_mul** session);
 int arkmpc_fr_batch_mul_finish_host(arkmpc_batch_mul* session, const uint64_t* de_peer_host, uint64_t* out_host,
                                     uint64_t* de_open_host);
 int arkmpc_fr_batch_mul_abort(arkmpc_batch_mul* session);

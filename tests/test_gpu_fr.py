@@ -227,8 +227,10 @@ def test_batch_mul_full_size_properties(engines, fid):
 
 @pytest.mark.parametrize("fid", FIDS)
 @pytest.mark.parametrize("n", [1, 1000, 200001])
-def test_host_buffer_batch_mul(engines, fid, n):
-    """The end-to-end C-ABI path over host AoS buffers (begin -> exchange -> finish), chunked/pipelined."""
+@pytest.mark.parametrize("share_planes", [False, True])
+def test_host_buffer_batch_mul(engines, fid, n, share_planes):
+    """The end-to-end C-ABI path over host buffers (begin -> exchange -> finish), chunked/pipelined: operands as the reference's
+    AoS ScalarShare images, or x and y as planes of their share halves (arkmpc_fr_batch_mul_begin_host_shares)."""
     E = engines[fid]
     D = TwoPartyData(fid, n, seed=5 + n)
     o0, o1, d_open, e_open = D.oracle_batch_mul()
@@ -236,7 +238,11 @@ def test_host_buffer_batch_mul(engines, fid, n):
     for p in (0, 1):
         P = D.party(p)
         de_mine = np.empty((2 * n, 4), dtype=np.uint64)
-        sess.append(E.batch_mul_begin_host(p, P["key"], aos(*P["x"]), aos(*P["y"]), aos(*P["a"]), aos(*P["b"]), aos(*P["c"]), de_mine))
+        if share_planes:
+            xs, ys = np.ascontiguousarray(P["x"][0]), np.ascontiguousarray(P["y"][0])
+            sess.append(E.batch_mul_begin_host_shares(p, P["key"], xs, ys, aos(*P["a"]), aos(*P["b"]), aos(*P["c"]), de_mine))
+        else:
+            sess.append(E.batch_mul_begin_host(p, P["key"], aos(*P["x"]), aos(*P["y"]), aos(*P["a"]), aos(*P["b"]), aos(*P["c"]), de_mine))
         de.append(de_mine)
     for p, want in ((0, o0), (1, o1)):
         out = np.empty((n, 8), dtype=np.uint64)
