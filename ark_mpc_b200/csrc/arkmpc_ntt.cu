@@ -113,6 +113,15 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, a && out && aligned32(a) && aligned32(out), "null or misaligned plane");
   ARK_REQUIRE(ctx, field == ARKMPC_BN254_FR || field == ARKMPC_CURVE25519_FR, "unknown field id");
+  if (n > kInvTop && n <= kInvTop * kInvGroup) {  // one launch: groups of 8 handled whole by one thread each
+    const size_t groups = (n + kInvGroup - 1) / kInvGroup;
+    const unsigned grid = (unsigned)((groups + kInvTopBlock - 1) / kInvTopBlock);
+    ARK_FIELD_SWITCH(ctx, field, {
+      if (use_kara()) fr_inv_small_kernel<F, true><<<grid, kInvTopBlock, 0, ctx->stream>>>(n, groups, vec(a), mvec(out));
+      else fr_inv_small_kernel<F, false><<<grid, kInvTopBlock, 0, ctx->stream>>>(n, groups, vec(a), mvec(out));
+    });
+    return post_launch(ctx, "fr_inv_small_kernel");
+  }
   // level sizes n_0 = n, n_(l+1) = ceil(n_l / kInvGroup) until <= kInvTop
   size_t sizes[16];
   int levels = 0;

@@ -88,6 +88,38 @@ __global__ void __launch_bounds__(kInvTopBlock) fr_inv_top_kernel(size_t n, Vec 
   st_fe(out, i, r);
 }
 
+// Batches of up to 8 kInvTop elements in ONE launch: every thread takes a whole group — product tree up in registers, one
+// inversion of the group product, tree down.  A lone warp per scheduler runs the 21 multiplications at ~1 us each, so above this
+// size the separate sweeps (many warps per scheduler) are faster (2^20: 98 against 105 us), below it the single launch is
+// (2^16: 40 against 44 us; profiles/r02z2_summary.txt).
+template <class F, bool K>
+__global__ void __launch_bounds__(kInvTopBlock) fr_inv_small_kernel(size_t n, size_t groups, Vec x, MVec out) {
+  const size_t g = (size_t)blockIdx.x * kInvTopBlock + threadIdx.x;
+  if (g >= groups) return;
+  fe8 z[kInvGroup], p[4], q[2], inv;
+  const uint32_t live = inv_load_group<F>(z, n, groups, g, x);
+#pragma unroll
+  for (int k = 0; k < 4; k++) fmul<F, K>(p[k], z[2 * k], z[2 * k + 1]);
+  fmul<F, K>(q[0], p[0], p[1]);
+  fmul<F, K>(q[1], p[2], p[3]);
+  fmul<F, K>(inv, q[0], q[1]);
+  Fp<F>::inv_mont(inv, inv);  // never zero: zeros entered the product as one
+  fe8 iq[2], ip[4];
+  fmul<F, K>(iq[0], inv, q[1]);
+  fmul<F, K>(iq[1], inv, q[0]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) fmul<F, K>(ip[k], iq[k >> 1], p[k ^ 1]);
+#pragma unroll
+  for (int j = 0; j < kInvGroup; j++) {
+    const size_t i = g + (size_t)j * groups;
+    if (i >= n) continue;
+    fe8 r;
+    fmul<F, K>(r, ip[j >> 1], z[j ^ 1]);
+    if (!((live >> j) & 1u)) Fp<F>::set_zero(r);  // zeros stay zero
+    st_fe(out, i, r);
+  }
+}
+
 template <class F, bool K>
 __global__ void __launch_bounds__(kInvBlock) fr_inv_down_kernel(size_t n, size_t groups, Vec x, Vec tree, Vec ginv, MVec out) {
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

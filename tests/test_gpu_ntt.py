@@ -19,13 +19,20 @@ def engines():
 
 
 @pytest.mark.parametrize("fid", [0, 1])
-@pytest.mark.parametrize("n", [1, 15, 16, 17, 1000, 100003])
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 15, 16, 17, 1000, 100003, 131072, 131073, (1 << 20) + 5])
 def test_batch_inverse(engines, fid, n):
+    """Sizes on both sides of every level boundary of the product tree (groups of 8; <= 131072 elements go to the top kernel
+    directly, 131073 needs one sweep, 2^20 + 5 one sweep with a ragged last group), zeros in every position class."""
     E = engines[fid]
     a = co.synth(fid, 21, 0, n)
     for k in (0, n // 2, n - 1):       # zeros stay zero (ark_ff::batch_inversion)
         if n > 2:
             a[k] = 0
+    if n >= 1000:
+        g = (n + 7) // 8
+        a[3::g] = 0                    # a whole group of zeros (elements 3, 3 + g, ... form group 3 of the first level)
+        a[5] = 0
+        a[5 + g] = 0
     got = E.download(E.batch_inverse(E.upload(a)))
     assert np.array_equal(got, co.batch_inverse(fid, a))
     # x * x^-1 = 1 wherever x != 0
