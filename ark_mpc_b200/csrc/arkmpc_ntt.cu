@@ -56,6 +56,12 @@ inline bool use_kara() {
   return k;
 }
 
+// ARKMPC_INV_COOP=0: the small levels of the inversion tree with one thread per group, like the large ones
+inline bool use_coop() {
+  static const bool c = [] { const char* e = getenv("ARKMPC_INV_COOP"); return !(e && strcmp(e, "0") == 0); }();
+  return c;
+}
+
 template <class F, bool K>
 int ntt_plane(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t* in, uint64_t* out) {
   const char* tw;
@@ -113,15 +119,6 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
   if (n == 0) return ARKMPC_OK;
   ARK_REQUIRE(ctx, a && out && aligned32(a) && aligned32(out), "null or misaligned plane");
   ARK_REQUIRE(ctx, field == ARKMPC_BN254_FR || field == ARKMPC_CURVE25519_FR, "unknown field id");
-  if (n > kInvTop && n <= kInvTop * kInvGroup) {  // one launch: groups of 8 handled whole by one thread each
-    const size_t groups = (n + kInvGroup - 1) / kInvGroup;
-    const unsigned grid = (unsigned)((groups + kInvTopBlock - 1) / kInvTopBlock);
-    ARK_FIELD_SWITCH(ctx, field, {
-      if (use_kara()) fr_inv_small_kernel<F, true><<<grid, kInvTopBlock, 0, ctx->stream>>>(n, groups, vec(a), mvec(out));
-      else fr_inv_small_kernel<F, false><<<grid, kInvTopBlock, 0, ctx->stream>>>(n, groups, vec(a), mvec(out));
-    });
-    return post_launch(ctx, "fr_inv_small_kernel");
-  }
   // level sizes n_0 = n, n_(l+1) = ceil(n_l / kInvGroup) until <= kInvTop
   size_t sizes[16];
   int levels = 0;
@@ -153,8 +150,13 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
     using F = typename decltype(fld)::type;
     constexpr bool K = decltype(kara)::value;
     int rc = ARKMPC_OK;
+    auto coop = [](size_t groups) { return use_coop() && groups <= kInvCoopMaxGroups; };
+    auto coop_blocks = [](size_t groups) { return (unsigned)((groups + kInvCoopGroups - 1) / kInvCoopGroups); };
     for (int l = 0; l < levels && rc == ARKMPC_OK; l++) {
-      fr_inv_up_kernel<F, K><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
+      if (coop(sizes[l + 1]))
+        fr_inv_up_coop_kernel<F, K><<<coop_blocks(sizes[l + 1]), kInvCoopBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
+      else
+        fr_inv_up_kernel<F, K><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
       rc = post_launch(ctx, "fr_inv_up_kernel");
     }
     if (rc == ARKMPC_OK) {
@@ -162,7 +164,10 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
       rc = post_launch(ctx, "fr_inv_top_kernel");
     }
     for (int l = levels - 1; l >= 0 && rc == ARKMPC_OK; l--) {
-      fr_inv_down_kernel<F, K><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
+      if (coop(sizes[l + 1]))
+        fr_inv_down_coop_kernel<F, K><<<coop_blocks(sizes[l + 1]), kInvCoopBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
+      else
+        fr_inv_down_kernel<F, K><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
       rc = post_launch(ctx, "fr_inv_down_kernel");
     }
     return rc;

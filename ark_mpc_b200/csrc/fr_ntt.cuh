@@ -75,6 +75,94 @@ __global__ void __launch_bounds__(kInvBlock) fr_inv_up_kernel(size_t n, size_t g
   st_fe(prod, g, z[0]);
 }
 
+// Cooperative sweeps for the SMALL levels of the tree (a few thousand groups): with one thread per group such a launch is a
+// lone warp per scheduler running 7 (up) or 14 (down) multiplications back to back at ~1 us each — 8.5 + 13.3 us at 2^20 for
+// an eighth of the data.  Here four threads share a group: thread (k, g) of a 256-thread block multiplies pair k of group g, the
+// levels of the tree meet in shared memory, and the dependent depth is 3 multiplications up and 1 + 2 down: 7.5 + 10.5 us
+// (profiles/r02z4_summary.txt; what remains is load latency and the ~1 us a lone warp needs per multiplication).  Doing the
+// last up sweep, the inversions and the first down sweep in ONE kernel, a thread per group, was tried and is slower above 2^16
+// elements (105 against 98 us at 2^20, profiles/r02z2_summary.txt): the 21 multiplications then run on a lone warp too.
+constexpr int kInvCoopGroups = 64;               // groups per block
+constexpr int kInvCoopBlock = 4 * kInvCoopGroups;
+constexpr size_t kInvCoopMaxGroups = 32768;      // above this the launch is throughput-bound and one thread per group is cheaper
+
+template <class F>
+__device__ __forceinline__ uint32_t inv_load_pair(fe8& z0, fe8& z1, size_t n, size_t groups, size_t g, int k, Vec x) {
+  const size_t i0 = g + (size_t)(2 * k) * groups, i1 = i0 + groups;
+  if (i0 < n) ld_fe(z0, x, i0); else Fp<F>::set_zero(z0);
+  if (i1 < n) ld_fe(z1, x, i1); else Fp<F>::set_zero(z1);
+  uint32_t live = 0;
+  if (Fp<F>::is_zero(z0)) Fp<F>::set_one(z0); else live |= 1u;
+  if (Fp<F>::is_zero(z1)) Fp<F>::set_one(z1); else live |= 2u;
+  return live;
+}
+
+template <class F, bool K>
+__global__ void __launch_bounds__(kInvCoopBlock) fr_inv_up_coop_kernel(size_t n, size_t groups, Vec x, MVec tree, MVec prod) {
+  __shared__ __align__(32) fe8 sp[4][kInvCoopGroups];
+  __shared__ __align__(32) fe8 sq[2][kInvCoopGroups];
+  const int k = threadIdx.x / kInvCoopGroups, gl = threadIdx.x % kInvCoopGroups;
+  const size_t g = (size_t)blockIdx.x * kInvCoopGroups + gl;
+  const bool act = g < groups;
+  if (act) {
+    fe8 z0, z1, p;
+    (void)inv_load_pair<F>(z0, z1, n, groups, g, k, x);
+    fmul<F, K>(p, z0, z1);
+    st_fe(tree, (size_t)k * groups + g, p);
+    sp[k][gl] = p;
+  }
+  __syncthreads();
+  if (act && k < 2) {
+    fe8 q;
+    fmul<F, K>(q, sp[2 * k][gl], sp[2 * k + 1][gl]);
+    st_fe(tree, (size_t)(4 + k) * groups + g, q);
+    sq[k][gl] = q;
+  }
+  __syncthreads();
+  if (act && k == 0) {
+    fe8 t;
+    fmul<F, K>(t, sq[0][gl], sq[1][gl]);
+    st_fe(prod, g, t);
+  }
+}
+
+template <class F, bool K>
+__global__ void __launch_bounds__(kInvCoopBlock) fr_inv_down_coop_kernel(size_t n, size_t groups, Vec x, Vec tree, Vec ginv, MVec out) {
+  __shared__ __align__(32) fe8 siq[2][kInvCoopGroups];
+  const int k = threadIdx.x / kInvCoopGroups, gl = threadIdx.x % kInvCoopGroups;
+  const size_t g = (size_t)blockIdx.x * kInvCoopGroups + gl;
+  const bool act = g < groups;
+  fe8 z0, z1, ps;
+  uint32_t live = 0;
+  if (act) {  // everything this thread needs from memory is requested before the first multiplication
+    live = inv_load_pair<F>(z0, z1, n, groups, g, k, x);
+    ld_fe(ps, tree, (size_t)(k ^ 1) * groups + g);  // the sibling pair's product
+  }
+  if (act && k < 2) {
+    fe8 inv, qo, iq;
+    ld_fe(inv, ginv, g);
+    ld_fe(qo, tree, (size_t)(4 + (k ^ 1)) * groups + g);
+    fmul<F, K>(iq, inv, qo);
+    siq[k][gl] = iq;
+  }
+  __syncthreads();
+  if (act) {
+    fe8 ip, r;
+    fmul<F, K>(ip, siq[k >> 1][gl], ps);
+    const size_t i0 = g + (size_t)(2 * k) * groups, i1 = i0 + groups;
+    if (i0 < n) {
+      fmul<F, K>(r, ip, z1);
+      if (!(live & 1u)) Fp<F>::set_zero(r);  // zeros stay zero
+      st_fe(out, i0, r);
+    }
+    if (i1 < n) {
+      fmul<F, K>(r, ip, z0);
+      if (!(live & 2u)) Fp<F>::set_zero(r);
+      st_fe(out, i1, r);
+    }
+  }
+}
+
 // One warp per block: the <= 16384 inversions at the top are latency-bound, so they are spread one warp per SM sub-partition
 // (512 blocks over 148 SMs x 4 schedulers) and cost the latency of a single inversion.
 constexpr int kInvTopBlock = 32;
@@ -86,38 +174,6 @@ __global__ void __launch_bounds__(kInvTopBlock) fr_inv_top_kernel(size_t n, Vec 
   ld_fe(v, x, i);
   if (Fp<F>::is_zero(v)) r = v; else Fp<F>::inv_mont(r, v);
   st_fe(out, i, r);
-}
-
-// Batches of up to 8 kInvTop elements in ONE launch: every thread takes a whole group — product tree up in registers, one
-// inversion of the group product, tree down.  A lone warp per scheduler runs the 21 multiplications at ~1 us each, so above this
-// size the separate sweeps (many warps per scheduler) are faster (2^20: 98 against 105 us), below it the single launch is
-// (2^16: 40 against 44 us; profiles/r02z2_summary.txt).
-template <class F, bool K>
-__global__ void __launch_bounds__(kInvTopBlock) fr_inv_small_kernel(size_t n, size_t groups, Vec x, MVec out) {
-  const size_t g = (size_t)blockIdx.x * kInvTopBlock + threadIdx.x;
-  if (g >= groups) return;
-  fe8 z[kInvGroup], p[4], q[2], inv;
-  const uint32_t live = inv_load_group<F>(z, n, groups, g, x);
-#pragma unroll
-  for (int k = 0; k < 4; k++) fmul<F, K>(p[k], z[2 * k], z[2 * k + 1]);
-  fmul<F, K>(q[0], p[0], p[1]);
-  fmul<F, K>(q[1], p[2], p[3]);
-  fmul<F, K>(inv, q[0], q[1]);
-  Fp<F>::inv_mont(inv, inv);  // never zero: zeros entered the product as one
-  fe8 iq[2], ip[4];
-  fmul<F, K>(iq[0], inv, q[1]);
-  fmul<F, K>(iq[1], inv, q[0]);
-#pragma unroll
-  for (int k = 0; k < 4; k++) fmul<F, K>(ip[k], iq[k >> 1], p[k ^ 1]);
-#pragma unroll
-  for (int j = 0; j < kInvGroup; j++) {
-    const size_t i = g + (size_t)j * groups;
-    if (i >= n) continue;
-    fe8 r;
-    fmul<F, K>(r, ip[j >> 1], z[j ^ 1]);
-    if (!((live >> j) & 1u)) Fp<F>::set_zero(r);  // zeros stay zero
-    st_fe(out, i, r);
-  }
 }
 
 template <class F, bool K>
