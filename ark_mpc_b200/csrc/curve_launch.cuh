@@ -236,6 +236,7 @@ struct CurveLaunch {
         return post_launch(ctx, "pt_beaver_recombine_kernel");
       }
     }
+    // (Curve25519 stays at 512 threads / 128 registers: 384 / 168 measured 48.3 against 46.7 ms at 2^20, profiles/r02_point_kernels_history.txt)
     pt_beaver_recombine_kernel<C><<<pt_grid(ctx, n, 1, C::kTwoPassBlock), C::kTwoPassBlock, 0, ctx->stream>>>(n, g, gt, ts);
     return post_launch(ctx, "pt_beaver_recombine_kernel");
   }

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""BN254 G1 point Beaver recombine at n = 2^17, a few launches and nothing else (for `ncu -k regex:pt_beaver_recombine`), and its
+"""Point Beaver recombine (BN254 G1, or Curve25519 with a second argument `ed25519`) at n = 2^17 by default, a few launches and nothing else (for `ncu -k regex:pt_beaver_recombine`), and its
 event-timed duration."""
 import os
 import sys
@@ -11,8 +11,9 @@ import torch
 from ark_mpc_b200.engine import Engine
 
 n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 17)
-E = Engine(0, "bn254_fr")
-E.bind_curve("bn254_g1")
+ed = len(sys.argv) > 2 and sys.argv[2] == "ed25519"
+E = Engine(0, "curve25519_fr" if ed else "bn254_fr")
+E.bind_curve("curve25519_edwards" if ed else "bn254_g1")
 rnd = lambda seed: E.random(seed, 0, n)
 key = E.download(E.random(77, 0, 1))[0].copy()
 xs, a_s, a_m, b_s, b_m, c_s, c_m = (rnd(i) for i in range(1, 8))
@@ -28,4 +29,5 @@ for _ in range(3):
     run()
 ev1.record()
 torch.cuda.synchronize()
-print(f"bn254_g1 pt_beaver_recombine n=2^{n.bit_length() - 1}: {ev0.elapsed_time(ev1) / 3:.3f} ms (block {os.environ.get('ARKMPC_PT_BN_BLOCK', '256')})")
+blk = "512" if ed else os.environ.get("ARKMPC_PT_BN_BLOCK", "auto")
+print(f"{'curve25519_edwards' if ed else 'bn254_g1'} pt_beaver_recombine n=2^{n.bit_length() - 1}: {ev0.elapsed_time(ev1) / 3:.3f} ms (block {blk})")
