@@ -92,6 +92,7 @@ struct Bn254G1 {
   // The recombination's two variable-base passes in lock-step were +5 % in round 1 (3.94 -> 4.14 M mults/s), but a lock-step
   // loop holds twice the inlined additions; with the single-copy loops of round 2 the sequential passes win (profiles/r02f_*).
   static constexpr bool kDualChain = false;
+  static constexpr int kSplitParts = 2;      // tables of the two-pass multiplications: P and 2^68 P (with the endomorphism: four sub-scalars)
   static constexpr int kAffWords = 16;  // u32 words per fixed-table entry
   // threads per block of the two-pass kernels (recombine, mul_authenticated): ONE block per SM whose warps move through the
   // loop body together (ARK_PHASE_SYNC); 230 registers per thread allow 256 threads
@@ -272,6 +273,7 @@ struct Ed25519 {
   static constexpr int kPointBytes = 128;
   static constexpr bool kGlv = false;        // no efficient endomorphism on Curve25519
   static constexpr bool kDualChain = false;  // measured slower here (8.68 -> 7.2-7.9 M mults/s): the 128-register build already keeps 16 warps busy
+  static constexpr int kSplitParts = 4;      // tables of the two-pass multiplications: P, 2^64 P, 2^128 P, 2^192 P (see var_mul_split)
   static constexpr int kMinBlocks = 4;  // 128 registers, <= 216 B of spills, +5 % over the unconstrained 230-register build
   static constexpr int kAffWords = 24;
   static constexpr int kTwoPassBlock = 512;  // one 16-warp block per SM at 128 registers per thread (see Bn254G1::kTwoPassBlock)
@@ -518,11 +520,17 @@ constexpr int kWindows = 64;      // 4-bit windows of a 256-bit scalar
 constexpr int kTabEntries = 8;    // 1P .. 8P (entry w-1 holds w*P)
 
 template <class C>
-struct LocalTab {
-  typename C::Cached t[kTabEntries];
-  ARK_DM void put(int idx, const typename C::Cached& c) { t[idx] = c; }
+struct LocalTab {  // a view of kTabEntries entries; sub(p) is the p-th table behind it (the split multiplications keep up to four)
+  typename C::Cached* t;
+  ARK_DM void put(int idx, const typename C::Cached& c) const { t[idx] = c; }
   ARK_DM void get(typename C::Cached& c, int idx) const { c = t[idx]; }
   ARK_DM void prefetch(int) const {}
+  ARK_DM LocalTab sub(int p) const { return LocalTab{t + p * kTabEntries}; }
+};
+template <class C, int PARTS = 1>
+struct LocalTabStore {
+  typename C::Cached t[PARTS * kTabEntries];
+  ARK_DM LocalTab<C> view() { return LocalTab<C>{t}; }
 };
 
 // store w*P for w = 1..8
@@ -732,10 +740,13 @@ ARK_D void var_mul2_glv(typename C::Pt& acc0, typename C::Pt& acc1, const Tab& t
 }
 
 // ----------------------------------------------------------------------------------------------
-// Two multiplications of the SAME point (share and MAC passes of a gate): split every scalar at the middle window,
-// k = k_lo + 2^s k_hi, and give the high half its own table of P' = 2^s P.  The s doublings that produce P' are paid once,
-// and each pass then runs over half the windows with two additions per window: for 256-bit scalars 128 + 2 x 124 doublings
-// instead of 2 x 252 (Edwards), for the 33-window GLV halves 68 + 2 x 64 instead of 2 x 128 (BN254).  Additions are unchanged.
+// Two multiplications of the SAME point (share and MAC passes of a gate): cut every scalar into C::kSplitParts pieces of W
+// windows, k = sum_p 2^(4 W p) k_p, and give piece p its own table of P_p = 2^(4 W p) P.  The doublings that produce the P_p
+// are paid once, and each pass then runs over W windows with one addition per piece per window.  With D scalar bits and s
+// pieces that is D (s + 1) / s doublings for the two passes instead of 2 D, and 7 s more additions for the tables:
+//   Curve25519 (D = 256, no endomorphism): s = 2: 128 + 2 x 124 doublings, s = 4: 192 + 2 x 60 — 8 % fewer field
+//   multiplications for the gate than s = 2 (s = 8 gives the saving back to its eight tables);
+//   BN254 (33-window GLV halves, four sub-scalars already): s = 2: 68 + 2 x 64 instead of 2 x 128; a further cut gains nothing.
 // ----------------------------------------------------------------------------------------------
 // ARK_PHASE_SYNC: the warps of a block re-converge after every point operation of the two-pass loops.  The loop body (one
 // doubling + one addition, 35 KB of SASS on Curve25519, 110 KB on BN254) is larger than the SM's 32 KB instruction cache and is
@@ -747,7 +758,7 @@ ARK_D void var_mul2_glv(typename C::Pt& acc0, typename C::Pt& acc1, const Tab& t
 #define ARK_PHASE_SYNC() do { } while (0)
 #endif
 
-constexpr int kSplitWindows = kWindows / 2;            // 32 windows = 128 bits
+constexpr int kMaxSplitParts = 4;
 constexpr int kGlvSplitWindows = (kGlvWindows + 1) / 2;  // 17 windows = 68 bits
 
 // P' = 2^(4 * windows) P
@@ -759,12 +770,13 @@ ARK_D void shift_windows(typename C::Pt& p, int windows) {
   for (int j = 4 * windows - 1; j >= 0; j--) C::dbl(p, j == 0);
 }
 template <class C>
-ARK_D int split_shift_windows() { return C::kGlv ? kGlvSplitWindows : kSplitWindows; }
+ARK_D int split_shift_windows() { return C::kGlv ? kGlvSplitWindows : kWindows / C::kSplitParts; }
 
-// acc = k * P given the tables of P (lo) and of P' (hi); acc must be the identity on entry
+// acc = k * P given the tables of the P_p (tab.sub(p)); acc must be the identity on entry
 template <class C, class Tab>
-ARK_D void var_mul_split(typename C::Pt& acc, const Tab& lo, const Tab& hi, const uint32_t* k) {
+ARK_D void var_mul_split(typename C::Pt& acc, const Tab& tab, const uint32_t* k) {
   if constexpr (C::kGlv) {
+    const Tab lo = tab, hi = tab.sub(1);
     uint32_t k1[5], k2[5], r[2][5];
     bool n[2];
     glv_decompose_bn254(k, k1, n[0], k2, n[1]);
@@ -801,15 +813,15 @@ ARK_D void var_mul_split(typename C::Pt& acc, const Tab& lo, const Tab& hi, cons
       }
     }
   } else {
+    constexpr int P = C::kSplitParts, W = kWindows / P;
     uint32_t kk[8];
     signed_recode(kk, k, 8);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-    for (int i = kSplitWindows - 1; i >= 0; i--) {
-      prefetch_signed(lo, (int)window4(kk, i) - 8);
-      prefetch_signed(hi, (int)window4(kk, i + kSplitWindows) - 8);
-      if (i != kSplitWindows - 1) {
+    for (int i = W - 1; i >= 0; i--) {
+      ARK_UNROLL for (int t = 0; t < P; t++) prefetch_signed(tab.sub(t), (int)window4(kk, i + t * W) - 8);
+      if (i != W - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -821,9 +833,9 @@ ARK_D void var_mul_split(typename C::Pt& acc, const Tab& lo, const Tab& hi, cons
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-      for (int t = 0; t < 2; t++) {
+      for (int t = 0; t < P; t++) {  // one inlined addition serves every piece
         ARK_PHASE_SYNC();
-        add_signed<C>(acc, t ? hi : lo, (int)window4(kk, i + (t ? kSplitWindows : 0)) - 8);
+        add_signed<C>(acc, tab.sub(t), (int)window4(kk, i + t * W) - 8);
       }
     }
   }
@@ -831,8 +843,9 @@ ARK_D void var_mul_split(typename C::Pt& acc, const Tab& lo, const Tab& hi, cons
 
 // (acc0, acc1) = (ka * P, kb * P) in lock-step (C::kDualChain), same tables
 template <class C, class Tab>
-ARK_D void var_mul2_split(typename C::Pt& acc0, typename C::Pt& acc1, const Tab& lo, const Tab& hi, const uint32_t* ka, const uint32_t* kb) {
+ARK_D void var_mul2_split(typename C::Pt& acc0, typename C::Pt& acc1, const Tab& tab, const uint32_t* ka, const uint32_t* kb) {
   if constexpr (C::kGlv) {
+    const Tab lo = tab, hi = tab.sub(1);
     uint32_t a1[5], a2[5], b1[5], b2[5], t[5];
     bool na1, na2, nb1, nb2;
     glv_decompose_bn254(ka, a1, na1, a2, na2);
@@ -871,17 +884,19 @@ ARK_D void var_mul2_split(typename C::Pt& acc0, typename C::Pt& acc1, const Tab&
       glv_add<C>(acc1, hi, hb2, true, nb2);
     }
   } else {
+    constexpr int P = C::kSplitParts, W = kWindows / P;
     uint32_t kk0[8], kk1[8];
     signed_recode(kk0, ka, 8);
     signed_recode(kk1, kb, 8);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-    for (int i = kSplitWindows - 1; i >= 0; i--) {
-      const int l0 = (int)window4(kk0, i) - 8, l1 = (int)window4(kk1, i) - 8;
-      const int h0 = (int)window4(kk0, i + kSplitWindows) - 8, h1 = (int)window4(kk1, i + kSplitWindows) - 8;
-      prefetch_signed(lo, l0); prefetch_signed(lo, l1); prefetch_signed(hi, h0); prefetch_signed(hi, h1);
-      if (i != kSplitWindows - 1) {
+    for (int i = W - 1; i >= 0; i--) {
+      ARK_UNROLL for (int t = 0; t < P; t++) {
+        prefetch_signed(tab.sub(t), (int)window4(kk0, i + t * W) - 8);
+        prefetch_signed(tab.sub(t), (int)window4(kk1, i + t * W) - 8);
+      }
+      if (i != W - 1) {
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -890,10 +905,13 @@ ARK_D void var_mul2_split(typename C::Pt& acc0, typename C::Pt& acc1, const Tab&
           C::dbl(acc1, j == 3);
         }
       }
-      add_signed<C>(acc0, lo, l0);
-      add_signed<C>(acc1, lo, l1);
-      add_signed<C>(acc0, hi, h0);
-      add_signed<C>(acc1, hi, h1);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+      for (int t = 0; t < P; t++) {
+        add_signed<C>(acc0, tab.sub(t), (int)window4(kk0, i + t * W) - 8);
+        add_signed<C>(acc1, tab.sub(t), (int)window4(kk1, i + t * W) - 8);
+      }
     }
   }
 }

@@ -33,39 +33,42 @@ ARK_D void pt_mul_elem(Tab& tab, typename C::Pt& out, const fe8& s, const typena
 }
 template <class C>
 ARK_D void pt_mul_elem(typename C::Pt& out, const fe8& s, const typename C::Pt& P) {
-  LocalTab<C> tab;
+  LocalTabStore<C> store;
+  LocalTab<C> tab = store.view();
   pt_mul_elem<C>(tab, out, s, P);
 }
 
-// tables of P and of P' = 2^s P for the split two-pass multiplications (curve.cuh)
+// tables of P_p = 2^(4 W p) P, p < C::kSplitParts, for the split two-pass multiplications (curve.cuh)
 template <class C, class Tab>
-ARK_D void build_split_tables(Tab& lo, Tab& hi, const typename C::Pt& P) {
+ARK_D void build_split_tables(const Tab& tab, const typename C::Pt& P) {
   typename C::Pt Q = P;
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-  for (int h = 0; h < 2; h++) {  // one inlined copy of the table construction
+  for (int h = 0; h < C::kSplitParts; h++) {  // one inlined copy of the table construction
     if (h) shift_windows<C>(Q, split_shift_windows<C>());
-    build_table<C>(h ? hi : lo, Q);
+    Tab part = tab.sub(h);
+    build_table<C>(part, Q);
   }
 }
 
 // (out0, out1) = (s0 * P, s1 * P): the two passes share the tables of P and 2^s P
 template <class C, class Tab>
-ARK_D void pt_mul2_elem(Tab& lo, Tab& hi, typename C::Pt& out0, typename C::Pt& out1, const fe8& s0, const fe8& s1, const typename C::Pt& P) {
+ARK_D void pt_mul2_elem(Tab& tab, typename C::Pt& out0, typename C::Pt& out1, const fe8& s0, const fe8& s1, const typename C::Pt& P) {
   uint32_t k[8];
-  build_split_tables<C>(lo, hi, P);
+  build_split_tables<C>(tab, P);
   scalar_to_plain<typename C::R>(k, s0);
   C::set_identity(out0);
-  var_mul_split<C>(out0, lo, hi, k);
+  var_mul_split<C>(out0, tab, k);
   scalar_to_plain<typename C::R>(k, s1);
   C::set_identity(out1);
-  var_mul_split<C>(out1, lo, hi, k);
+  var_mul_split<C>(out1, tab, k);
 }
 template <class C>
 ARK_D void pt_mul2_elem(typename C::Pt& out0, typename C::Pt& out1, const fe8& s0, const fe8& s1, const typename C::Pt& P) {
-  LocalTab<C> lo, hi;
-  pt_mul2_elem<C>(lo, hi, out0, out1, s0, s1, P);
+  LocalTabStore<C, kMaxSplitParts> store;
+  LocalTab<C> tab = store.view();
+  pt_mul2_elem<C>(tab, out0, out1, s0, s1, P);
 }
 
 // out = s * G
@@ -93,7 +96,8 @@ ARK_D void pt_share_add_public_elem(Tab& tab, typename C::Pt& out_s, typename C:
 template <class C>
 ARK_D void pt_share_add_public_elem(typename C::Pt& out_s, typename C::Pt& out_m, int party, bool sub, const fe8& key,
                                     const typename C::Pt& a_s, const typename C::Pt& a_m, const typename C::Pt& pub) {
-  LocalTab<C> tab;
+  LocalTabStore<C> store;
+  LocalTab<C> tab = store.view();
   pt_share_add_public_elem<C>(tab, out_s, out_m, party, sub, key, a_s, a_m, pub);
 }
 
@@ -107,7 +111,8 @@ ARK_D void pt_mac_check_elem(Tab& tab, typename C::Pt& out, const fe8& key, cons
 }
 template <class C>
 ARK_D void pt_mac_check_elem(typename C::Pt& out, const fe8& key, const typename C::Pt& opened, const typename C::Pt& mac) {
-  LocalTab<C> tab;
+  LocalTabStore<C> store;
+  LocalTab<C> tab = store.view();
   pt_mac_check_elem<C>(tab, out, key, opened, mac);
 }
 
@@ -130,7 +135,8 @@ ARK_D bool pt_valid_elem(Tab& tab, const typename C::Pt& P) {
 }
 template <class C>
 ARK_D bool pt_valid_elem(const typename C::Pt& P) {
-  LocalTab<C> tab;
+  LocalTabStore<C> store;
+  LocalTab<C> tab = store.view();
   return pt_valid_elem<C>(tab, P);
 }
 
@@ -148,7 +154,7 @@ ARK_D void pt_beaver_mask_elem(fe8& d_mine, typename C::Pt& E_mine, const fe8& x
 // Writes the opened d and E, and the two result points through `emit(which, point)` (which = 0 share, 1 mac)
 // so that a kernel can store each as soon as its pass finishes.
 template <class C, bool DUAL, class Tab, class Emit>
-ARK_D void pt_beaver_recombine_elem(Tab& tab, Tab& tab_hi, fe8& d, typename C::Pt& E, int party, const fe8& key, const fe8& d_mine, const fe8& d_peer,
+ARK_D void pt_beaver_recombine_elem(Tab& tab, fe8& d, typename C::Pt& E, int party, const fe8& key, const fe8& d_mine, const fe8& d_peer,
                                     const typename C::Pt& E_mine, const typename C::Pt& E_peer, const fe8& a_s, const fe8& a_m,
                                     const fe8& b_s, const fe8& b_m, const fe8& c_s, const fe8& c_m,
                                     const typename C::Aff* gtab, Emit emit) {
@@ -156,7 +162,7 @@ ARK_D void pt_beaver_recombine_elem(Tab& tab, Tab& tab_hi, fe8& d, typename C::P
   FR::add(d, d_mine, d_peer);
   E = E_mine;
   C::add(E, E_peer);
-  build_split_tables<C>(tab, tab_hi, E);
+  build_split_tables<C>(tab, E);
   fe8 sv[2], tv[2], t;
   if (party == 0) FR::add(sv[0], a_s, d); else sv[0] = a_s;
   FR::mul(t, d, b_s);
@@ -172,7 +178,7 @@ ARK_D void pt_beaver_recombine_elem(Tab& tab, Tab& tab_hi, fe8& d, typename C::P
     C::set_identity(acc1);
     scalar_to_plain<typename C::R>(k0, sv[0]);
     scalar_to_plain<typename C::R>(k1, sv[1]);
-    var_mul2_split<C>(acc0, acc1, tab, tab_hi, k0, k1);
+    var_mul2_split<C>(acc0, acc1, tab, k0, k1);
     scalar_to_plain<typename C::R>(k0, tv[0]);
     fix_mul_acc<C>(acc0, gtab, k0);
     emit(0, acc0);
@@ -188,7 +194,7 @@ ARK_D void pt_beaver_recombine_elem(Tab& tab, Tab& tab_hi, fe8& d, typename C::P
       typename C::Pt acc;
       C::set_identity(acc);
       scalar_to_plain<typename C::R>(k, sv[which]);
-      var_mul_split<C>(acc, tab, tab_hi, k);
+      var_mul_split<C>(acc, tab, k);
       scalar_to_plain<typename C::R>(k, tv[which]);
       fix_mul_acc<C>(acc, gtab, k);
       emit(which, acc);
@@ -201,8 +207,9 @@ ARK_D void pt_beaver_recombine_elem(fe8& d, typename C::Pt& E, int party, const 
                                     const typename C::Pt& E_mine, const typename C::Pt& E_peer, const fe8& a_s, const fe8& a_m,
                                     const fe8& b_s, const fe8& b_m, const fe8& c_s, const fe8& c_m,
                                     const typename C::Aff* gtab, Emit emit) {
-  LocalTab<C> tab, tab_hi;
-  pt_beaver_recombine_elem<C, DUAL>(tab, tab_hi, d, E, party, key, d_mine, d_peer, E_mine, E_peer, a_s, a_m, b_s, b_m, c_s, c_m, gtab, emit);
+  LocalTabStore<C, kMaxSplitParts> store;
+  LocalTab<C> tab = store.view();
+  pt_beaver_recombine_elem<C, DUAL>(tab, d, E, party, key, d_mine, d_peer, E_mine, E_peer, a_s, a_m, b_s, b_m, c_s, c_m, gtab, emit);
 }
 
 }  // namespace ark

@@ -43,12 +43,12 @@ __device__ __forceinline__ void st_pt(const PMVec& v, size_t i, const typename C
 // Window tables of the variable-base multiplications: L2-resident scratch records instead of per-thread local arrays.
 // Every resident 128-thread block claims one of kTabSlotsPerSm slots of its SM (an atomic bit mask per SM id), and each of its
 // threads owns one contiguous kTabRecordBytes record in that slot: entries are written and read with 256-bit accesses, one
-// 32-byte sector per lane per instruction, no over-fetch.  The scratch is (SM ids) x 6 x 128 x 2 KiB, is reused by every
+// 32-byte sector per lane per instruction, no over-fetch.  The scratch is (SM ids) x 6 x 128 x 4 KiB, is reused by every
 // block that ever runs on the SM, and therefore stays in (or near) L2.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTabSlotsPerSm = 6;
 constexpr int kTabHalfBytes = kTabEntries * 128;     // one table: 8 entries of up to 128 B (Edwards cached form); BN254 uses 96 B of each
-constexpr int kTabRecordBytes = 2 * kTabHalfBytes;   // the table of P and, for the two-pass gates, of 2^s P behind it
+constexpr int kTabRecordBytes = kMaxSplitParts * kTabHalfBytes;  // the table of P and, for the two-pass gates, of the 2^(s p) P behind it
 
 struct TabScratch {
   char* base;
@@ -83,6 +83,7 @@ struct GlobalTab {
                    : "memory");
   }
   __device__ __forceinline__ void prefetch(int idx) const { asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + idx * 128)); }
+  __device__ __forceinline__ GlobalTab sub(int p) const { return GlobalTab{rec + p * kTabHalfBytes}; }
 };
 
 // All threads of the block call both; `token` identifies the claim between the two.  A block of B = 128 u threads claims u
@@ -198,7 +199,6 @@ template <class C>
 __global__ void __launch_bounds__(C::kTwoPassBlock, 1) pt_mul_auth_kernel(size_t n, Vec s_share, Vec s_mac, PVec P, PMVec out_s, PMVec out_m, TabScratch ts) {
   unsigned int token;
   GlobalTab<C> tab = tab_claim<C>(ts, token);
-  GlobalTab<C> tab_hi{tab.rec + kTabHalfBytes};
   const size_t step = (size_t)gridDim.x * blockDim.x;
   // block-uniform trip count (the two-pass loops synchronise the block, ARK_PHASE_SYNC): idle lanes recompute element n-1
   for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += step) {
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(C::kTwoPassBlock, 1) pt_mul_auth_kernel(size_t
     ld_pt<C>(x, P, i);
     ld_fe(k0, s_share, i);
     ld_fe(k1, s_mac, i);
-    pt_mul2_elem<C>(tab, tab_hi, r0, r1, k0, k1, x);
+    pt_mul2_elem<C>(tab, r0, r1, k0, k1, x);
     if (live) {
       st_pt<C>(out_s, i, r0);
       st_pt<C>(out_m, i, r1);
@@ -359,7 +359,6 @@ __global__ void __launch_bounds__(B, 1) pt_beaver_recombine_kernel(size_t n, con
                                                                       const typename C::Aff* __restrict__ gtab, TabScratch ts) {
   unsigned int token;
   GlobalTab<C> tab = tab_claim<C>(ts, token);
-  GlobalTab<C> tab_hi{tab.rec + kTabHalfBytes};
   const size_t step = (size_t)gridDim.x * blockDim.x;
   // block-uniform trip count (the two-pass loops synchronise the block, ARK_PHASE_SYNC): idle lanes recompute element n-1
   for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += step) {
@@ -377,7 +376,7 @@ __global__ void __launch_bounds__(B, 1) pt_beaver_recombine_kernel(size_t n, con
     ld_fe(bm, g.b_m, i);
     ld_fe(cs, g.c_s, i);
     ld_fe(cm, g.c_m, i);
-    pt_beaver_recombine_elem<C, C::kDualChain>(tab, tab_hi, d, E, g.party, g.key, dm, dp, Em, Ep, as, am, bs, bm, cs, cm, gtab,
+    pt_beaver_recombine_elem<C, C::kDualChain>(tab, d, E, g.party, g.key, dm, dp, Em, Ep, as, am, bs, bm, cs, cm, gtab,
                                 [&](int which, const typename C::Pt& r) { if (live) st_pt<C>(which ? g.out_m : g.out_s, i, r); });
     if (g.open && live) {
       st_fe(g.d_open, i, d);
