@@ -93,6 +93,7 @@ struct Bn254G1 {
   // loop holds twice the inlined additions; with the single-copy loops of round 2 the sequential passes win (profiles/r02f_*).
   static constexpr bool kDualChain = false;
   static constexpr int kSplitParts = 2;      // tables of the two-pass multiplications: P and 2^68 P (with the endomorphism: four sub-scalars)
+  static constexpr bool kAffineTables = true;  // window tables normalised with one shared inversion: mixed additions in the loops
   static constexpr int kAffWords = 16;  // u32 words per fixed-table entry
   // threads per block of the two-pass kernels (recombine, mul_authenticated): ONE block per SM whose warps move through the
   // loop body together (ARK_PHASE_SYNC); 230 registers per thread allow 256 threads
@@ -274,6 +275,7 @@ struct Ed25519 {
   static constexpr bool kGlv = false;        // no efficient endomorphism on Curve25519
   static constexpr bool kDualChain = false;  // measured slower here (8.68 -> 7.2-7.9 M mults/s): the 128-register build already keeps 16 warps busy
   static constexpr int kSplitParts = 4;      // tables of the two-pass multiplications: P, 2^64 P, 2^128 P, 2^192 P (see var_mul_split)
+  static constexpr bool kAffineTables = false;  // the extended-coordinates addition gains one multiplication from Z = 1: not worth an inversion
   static constexpr int kMinBlocks = 4;  // 128 registers, <= 216 B of spills, +5 % over the unconstrained 230-register build
   static constexpr int kAffWords = 24;
   static constexpr int kTwoPassBlock = 512;  // one 16-warp block per SM at 128 registers per thread (see Bn254G1::kTwoPassBlock)
@@ -521,16 +523,24 @@ constexpr int kTabEntries = 8;    // 1P .. 8P (entry w-1 holds w*P)
 
 template <class C>
 struct LocalTab {  // a view of kTabEntries entries; sub(p) is the p-th table behind it (the split multiplications keep up to four)
+  static constexpr bool kAffine = C::kAffineTables;  // entry format once the tables are finished (finish_tables)
   typename C::Cached* t;
-  ARK_DM void put(int idx, const typename C::Cached& c) const { t[idx] = c; }
-  ARK_DM void get(typename C::Cached& c, int idx) const { c = t[idx]; }
+  fe8* aux;  // one spare field element per entry (normalize_tables)
+  template <class T> ARK_DM void put(int idx, const T& c) const {
+    static_assert(sizeof(T) <= sizeof(typename C::Cached), "entry too large");
+    memcpy(static_cast<void*>(&t[idx]), &c, sizeof(T));
+  }
+  template <class T> ARK_DM void get(T& c, int idx) const { memcpy(&c, static_cast<const void*>(&t[idx]), sizeof(T)); }
+  ARK_DM void put_aux(int idx, const fe8& v) const { aux[idx] = v; }
+  ARK_DM void get_aux(fe8& v, int idx) const { v = aux[idx]; }
   ARK_DM void prefetch(int) const {}
-  ARK_DM LocalTab sub(int p) const { return LocalTab{t + p * kTabEntries}; }
+  ARK_DM LocalTab sub(int p) const { return LocalTab{t + p * kTabEntries, aux + p * kTabEntries}; }
 };
 template <class C, int PARTS = 1>
 struct LocalTabStore {
   typename C::Cached t[PARTS * kTabEntries];
-  ARK_DM LocalTab<C> view() { return LocalTab<C>{t}; }
+  fe8 aux[PARTS * kTabEntries];
+  ARK_DM LocalTab<C> view() { return LocalTab<C>{t, aux}; }
 };
 
 // store w*P for w = 1..8
@@ -548,6 +558,57 @@ ARK_D void build_table(Tab& tab, const typename C::Pt& P) {
     C::cache(c, t);
     tab.put(w - 1, c);
   }
+}
+
+// Tab::kAffine (BN254, C::kAffineTables, wherever the kernel asks for it): the entries just built (Jacobian, `nparts` tables of kTabEntries behind `tab`) are brought to affine
+// form with ONE shared inversion (Montgomery's trick over the Z coordinates: a prefix product per entry parked in the entry's
+// spare 32 bytes, a safegcd inversion, a walk back), so that every addition of the multiplication loops is the mixed one — 7M + 4S
+// instead of 11M + 5S, 132 times per two-pass gate — for ~7 multiplications per entry and an inversion that costs about as many
+// instructions as 110 multiplications.  The identity (Z = 0) becomes (0, 0), which is not on the curve and is skipped by glv_add.
+template <class C, class Tab>
+ARK_D void normalize_tables(const Tab& tab, int nparts) {
+  using K = typename C::K;
+  const int n = nparts * kTabEntries;
+  fe8 acc;
+  K::one(acc);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int e = 0; e < n; e++) {
+    typename C::Pt q;
+    tab.get(q, e);
+    tab.put_aux(e, acc);  // product of the (non-zero) Z before this entry
+    if (!K::is_zero(q.Z)) K::mul(acc, acc, q.Z);
+  }
+  fe8 inv;
+  Fp<typename C::Q>::inv_mont(inv, acc);  // acc != 0: zeros were skipped
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int e = n - 1; e >= 0; e--) {
+    typename C::Pt q;
+    typename C::Aff a;
+    fe8 pre, zi, zi2;
+    tab.get(q, e);
+    tab.get_aux(pre, e);
+    if (K::is_zero(q.Z)) {
+      K::zero(a.x);
+      K::zero(a.y);
+    } else {
+      K::mul(zi, inv, pre);     // 1 / Z_e
+      K::mul(inv, inv, q.Z);    // drop Z_e from the running inverse
+      K::sqr(zi2, zi);
+      K::mul(a.x, q.X, zi2);
+      K::mul(zi2, zi2, zi);
+      K::mul(a.y, q.Y, zi2);
+    }
+    tab.put(e, a);
+  }
+}
+// called once the tables of a multiplication are built
+template <class C, class Tab>
+ARK_D void finish_tables(const Tab& tab, int nparts) {
+  if constexpr (Tab::kAffine) normalize_tables<C>(tab, nparts);
 }
 
 // k' = k + 0x8888...8 over `limbs` words; returns the carry out of the top word (an extra, non-negative top digit)
@@ -647,6 +708,20 @@ constexpr int kGlvWindows = 33;
 template <class C, class Tab>
 ARK_D void glv_add(typename C::Pt& acc, const Tab& tab, int digit, bool endo, bool neg) {
   if (digit == 0) return;
+  if constexpr (Tab::kAffine) {
+    typename C::Aff a;
+    tab.get(a, (digit < 0 ? -digit : digit) - 1);
+    if (C::K::is_zero(a.x) && C::K::is_zero(a.y)) return;  // the identity (normalize_tables)
+    if (endo) {
+      fe8 beta;
+      beta.v[0] = 0xd782e155u; beta.v[1] = 0x71930c11u; beta.v[2] = 0xffbe3323u; beta.v[3] = 0xa6bb947cu;
+      beta.v[4] = 0xd4741444u; beta.v[5] = 0xaa303344u; beta.v[6] = 0x26594943u; beta.v[7] = 0x2c3b3f0du;
+      C::K::mul(a.x, a.x, beta);
+    }
+    if (neg != (digit < 0)) C::K::neg(a.y, a.y);
+    C::madd(acc, a);
+    return;
+  }
   typename C::Cached t;
   tab.get(t, (digit < 0 ? -digit : digit) - 1);
   if (endo) {

@@ -27,6 +27,7 @@ template <class C, class Tab>
 ARK_D void pt_mul_elem(Tab& tab, typename C::Pt& out, const fe8& s, const typename C::Pt& P) {
   uint32_t k[8];
   build_table<C>(tab, P);
+  finish_tables<C>(tab, 1);
   scalar_to_plain<typename C::R>(k, s);
   C::set_identity(out);
   var_mul<C>(out, tab, k);
@@ -50,6 +51,7 @@ ARK_D void build_split_tables(const Tab& tab, const typename C::Pt& P) {
     Tab part = tab.sub(h);
     build_table<C>(part, Q);
   }
+  finish_tables<C>(tab, C::kSplitParts);
 }
 
 // (out0, out1) = (s0 * P, s1 * P): the two passes share the tables of P and 2^s P
@@ -127,6 +129,7 @@ ARK_D bool pt_valid_elem(Tab& tab, const typename C::Pt& P) {
     const uint32_t k[8] = {R::P0, R::P1, R::P2, R::P3, R::P4, R::P5, R::P6, R::P7};
     typename C::Pt acc;
     build_table<C>(tab, P);
+    finish_tables<C>(tab, 1);
     C::set_identity(acc);
     var_mul<C>(acc, tab, k);
     return C::is_identity(acc);

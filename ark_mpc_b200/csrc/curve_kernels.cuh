@@ -59,28 +59,44 @@ struct TabScratch {
 // round trip in the middle of a dependent chain of point additions, and `prefetch` lets the variable-base loops request the
 // entry of the NEXT window before the four doublings that precede its use.  A thread only ever reads records it wrote itself,
 // so L1 residency needs no coherence beyond program order.
-template <class C>
+template <class C, bool AFF = C::kAffineTables>
 struct GlobalTab {
+  static constexpr bool kAffine = AFF;  // entries are affine once the tables are finished (curve.cuh: finish_tables, glv_add)
   char* rec;
-  __device__ __forceinline__ void put(int idx, const typename C::Cached& c) const {
+  template <class T>
+  __device__ __forceinline__ void put(int idx, const T& c) const {
+    static_assert(sizeof(T) % 32 == 0 && sizeof(T) <= 128, "entries are whole 32-byte words of a 128-byte slot");
     const fe8* f = reinterpret_cast<const fe8*>(&c);
     char* a = rec + idx * 128;
 #pragma unroll
-    for (int k = 0; k < (int)(sizeof(typename C::Cached) / 32); k++)
+    for (int k = 0; k < (int)(sizeof(T) / 32); k++)
       asm volatile("st.global.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(f[k].v[0]), "r"(f[k].v[1]), "r"(f[k].v[2]), "r"(f[k].v[3]),
                    "r"(f[k].v[4]), "r"(f[k].v[5]), "r"(f[k].v[6]), "r"(f[k].v[7]), "l"(a + 32 * k)
                    : "memory");
   }
-  __device__ __forceinline__ void get(typename C::Cached& c, int idx) const {
+  template <class T>
+  __device__ __forceinline__ void get(T& c, int idx) const {
     fe8* f = reinterpret_cast<fe8*>(&c);
     const char* a = rec + idx * 128;
 #pragma unroll
-    for (int k = 0; k < (int)(sizeof(typename C::Cached) / 32); k++)
+    for (int k = 0; k < (int)(sizeof(T) / 32); k++)
       asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                    : "=r"(f[k].v[0]), "=r"(f[k].v[1]), "=r"(f[k].v[2]), "=r"(f[k].v[3]), "=r"(f[k].v[4]), "=r"(f[k].v[5]), "=r"(f[k].v[6]),
                      "=r"(f[k].v[7])
                    : "l"(a + 32 * k)
                    : "memory");
+  }
+  // the last 32 bytes of a slot: free while the entry is a 96-byte Jacobian point (normalize_tables parks a prefix product there)
+  __device__ __forceinline__ void put_aux(int idx, const fe8& v) const {
+    asm volatile("st.global.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(v.v[0]), "r"(v.v[1]), "r"(v.v[2]), "r"(v.v[3]), "r"(v.v[4]),
+                 "r"(v.v[5]), "r"(v.v[6]), "r"(v.v[7]), "l"(rec + idx * 128 + 96)
+                 : "memory");
+  }
+  __device__ __forceinline__ void get_aux(fe8& v, int idx) const {
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.v[0]), "=r"(v.v[1]), "=r"(v.v[2]), "=r"(v.v[3]), "=r"(v.v[4]), "=r"(v.v[5]), "=r"(v.v[6]), "=r"(v.v[7])
+                 : "l"(rec + idx * 128 + 96)
+                 : "memory");
   }
   __device__ __forceinline__ void prefetch(int idx) const { asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + idx * 128)); }
   __device__ __forceinline__ GlobalTab sub(int p) const { return GlobalTab{rec + p * kTabHalfBytes}; }
@@ -358,7 +374,10 @@ template <class C, int B = C::kTwoPassBlock>
 __global__ void __launch_bounds__(B, 1) pt_beaver_recombine_kernel(size_t n, const __grid_constant__ PtRecombineArgs g,
                                                                       const typename C::Aff* __restrict__ gtab, TabScratch ts) {
   unsigned int token;
-  GlobalTab<C> tab = tab_claim<C>(ts, token);
+  // BN254: affine tables (mixed additions) pay in the 256-thread build (11.8 -> 11.3 ms at 2^17) and cost in the 384-thread one
+  // (78.9 -> 81.3 ms at 2^20, profiles/r02z7_summary.txt), so the deep-grid variant keeps Jacobian entries
+  constexpr bool kAff = C::kAffineTables && B == C::kTwoPassBlock;
+  GlobalTab<C, kAff> tab{tab_claim<C>(ts, token).rec};
   const size_t step = (size_t)gridDim.x * blockDim.x;
   // block-uniform trip count (the two-pass loops synchronise the block, ARK_PHASE_SYNC): idle lanes recompute element n-1
   for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += step) {
