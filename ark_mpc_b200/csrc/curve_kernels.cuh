@@ -141,12 +141,14 @@ static __global__ void nsmid_kernel(unsigned int* out) {
   *out = n;
 }
 
-// fixed-base table: 32 windows x 256 entries, one thread per entry (entry 0 of each window is unused)
+// fixed-base table: kFixWindows x kFixEntries entries, one thread per entry (entry 0 of each window is unused)
+constexpr int kGtabBlock = 256;
 template <class C>
-__global__ void __launch_bounds__(kFixEntries) pt_gtab_kernel(typename C::Aff* gtab) {
-  const int j = blockIdx.x;
-  const uint32_t w = threadIdx.x;
-  if (j < kFixWindows && w != 0) build_gtab_entry<C>(gtab[j * kFixEntries + w], j, w);
+__global__ void __launch_bounds__(kGtabBlock) pt_gtab_kernel(typename C::Aff* gtab) {
+  const unsigned e = blockIdx.x * kGtabBlock + threadIdx.x;
+  const int j = (int)(e / kFixEntries);
+  const uint32_t w = e % kFixEntries;
+  if (j < kFixWindows && w != 0) build_gtab_entry<C>(gtab[e], j, w);
 }
 
 // strided point copy: PointShare vector <-> separate share / mac point vectors

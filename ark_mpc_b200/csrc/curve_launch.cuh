@@ -73,7 +73,7 @@ struct CurveLaunch {
       ARK_CUDA(ctx, cudaMalloc(&mem, sizeof(Aff) * kFixWindows * kFixEntries));
       cudaError_t e = cudaMemsetAsync(mem, 0, sizeof(Aff) * kFixWindows * kFixEntries, ctx->stream);
       if (e == cudaSuccess) {
-        pt_gtab_kernel<C><<<kFixWindows, kFixEntries, 0, ctx->stream>>>(static_cast<Aff*>(mem));
+        pt_gtab_kernel<C><<<kFixWindows * kFixEntries / kGtabBlock, kGtabBlock, 0, ctx->stream>>>(static_cast<Aff*>(mem));
         ctx->launches++;
         e = cudaGetLastError();
       }

@@ -61,15 +61,33 @@ extern "C" int emu_run(int field, int op, int party, const uint32_t* in, uint32_
 }
 
 // ---- curve gates (curve.cuh / curve_gates.cuh) ----
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "../../ark_mpc_b200/csrc/curve_gates.cuh"
 
 template <class C> static const typename C::Aff* host_gtab() {
   static std::vector<typename C::Aff> tab;
   if (tab.empty()) {
+    // Built incrementally (entry w = entry w - 1 + base_j: one addition and one normalisation each; build_gtab_entry's 12 j
+    // doublings per entry would take minutes under emulation) and checked against build_gtab_entry on a sample of entries.
     tab.resize(kFixWindows * kFixEntries);
-    for (int j = 0; j < kFixWindows; j++)
-      for (uint32_t w = 1; w < (uint32_t)kFixEntries; w++) build_gtab_entry<C>(tab[j * kFixEntries + w], j, w);
+    typename C::Pt base;
+    C::set_generator(base);
+    for (int j = 0; j < kFixWindows; j++) {
+      typename C::Pt acc;
+      C::set_identity(acc);
+      for (uint32_t w = 1; w < (uint32_t)kFixEntries; w++) {
+        C::add(acc, base);
+        C::to_aff(tab[j * kFixEntries + w], acc);
+      }
+      for (uint32_t w : {1u, 2u, 255u, 256u, 2049u, (uint32_t)kFixEntries - 1u}) {
+        typename C::Aff chk;
+        build_gtab_entry<C>(chk, j, w);
+        if (memcmp(&chk, &tab[j * kFixEntries + w], sizeof chk) != 0) { fprintf(stderr, "fixed-base table mismatch at (%d, %u)\n", j, w); abort(); }
+      }
+      for (int i = 0; i < kFixBits; i++) C::dbl(base);
+    }
   }
   return tab.data();
 }
