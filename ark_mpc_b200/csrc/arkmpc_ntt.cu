@@ -73,7 +73,8 @@ int ntt_plane(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t
   const size_t tiles = n >> tile_log;
   static const int tile_threads = [] { const char* e = getenv("ARKMPC_NTT_TILE_THREADS"); const int v = e ? atoi(e) : 0; return v == 128 || v == 256 ? v : kNttThreads; }();
   static const int stride_threads = [] { const char* e = getenv("ARKMPC_NTT_STRIDE_THREADS"); const int v = e ? atoi(e) : 0; return v == 128 || v == 256 || v == 512 ? v : 0; }();
-  fr_ntt_tile_kernel<F, K><<<(unsigned)tiles, tile_threads, ((size_t)32 << tile_log), ctx->stream>>>(log2n, vec(in), vec(tw), mvec(out));
+  const bool fold_scale = inverse && log2n >= 2;  // n^-1 rides on the first double stage of the tile kernel
+  fr_ntt_tile_kernel<F, K><<<(unsigned)tiles, tile_threads, ((size_t)32 << tile_log), ctx->stream>>>(log2n, vec(in), vec(tw), fold_scale ? consts + 1 : nullptr, mvec(out));
   rc = post_launch(ctx, "fr_ntt_tile_kernel");
   const int rest = log2n > kNttTileLog ? log2n - kNttTileLog : 0;
   int passes = (rest + kNttStrideLog - 1) / kNttStrideLog;
@@ -89,7 +90,7 @@ int ntt_plane(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t
     rc = post_launch(ctx, "fr_ntt_strided_kernel");
     s0 += T;
   }
-  if (rc == ARKMPC_OK && inverse) {
+  if (rc == ARKMPC_OK && inverse && !fold_scale) {
     fr_scale_dev_kernel<F><<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(n, vec(out), consts + 1, mvec(out));
     rc = post_launch(ctx, "fr_scale_dev_kernel");
   }
