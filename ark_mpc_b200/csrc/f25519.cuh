@@ -156,19 +156,13 @@ struct F25519 {
     canon(r, t);
   }
 
-  // a^(p-2); inv(0) = 0
+  // a^-1 by division steps on the canonical residue (Fp::inv_safegcd; a Fermat chain for 2^255 - 21 is 255 squarings and 250
+  // multiplications); inv(0) = 0
   ARK_DM static void inv(fe8& r, const fe8& a) {
-    const uint32_t e[8] = {0xffffffebu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x7fffffffu};
-    fe8 acc;
-    one(acc);
-#if defined(__CUDACC__)
-#pragma unroll 1
-#endif
-    for (int i = 254; i >= 0; i--) {
-      sqr(acc, acc);
-      if ((e[i >> 5] >> (i & 31)) & 1u) mul(acc, acc, a);
-    }
-    r = acc;
+    fe8 c;
+    canon(c, a);
+    if (is_zero(c)) { zero(r); return; }
+    Fp<Curve25519Fq>::inv_safegcd(r, c);
   }
 };
 
