@@ -31,7 +31,7 @@ void launch_pdl(const arkmpc_ctx* ctx, void (*kern)(KArgs...), unsigned grid, cu
 // ---- launch helpers shared by the device-pointer ABI and the host-buffer path ----
 template <class F>
 int launch_mask(arkmpc_ctx* ctx, cudaStream_t s, size_t n, Vec x, Vec y, Vec a, Vec b, MVec d, MVec e) {
-  launch_pdl(ctx, beaver_mask_kernel<F>, grid_stream(ctx, n, 8), s, n, x, y, a, b, d, e, take_hint(ctx));
+  launch_pdl(ctx, beaver_mask_kernel<F>, grid_stream(ctx, n, 8), s, n, x, y, a, b, d, e, take_hint(ctx), ctx->l2_keep ? 1 : 0);
   return post_launch(ctx, "beaver_mask_kernel");
 }
 
@@ -150,6 +150,8 @@ int arkmpc_ctx_create(int device, arkmpc_ctx** out) {
   {
     const char* v = getenv("ARKMPC_RECOMBINE");
     ctx->use_tma = v && strcmp(v, "tma") == 0;
+    const char* l2 = getenv("ARKMPC_L2_KEEP");
+    if (l2) ctx->l2_keep = strcmp(l2, "0") != 0;
     const char* pd = getenv("ARKMPC_PDL");
     if (pd && strcmp(pd, "0") == 0) ctx->pdl = false;
     const char* gm = getenv("ARKMPC_GRID");

@@ -45,6 +45,7 @@ struct arkmpc_ctx {
   int* flag_host = nullptr;  // pinned
   bool use_tma = false;      // ARKMPC_RECOMBINE=tma
   bool hint_independent = false;  // arkmpc_ctx_hint_independent: consumed by the next Beaver kernel launch
+  bool l2_keep = true;       // K1 stores its masks evict-last in L2 (ARKMPC_L2_KEEP=0 disables)
   bool pdl = true;           // Beaver K1/K2 launched with programmatic stream serialization (ARKMPC_PDL=0 disables)
   bool full_grids = true;    // element-wise kernels: one element per thread instead of a persistent wave (ARKMPC_GRID=persistent reverts)
   int xy_mode = 2;           // host-buffer path, how x.share / y.share reach the mask kernel: 0 flat AoS copy, 1 strided DMA copy, 2 zero-copy reads of pinned memory (ARKMPC_XY=flat|2d|zc)

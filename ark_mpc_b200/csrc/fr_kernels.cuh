@@ -36,6 +36,24 @@ __device__ __forceinline__ void st_fe(const MVec& v, size_t i, const fe8& r) {
                : "memory");
 }
 
+// L2 eviction priorities for the Beaver kernels: operands that are read exactly once (triples, x, y) are marked evict-first and
+// the masks K1 writes evict-last, so that what K2 reads back a moment later — the four d / e planes, 128 MB per 2^20-gate
+// two-party step against a 126 MB L2 — is less likely to have been pushed out by the streams.
+__device__ __forceinline__ void ld_fe_stream(fe8& r, const Vec& v, size_t i) {
+  const char* a = v.p + i * (size_t)v.stride;
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(a)
+               : "memory");
+}
+__device__ __forceinline__ void st_fe_keep(const MVec& v, size_t i, const fe8& r) {
+  char* a = v.p + i * (size_t)v.stride;
+  asm volatile("st.global.L1::no_allocate.L2::evict_last.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+               :
+               : "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]), "l"(a)
+               : "memory");
+}
+
 constexpr int kBlock = 256;
 
 // Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
@@ -62,18 +80,23 @@ __device__ __forceinline__ void pdl_epilogue(bool independent) {
 // Beaver phase 1: d_mine = x - a, e_mine = y - b on the share components.   192 B / gate.
 // ---------------------------------------------------------------------------------------------
 template <class F>
-__global__ void __launch_bounds__(kBlock) beaver_mask_kernel(size_t n, Vec x, Vec y, Vec a, Vec b, MVec d, MVec e, int independent) {
+__global__ void __launch_bounds__(kBlock) beaver_mask_kernel(size_t n, Vec x, Vec y, Vec a, Vec b, MVec d, MVec e, int independent, int keep) {
   pdl_prologue(independent != 0);
   const size_t step = (size_t)gridDim.x * kBlock;
   for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) {
     fe8 xs, ys, as, bs, dm, em;
-    ld_fe(xs, x, i);
-    ld_fe(ys, y, i);
-    ld_fe(as, a, i);
-    ld_fe(bs, b, i);
+    ld_fe_stream(xs, x, i);
+    ld_fe_stream(ys, y, i);
+    ld_fe_stream(as, a, i);
+    ld_fe_stream(bs, b, i);
     beaver_mask_elem<F>(dm, em, xs, ys, as, bs);
-    st_fe(d, i, dm);
-    st_fe(e, i, em);
+    if (keep) {
+      st_fe_keep(d, i, dm);
+      st_fe_keep(e, i, em);
+    } else {
+      st_fe(d, i, dm);
+      st_fe(e, i, em);
+    }
   }
   pdl_epilogue(independent != 0);
 }
@@ -106,12 +129,12 @@ __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_
     ld_fe(dp, g.d_peer, i);
     ld_fe(em, g.e_mine, i);
     ld_fe(ep, g.e_peer, i);
-    ld_fe(bs, g.b_s, i);
-    ld_fe(as, g.a_s, i);
-    ld_fe(bm, g.b_m, i);
-    ld_fe(am, g.a_m, i);
-    ld_fe(cs, g.c_s, i);
-    ld_fe(cm, g.c_m, i);
+    ld_fe_stream(bs, g.b_s, i);
+    ld_fe_stream(as, g.a_s, i);
+    ld_fe_stream(bm, g.b_m, i);
+    ld_fe_stream(am, g.a_m, i);
+    ld_fe_stream(cs, g.c_s, i);
+    ld_fe_stream(cm, g.c_m, i);
     fe8 os, om, d, e;
     beaver_recombine_elem<F>(os, om, d, e, PARTY, g.key, dm, em, dp, ep, as, am, bs, bm, cs, cm);
     st_fe(g.out_s, i, os);
@@ -148,12 +171,12 @@ __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_
     ld_fe(dp, g.d_peer, i);
     ld_fe(em, g.e_mine, i);
     ld_fe(ep, g.e_peer, i);
-    ld_fe(bs, g.b_s, i);
-    ld_fe(as, g.a_s, i);
-    ld_fe(bm, g.b_m, i);
-    ld_fe(am, g.a_m, i);
-    ld_fe(cs, g.c_s, i);
-    ld_fe(cm, g.c_m, i);
+    ld_fe_stream(bs, g.b_s, i);
+    ld_fe_stream(as, g.a_s, i);
+    ld_fe_stream(bm, g.b_m, i);
+    ld_fe_stream(am, g.a_m, i);
+    ld_fe_stream(cs, g.c_s, i);
+    ld_fe_stream(cm, g.c_m, i);
     fe8 os, om, d, e;
     beaver_recombine_elem<F>(os, om, d, e, PARTY, g.key, dm, em, dp, ep, as, am, bs, bm, cs, cm);
     st_fe(g.out_s, i, os);
@@ -201,12 +224,12 @@ __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_
     ld_fe(dp, g.d_peer, i);
     ld_fe(em, g.e_mine, i);
     ld_fe(ep, g.e_peer, i);
-    ld_fe(bs, g.b_s, i);
-    ld_fe(as, g.a_s, i);
-    ld_fe(bm, g.b_m, i);
-    ld_fe(am, g.a_m, i);
-    ld_fe(cs, g.c_s, i);
-    ld_fe(cm, g.c_m, i);
+    ld_fe_stream(bs, g.b_s, i);
+    ld_fe_stream(as, g.a_s, i);
+    ld_fe_stream(bm, g.b_m, i);
+    ld_fe_stream(am, g.a_m, i);
+    ld_fe_stream(cs, g.c_s, i);
+    ld_fe_stream(cm, g.c_m, i);
     fe8 os, om, d, e;
     beaver_recombine_elem<F>(os, om, d, e, PARTY, g.key, dm, em, dp, ep, as, am, bs, bm, cs, cm);
     st_fe(g.out_s, i, os);
@@ -569,12 +592,12 @@ __global__ void __launch_bounds__(kBlock, kRecombineMinBlocks) beaver_recombine_
     ld_fe(dp, g.d_peer, i);
     ld_fe(em, g.e_mine, i);
     ld_fe(ep, g.e_peer, i);
-    ld_fe(bs, g.b_s, i);
-    ld_fe(as, g.a_s, i);
-    ld_fe(bm, g.b_m, i);
-    ld_fe(am, g.a_m, i);
-    ld_fe(cs, g.c_s, i);
-    ld_fe(cm, g.c_m, i);
+    ld_fe_stream(bs, g.b_s, i);
+    ld_fe_stream(as, g.a_s, i);
+    ld_fe_stream(bm, g.b_m, i);
+    ld_fe_stream(am, g.a_m, i);
+    ld_fe_stream(cs, g.c_s, i);
+    ld_fe_stream(cm, g.c_m, i);
     fe8 os, om, d, e, r;
     beaver_recombine_elem<F>(os, om, d, e, PARTY, g.key, dm, em, dp, ep, as, am, bs, bm, cs, cm);
     Fp<F>::add(r, acc_s, os);
