@@ -19,7 +19,7 @@
 
 namespace arkctx {
 constexpr int kSlots = 3;                 // chunk pipeline depth of the host-buffer path
-constexpr size_t kChunkElems = 1u << 18;  // elements per staged chunk (tools/e2e_sweep.sh: 2^16 17.6 ms, 2^18 16.6 ms per 2^20-gate step)
+constexpr size_t kChunkElems = 1u << 19;  // elements per staged chunk (per 2^20-gate two-party step: 2^17 17.1 ms, 2^18 16.5 ms, 2^19 16.2 ms, 2^20 16.6 ms; profiles/r02z18_summary.txt)
 constexpr int kMaxPartialBlocks = 1024;
 constexpr int kNumCurves = 2;
 }  // namespace arkctx
