@@ -472,3 +472,36 @@ def test_small_host_to_device_copies_are_staged_and_release_the_source():
         assert np.array_equal(devbuf.cpu().numpy(), want)
     finally:
         lib.arkmpc_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("share_planes", [False, True])
+def test_host_buffer_batch_mul_many_chunks(monkeypatch, share_planes):
+    """The host path's chunk pipeline with a small staging chunk (2^12 gates: a dozen chunks over three slots, ragged last one),
+    so that slot reuse and the chunk boundaries are exercised at a size the oracle finishes quickly."""
+    from ark_mpc_b200.engine import Engine
+
+    monkeypatch.setenv("ARKMPC_CHUNK_LOG2", "12")
+    E = Engine(0, FIELD_NAME[0])  # the chunk size is read when the context is created
+    try:
+        n = 12 * 4096 + 777
+        D = TwoPartyData(0, n, seed=99)
+        o0, o1, d_open, e_open = D.oracle_batch_mul()
+        sess, de = [], []
+        for p in (0, 1):
+            P = D.party(p)
+            de_mine = np.empty((2 * n, 4), dtype=np.uint64)
+            if share_planes:
+                sess.append(E.batch_mul_begin_host_shares(p, P["key"], np.ascontiguousarray(P["x"][0]), np.ascontiguousarray(P["y"][0]),
+                                                          aos(*P["a"]), aos(*P["b"]), aos(*P["c"]), de_mine))
+            else:
+                sess.append(E.batch_mul_begin_host(p, P["key"], aos(*P["x"]), aos(*P["y"]), aos(*P["a"]), aos(*P["b"]), aos(*P["c"]), de_mine))
+            de.append(de_mine)
+        for p, want in ((0, o0), (1, o1)):
+            out = np.empty((n, 8), dtype=np.uint64)
+            de_open = np.empty((2 * n, 4), dtype=np.uint64) if p == 0 else None
+            E.batch_mul_finish_host(sess[p], de[1 - p], out, de_open)
+            assert np.array_equal(out, want)
+            if de_open is not None:
+                assert np.array_equal(de_open[:n], d_open) and np.array_equal(de_open[n:], e_open)
+    finally:
+        E.close()
