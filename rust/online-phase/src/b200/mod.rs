@@ -113,6 +113,20 @@ impl B200Context {
     pub fn hint_independent(&self) {
         unsafe { sys::arkmpc_ctx_hint_independent(self.raw) };
     }
+
+    /// Return the device blocks `DevBuf` drops have parked in the library's cache to the driver (synchronises the device)
+    pub fn mem_trim(&self) {
+        let rc = unsafe { sys::arkmpc_mem_trim(self.raw) };
+        self.check(rc, "arkmpc_mem_trim");
+    }
+
+    /// Bytes currently parked in the cache of free device blocks
+    pub fn mem_cached_bytes(&self) -> usize {
+        let mut bytes: usize = 0;
+        let rc = unsafe { sys::arkmpc_mem_cached_bytes(self.raw, &mut bytes) };
+        self.check(rc, "arkmpc_mem_cached_bytes");
+        bytes
+    }
 }
 
 impl Drop for B200Context {
@@ -121,7 +135,9 @@ impl Drop for B200Context {
     }
 }
 
-/// A device allocation, freed on drop
+/// A device allocation, freed on drop.  `arkmpc_free` parks the block in a per-device cache and orders its reuse on the device
+/// after the work already submitted to every live context's stream, so dropping a buffer never synchronises the host — the
+/// allocation pattern of one `ResultValue` per gate result stays cheap (include/arkmpc_b200.h, "memory").
 pub struct DevBuf {
     ctx: Arc<B200Context>,
     ptr: *mut c_void,
