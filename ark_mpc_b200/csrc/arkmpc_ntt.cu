@@ -9,6 +9,24 @@ using namespace arkctx;
 
 namespace {
 
+// Launch a kernel of a dependent chain (inversion tree, NTT passes) with the programmatic-stream-serialization attribute: its
+// blocks may become resident while the previous kernel of the chain drains; every such kernel starts with pdl_prologue(), i.e.
+// waits for its predecessor's completion and memory flush before it touches anything (fr_ntt.cuh).
+template <class... KArgs, class... Args>
+void launch_chain(const arkmpc_ctx* ctx, void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, args...);  // errors surface through cudaGetLastError in post_launch
+}
+
 template <class F> struct FieldTag { using type = F; };
 constexpr bool kMulKaraDefault = false;
 
@@ -74,7 +92,7 @@ int ntt_plane(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t
   static const int tile_threads = [] { const char* e = getenv("ARKMPC_NTT_TILE_THREADS"); const int v = e ? atoi(e) : 0; return v == 128 || v == 256 ? v : kNttThreads; }();
   static const int stride_threads = [] { const char* e = getenv("ARKMPC_NTT_STRIDE_THREADS"); const int v = e ? atoi(e) : 0; return v == 128 || v == 256 || v == 512 ? v : 0; }();
   const bool fold_scale = inverse && log2n >= 2;  // n^-1 rides on the first double stage of the tile kernel
-  fr_ntt_tile_kernel<F, K><<<(unsigned)tiles, tile_threads, ((size_t)32 << tile_log), ctx->stream>>>(log2n, vec(in), vec(tw), fold_scale ? consts + 1 : nullptr, mvec(out));
+  launch_chain(ctx, fr_ntt_tile_kernel<F, K>, (unsigned)tiles, (unsigned)tile_threads, ((size_t)32 << tile_log), ctx->stream, log2n, vec(in), vec(tw), fold_scale ? consts + 1 : (const fe8*)nullptr, mvec(out));
   rc = post_launch(ctx, "fr_ntt_tile_kernel");
   const int rest = log2n > kNttTileLog ? log2n - kNttTileLog : 0;
   int passes = (rest + kNttStrideLog - 1) / kNttStrideLog;
@@ -86,7 +104,7 @@ int ntt_plane(arkmpc_ctx* ctx, int field, int log2n, int inverse, const uint64_t
     // profiles/r02u_summary.txt); small ones keep one butterfly per thread, where the latency of a level is what counts
     const int one_each = 32 << (T - 1);  // one butterfly per thread per level
     const int threads = stride_threads ? stride_threads : (log2n >= 19 && one_each >= 64 ? one_each / 2 : one_each);
-    fr_ntt_strided_kernel<F, K><<<(unsigned)blocks, threads, 0, ctx->stream>>>(log2n, s0, T, vec(tw), mvec(out));
+    launch_chain(ctx, fr_ntt_strided_kernel<F, K>, (unsigned)blocks, (unsigned)threads, 0, ctx->stream, log2n, s0, T, vec(tw), mvec(out));
     rc = post_launch(ctx, "fr_ntt_strided_kernel");
     s0 += T;
   }
@@ -155,20 +173,22 @@ int arkmpc_fr_batch_inverse(arkmpc_ctx* ctx, int field, size_t n, const uint64_t
     auto coop_blocks = [](size_t groups) { return (unsigned)((groups + kInvCoopGroups - 1) / kInvCoopGroups); };
     for (int l = 0; l < levels && rc == ARKMPC_OK; l++) {
       if (coop(sizes[l + 1]))
-        fr_inv_up_coop_kernel<F, K><<<coop_blocks(sizes[l + 1]), kInvCoopBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
+        launch_chain(ctx, fr_inv_up_coop_kernel<F, K>, coop_blocks(sizes[l + 1]), (unsigned)kInvCoopBlock, 0, s, sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
       else
-        fr_inv_up_kernel<F, K><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
+        launch_chain(ctx, fr_inv_up_kernel<F, K>, blocks(sizes[l + 1]), (unsigned)inv_block, 0, s, sizes[l], sizes[l + 1], vec(xs[l]), mvec(tree[l]), mvec(const_cast<char*>(xs[l + 1])));
       rc = post_launch(ctx, "fr_inv_up_kernel");
     }
     if (rc == ARKMPC_OK) {
+      // a plain launch: placed while its predecessor still holds the SMs, the single-warp blocks land unevenly and the inversions,
+      // which want one warp per scheduler, take longer (2^20: 105 against 95 us for the whole inversion, profiles/r02z20_summary.txt)
       fr_inv_top_kernel<F><<<(unsigned)((sizes[levels] + kInvTopBlock - 1) / kInvTopBlock), kInvTopBlock, 0, s>>>(sizes[levels], vec(xs[levels]), mvec(inv[levels]));
       rc = post_launch(ctx, "fr_inv_top_kernel");
     }
     for (int l = levels - 1; l >= 0 && rc == ARKMPC_OK; l--) {
       if (coop(sizes[l + 1]))
-        fr_inv_down_coop_kernel<F, K><<<coop_blocks(sizes[l + 1]), kInvCoopBlock, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
+        launch_chain(ctx, fr_inv_down_coop_kernel<F, K>, coop_blocks(sizes[l + 1]), (unsigned)kInvCoopBlock, 0, s, sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
       else
-        fr_inv_down_kernel<F, K><<<blocks(sizes[l + 1]), inv_block, 0, s>>>(sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
+        launch_chain(ctx, fr_inv_down_kernel<F, K>, blocks(sizes[l + 1]), (unsigned)inv_block, 0, s, sizes[l], sizes[l + 1], vec(xs[l]), vec(tree[l]), vec(inv[l + 1]), mvec(inv[l]));
       rc = post_launch(ctx, "fr_inv_down_kernel");
     }
     return rc;

@@ -57,6 +57,7 @@ __device__ __forceinline__ uint32_t inv_load_group(fe8 (&z)[kInvGroup], size_t n
 
 template <class F, bool K>
 __global__ void __launch_bounds__(kInvBlock) fr_inv_up_kernel(size_t n, size_t groups, Vec x, MVec tree, MVec prod) {
+  pdl_prologue();  // launched with programmatic stream serialization: wait for the previous kernel of the chain, release the next
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= groups) return;
   fe8 z[kInvGroup];
@@ -99,6 +100,7 @@ __device__ __forceinline__ uint32_t inv_load_pair(fe8& z0, fe8& z1, size_t n, si
 
 template <class F, bool K>
 __global__ void __launch_bounds__(kInvCoopBlock) fr_inv_up_coop_kernel(size_t n, size_t groups, Vec x, MVec tree, MVec prod) {
+  pdl_prologue();  // launched with programmatic stream serialization: wait for the previous kernel of the chain, release the next
   __shared__ __align__(32) fe8 sp[4][kInvCoopGroups];
   __shared__ __align__(32) fe8 sq[2][kInvCoopGroups];
   const int k = threadIdx.x / kInvCoopGroups, gl = threadIdx.x % kInvCoopGroups;
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(kInvCoopBlock) fr_inv_up_coop_kernel(size_t n,
 
 template <class F, bool K>
 __global__ void __launch_bounds__(kInvCoopBlock) fr_inv_down_coop_kernel(size_t n, size_t groups, Vec x, Vec tree, Vec ginv, MVec out) {
+  pdl_prologue();  // launched with programmatic stream serialization: wait for the previous kernel of the chain, release the next
   __shared__ __align__(32) fe8 siq[2][kInvCoopGroups];
   const int k = threadIdx.x / kInvCoopGroups, gl = threadIdx.x % kInvCoopGroups;
   const size_t g = (size_t)blockIdx.x * kInvCoopGroups + gl;
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(kInvCoopBlock) fr_inv_down_coop_kernel(size_t 
 constexpr int kInvTopBlock = 32;
 template <class F>
 __global__ void __launch_bounds__(kInvTopBlock) fr_inv_top_kernel(size_t n, Vec x, MVec out) {
+  pdl_prologue();  // launched with programmatic stream serialization: wait for the previous kernel of the chain, release the next
   const size_t i = (size_t)blockIdx.x * kInvTopBlock + threadIdx.x;
   if (i >= n) return;
   fe8 v, r;
@@ -178,6 +182,7 @@ __global__ void __launch_bounds__(kInvTopBlock) fr_inv_top_kernel(size_t n, Vec 
 
 template <class F, bool K>
 __global__ void __launch_bounds__(kInvBlock) fr_inv_down_kernel(size_t n, size_t groups, Vec x, Vec tree, Vec ginv, MVec out) {
+  pdl_prologue();  // launched with programmatic stream serialization: wait for the previous kernel of the chain, release the next
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= groups) return;
   fe8 z[kInvGroup], p[4], q[2], inv;
@@ -288,6 +293,7 @@ __device__ __forceinline__ void ntt_butterfly(fe8& lo, fe8& hi, const fe8& w) {
 // multiplications per four elements) instead of a separate pass over the data.
 template <class F, bool K>
 __global__ void __launch_bounds__(kNttThreads) fr_ntt_tile_kernel(int log2n, Vec in, Vec tw, const fe8* __restrict__ scale, MVec out) {
+  pdl_prologue();  // launched with programmatic stream serialization: wait for the previous kernel of the chain, release the next
   extern __shared__ __align__(32) unsigned char ntt_smem[];
   __shared__ __align__(32) fe8 stw[kNttTile / 2];  // stw[k] = w^(k n / 2^tile_log)
   fe8* x = reinterpret_cast<fe8*>(ntt_smem);
@@ -374,6 +380,7 @@ constexpr int kNttStrideThreads = 32 << (kNttStrideLog - 1);  // 512
 
 template <class F, bool K>
 __global__ void __launch_bounds__(kNttStrideThreads) fr_ntt_strided_kernel(int log2n, int s0, int T, Vec tw, MVec x) {
+  pdl_prologue();  // launched with programmatic stream serialization: wait for the previous kernel of the chain, release the next
   __shared__ __align__(32) fe8 sm[32 << kNttStrideLog];  // [k][lo]
   const int lane = threadIdx.x & 31;
   const int row = threadIdx.x >> 5;                       // 0 .. 15
